@@ -1,0 +1,203 @@
+/*
+ * decipher_b200.h — C ABI of the B200-native DECIPHeR Monte-Carlo rainfall-runoff path.
+ *
+ * This is the drop-in boundary.  The reference has no FFI layer; the seam it offers is the
+ * Fortran call
+ *
+ *     call mainloop(all_pm_names, nac, nstep, num_rivers, acc, dt, dtt, dyna_hru, mcpar, ntt,
+ *                   node_to_flow_mapping, num_par_types, pe_step, qobs_riv_step_start,
+ *                   r_gau_step, rivers, route_riv, route_tdh, sum_ac_riv, wt)
+ *
+ * made once per ensemble member from the serial loop in RRMODEL/dyna_main.f90:166-206
+ * (definition RRMODEL/dyna_main_loop.f90:9-28).  The functions below replace that loop body
+ * for ALL members at once: the caller samples every parameter set first (genpar,
+ * RRMODEL/dyna_genpar.f90:35-41), then makes ONE dcp_run_ensemble call.
+ *
+ * Conventions (chosen so that a Fortran `bind(C)` interface is 1:1):
+ *   - plain C, no exceptions cross the boundary, int32_t / int64_t / double / opaque handles only;
+ *   - every array is contiguous and laid out exactly as the Fortran reference stores it
+ *     (column-major, first index fastest);
+ *   - every index stored IN an array (itrans, ipar, ipriv, ippt, ipet, upstream tree, mapping)
+ *     stays 1-based as in the reference files;
+ *   - the library copies what it needs at create time; the caller may free its buffers after
+ *     dcp_catchment_create returns;
+ *   - return value 0 = DCP_OK, anything else is an error code and dcp_last_error() describes it;
+ *   - there is no CPU fallback and no backend dispatch: without a CUDA device every compute
+ *     entry point returns DCP_ERR_NO_DEVICE.
+ */
+#ifndef DECIPHER_B200_H
+#define DECIPHER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DCP_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------- */
+#define DCP_OK               0
+#define DCP_ERR_INVALID      1   /* bad argument / inconsistent descriptor                      */
+#define DCP_ERR_NO_DEVICE    2   /* no CUDA device, or the device is not sm_100                 */
+#define DCP_ERR_CUDA         3   /* a CUDA runtime call failed (message holds cudaGetErrorString) */
+#define DCP_ERR_NOMEM        4   /* host or device allocation failed                            */
+#define DCP_ERR_UNSUPPORTED  5   /* a reference feature this build does not implement           */
+
+/* ---- per-member status word (dcp_run_ensemble: status[]) ---------------------------------
+ * The reference STOPs the whole process on these conditions; the ensemble path records them
+ * per member instead and keeps going.                                                         */
+#define DCP_ST_SOLFLAG_MASK   0x3       /* init_satzone sol_flag 0/1/2 (dyna_init_satzone.f90:120-186) */
+#define DCP_ST_RZ_BALANCE     0x4       /* root-zone store balance STOP (dyna_root_zone1.f90:73-77)   */
+#define DCP_ST_TS_OUTSUM      0x8       /* output-sum STOP (dyna_results_ts.f90:88-93)                */
+#define DCP_ST_TS_WBAL        0x10      /* water-balance STOP (dyna_results_ts.f90:95-101)            */
+#define DCP_ST_NONFINITE      0x20      /* a routed flow of this member is inf/NaN                    */
+#define DCP_ST_INIT_ITERCAP   0x40      /* init search hit DCP_INIT_MAX_ITER (guard, not in reference)*/
+#define DCP_ST_HIST_DROPPED   0x80      /* hist_add_value dropped a cell (dta_route_processing.f90:378-382) */
+
+#define DCP_INIT_MAX_ITER     20000     /* cap on the while loop of dyna_init_satzone.f90:134-174     */
+
+/* ---- run option flags -------------------------------------------------------------------- */
+#define DCP_OPT_CHECK_BALANCE   0x1     /* evaluate the results_ts / root_zone1 STOP conditions       */
+#define DCP_OPT_DEVICE_BUFFERS  0x2     /* mcpar / outputs are DEVICE pointers (no H2D/D2H copies)    */
+#define DCP_OPT_FAST_MATH       0x4     /* reciprocal-hoisted arithmetic (<=1e-9 rel.; default is the
+                                           reference's operation order with IEEE division)            */
+
+/* kernel selector (dcp_run_opts.kernel) */
+#define DCP_KERNEL_AUTO      0
+#define DCP_KERNEL_STREAMED  1          /* state streamed through L2/HBM, any nac                     */
+#define DCP_KERNEL_RESIDENT  2          /* persistent kernel, state on chip for the whole simulation  */
+
+/* number of performance measures per (gauge, member): 1 = NSE, 2 = log-NSE */
+#define DCP_NMEASURE 2
+
+/*
+ * Static description of one catchment: everything the reference holds after
+ * Tread_dyna / Inputs / modelstruct_setup / read_routingdata have run
+ * (RRMODEL/dyna_main.f90:95-160), flattened out of its derived types.
+ */
+typedef struct dcp_catchment_desc {
+    int32_t struct_size;        /* sizeof(dcp_catchment_desc), for ABI checking                       */
+    int32_t nac;                /* number of HRUs                 (dyna_tread_dyna.f90:47)            */
+    int32_t nriv;               /* num_rivers                     (dyna_tread_dyna.f90:115)           */
+    int32_t npt;                /* num_par_types                  (dyna_mc_setup.f90:84)              */
+    int32_t nstep;              /* timesteps of rain/PET          (dyna_inputs.f90:166-169)           */
+    int32_t ngp;                /* rain gauges / grid ids         (dyna_inputs.f90:126)               */
+    int32_t nge;                /* PET gauges / grid ids          (dyna_inputs.f90:148)               */
+    int32_t ntt;                /* inner sub-steps NTT            (dyna_mc_setup.f90:83)              */
+    double  dt;                 /* timestep length                (dyna_inputs.f90:148)               */
+
+    /* per-HRU static data, all [nac] (dyna_common_types.f90:22-44) */
+    const double  *ac;          /* fractional area, after the renormalisation of dyna_tread_dyna.f90:186-190 */
+    const double  *st;          /* mean topographic index                                            */
+    const double  *mslp;        /* mean slope (radians)                                              */
+    const int32_t *ippt;        /* 1-based rain column                                               */
+    const int32_t *ipet;        /* 1-based PET column                                                */
+    const int32_t *ipar;        /* 1-based parameter layer                                           */
+    const int32_t *ipriv;       /* 1-based river the HRU's overland flow drains to                   */
+    const int32_t *ims_rz;      /* root-zone structure id (only 1 exists, dyna_topmod.f90:146)       */
+    const int32_t *ims_uz;      /* unsat-zone structure id (only 1 exists, dyna_topmod.f90:161)      */
+
+    /* HRU->HRU flux weights as read by dyna_tread_dyna.f90:133-148 (after :173-184) */
+    const int32_t *ntrans;      /* [nac]                                                             */
+    const int32_t *itrans;      /* [sum(ntrans)]   1-based target HRUs, HRU after HRU                */
+    const double  *wtrans;      /* [sum(ntrans+1)] weights, the river weight LAST for each HRU       */
+    const double  *rivers;      /* [nac x nriv] column-major, share of HRU ia going to river iriv    */
+    const double  *sum_ac_riv;  /* [nriv]  (dyna_tread_dyna.f90:166-167,192-194)                     */
+    const double  *qobs_start;  /* [nriv]  qobs_riv_step_start (dyna_inputs.f90:84-113)              */
+
+    /* river network (route_river_info_type, DTA/dta_route_processing.f90:10-27) */
+    int32_t nnode;              /* size(node_list)                                                   */
+    int32_t ncell;              /* rows of river_data                                                */
+    const int32_t *node_gauge_id;   /* [nnode]                                                       */
+    const int32_t *node_type;       /* [nnode] 1 sea, 2 gauge, 3 river                               */
+    const int32_t *uptree_count;    /* [nnode] upstream_tree_count                                   */
+    const int32_t *uptree_index;    /* [sum(uptree_count)] 1-based node indexes in the order produced
+                                       by riv_node_full_upstream (DTA/dta_riv_tree_node.f90:80-110)  */
+    const double  *frac_sub_area;   /* [nnode] (dyna_read_routingdata.f90:52-89)                     */
+    const double  *river_data;      /* [ncell x 8] column-major: riv_id, area, dist, section_dist,
+                                       elevation, slope, ds_dist, ds_elevation                       */
+    const int32_t *node_to_flow_mapping; /* [nriv] 1-based (dyna_read_routingdata.f90:100-102)       */
+
+    /* forcing (dyna_inputs.f90:117-160), gauge index fastest */
+    const double  *rain;        /* r_gau_step [ngp x nstep]                                          */
+    const double  *pet;         /* pe_step    [nge x nstep]                                          */
+
+    /* observed flow, optional (NULL: no performance measures).  The reference reads and drops it
+       (dyna_inputs.f90:31,78,90); it is used only by the NSE / log-NSE extension. */
+    const double  *qobs;        /* [nriv x nstep_obs]                                                */
+    int32_t nstep_obs;
+    int32_t t_warm;             /* steps 1..t_warm are excluded from the performance measures        */
+    double  flow_err;           /* missing-data code of the flow file (dyna_inputs.f90:57)           */
+} dcp_catchment_desc;
+
+typedef struct dcp_run_opts {
+    int32_t struct_size;        /* sizeof(dcp_run_opts)                                              */
+    int32_t flags;              /* DCP_OPT_*                                                         */
+    int32_t kernel;             /* DCP_KERNEL_*                                                      */
+    int32_t members_per_batch;  /* 0 = library chooses                                               */
+    int32_t steps_per_tile;     /* 0 = library chooses (time tile of the flow ring buffer)           */
+    int32_t reserved;
+} dcp_run_opts;
+
+/* timing of the last dcp_run_ensemble call on this handle, CUDA events on the library's stream */
+typedef struct dcp_run_stats {
+    double ms_total;            /* first kernel start -> last kernel end                              */
+    double ms_init;             /* init_satzone + build_hist kernel                                   */
+    double ms_physics;          /* time-loop kernel(s)                                                */
+    double ms_route;            /* routing / objective kernel(s)                                      */
+    double ms_h2d;              /* host->device copies inside the call                                */
+    double ms_d2h;              /* device->host copies inside the call                                */
+    int64_t n_physics_launches;
+    int64_t n_launches;         /* all kernels launched by the call                                   */
+    int32_t kernel_used;        /* DCP_KERNEL_STREAMED or DCP_KERNEL_RESIDENT                         */
+    int32_t hist_len;           /* T of route_processing_build_hist for the slowest member            */
+} dcp_run_stats;
+
+typedef struct dcp_catchment dcp_catchment;   /* opaque; one handle per (host thread, GPU)            */
+
+/* Device management.  dcp_device_count() returns 0 without a usable GPU (never an error). */
+int  dcp_device_count(void);
+int  dcp_set_device(int device);
+int  dcp_abi_version(void);
+const char *dcp_last_error(void);            /* thread-local, valid until the next call              */
+
+/* Replaces the state the reference builds in RRMODEL/dyna_main.f90:95-160 and keeps alive
+   across the MC loop.  Validates the descriptor and copies it to the current device. */
+int  dcp_catchment_create(const dcp_catchment_desc *desc, dcp_catchment **out);
+int  dcp_catchment_destroy(dcp_catchment *c);
+
+/*
+ * Replaces the body of `do i_mc = 1, numsim` (RRMODEL/dyna_main.f90:166-206) for members
+ * first_member .. first_member+n_member-1 (first_member is informational: the caller passes
+ * the parameter sets of exactly these members).
+ *
+ *   mcpar         [npt x 7 x n_member]  in/out — column order szm, lnto, srmax, srinit, chv, td, smax
+ *                 (dyna_param_setup.f90:58-70); srinit is clipped to srmax on return exactly as
+ *                 dyna_init_satzone.f90:203-206 rewrites mcpar(ipar,4).
+ *   q_out         [nriv x nstep x n_member] or NULL — routed flow q(iriv,it) in m/timestep
+ *                 (dyna_river.f90:57-59), the numbers write_output prints to the .flow file.
+ *   perf_out      [DCP_NMEASURE x nriv x n_member] or NULL — NSE, log-NSE (extension).
+ *   reach_totals  [3 x nriv x n_member] or NULL — precip, PET, actual-ET totals per reach in mm
+ *                 (dyna_write_output.f90:61-77).
+ *   init_diag     [3 x n_member] or NULL — mean_q_ac_weighted, qb_tmp, mean_q_ac_weighted_guess
+ *                 (m/timestep; dyna_init_satzone.f90:188-190 prints them x1000).
+ *   status        [n_member] or NULL — DCP_ST_* bit flags.
+ *
+ * Synchronous: all outputs are complete on return.
+ */
+int  dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member,
+                      double *mcpar, const dcp_run_opts *opts,
+                      double *q_out, double *perf_out, double *reach_totals,
+                      double *init_diag, int32_t *status);
+
+int  dcp_get_run_stats(const dcp_catchment *c, dcp_run_stats *out);
+
+/* Standalone FP64 pipe micro-benchmark (dependency-free DFMA chains) used as the roofline
+   denominator; returns TFLOP/s (2 flops per DFMA) in *tflops. */
+int  dcp_measure_fp64_peak(double *tflops, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DECIPHER_B200_H */
