@@ -1,0 +1,572 @@
+// dcp_api.cu — host side of the C ABI (include/decipher_b200.h).
+//
+// dcp_catchment_create flattens the descriptor into device structures once (the state the reference
+// keeps alive across its MC loop, RRMODEL/dyna_main.f90:95-160); dcp_run_ensemble replaces the loop
+// body for all members: batches of members, each batch = init kernel, then time tiles of
+// {physics, routing convolution, gauge summation + objective}, then the finalize kernel.
+// No CPU compute path exists here: without a device every entry point fails.
+#include "dcp_kernels.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <string>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_err;
+
+int fail(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t e_ = (expr);                                                                \
+        if (e_ != cudaSuccess)                                                                  \
+            return fail(e_ == cudaErrorMemoryAllocation ? DCP_ERR_NOMEM : DCP_ERR_CUDA,         \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+struct DevBuf {                     // growable device allocation
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, bytes);
+        if (e == cudaSuccess) cap = bytes;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+template <class T>
+cudaError_t upload(const std::vector<T> &v, const T **dst, std::vector<void *> &owned) {
+    void *p = nullptr;
+    const size_t bytes = std::max<size_t>(v.size(), 1) * sizeof(T);
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+    owned.push_back(p);
+    if (!v.empty()) e = cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice);
+    *dst = (const T *)p;
+    return e;
+}
+
+}  // namespace
+
+struct dcp_catchment {
+    int device = 0;
+    DevCatchment C{};
+    std::vector<void *> owned;          // static device arrays
+    DevBuf ws;                          // per-batch workspace (one slab)
+    DevBuf io;                          // staging for host<->device outputs
+    cudaStream_t stream = nullptr;
+    // host copies needed at run time
+    std::vector<double> node_reach_dist, node_down_dist;
+    bool has_qobs = false;
+    dcp_run_stats stats{};
+};
+
+extern "C" {
+
+int dcp_abi_version(void) { return DCP_ABI_VERSION; }
+
+const char *dcp_last_error(void) { return g_err.c_str(); }
+
+int dcp_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int dcp_set_device(int device) {
+    CUDA_TRY(cudaSetDevice(device));
+    return DCP_OK;
+}
+
+int dcp_catchment_destroy(dcp_catchment *c) {
+    if (!c) return DCP_OK;
+    cudaSetDevice(c->device);
+    for (void *p : c->owned) cudaFree(p);
+    c->ws.release();
+    c->io.release();
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+    return DCP_OK;
+}
+
+int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
+    if (!d || !out) return fail(DCP_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->struct_size != (int)sizeof(dcp_catchment_desc))
+        return fail(DCP_ERR_INVALID, "dcp_catchment_desc.struct_size %d != %d (ABI mismatch)", d->struct_size,
+                    (int)sizeof(dcp_catchment_desc));
+    if (dcp_device_count() < 1) return fail(DCP_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    const int nac = d->nac, nriv = d->nriv, npt = d->npt, nnode = d->nnode, ncell = d->ncell;
+    if (nac < 1 || nriv < 1 || npt < 1 || d->nstep < 1 || d->ngp < 1 || d->nge < 1 || d->ntt < 1 || !(d->dt > 0))
+        return fail(DCP_ERR_INVALID, "non-positive dimension or dt");
+    if (nnode < nriv || ncell < 1) return fail(DCP_ERR_INVALID, "routing: nnode (%d) < nriv (%d) or no river cells", nnode, nriv);
+    if (!d->ac || !d->st || !d->mslp || !d->ippt || !d->ipet || !d->ipar || !d->ipriv || !d->ims_rz || !d->ims_uz ||
+        !d->ntrans || !d->wtrans || !d->rivers || !d->sum_ac_riv || !d->qobs_start || !d->node_gauge_id ||
+        !d->node_type || !d->uptree_count || !d->frac_sub_area || !d->river_data || !d->node_to_flow_mapping ||
+        !d->rain || !d->pet)
+        return fail(DCP_ERR_INVALID, "null array in descriptor");
+
+    // ---------------- validate + flatten on the host ----------------
+    std::vector<HruStatic> hru(nac);
+    std::vector<std::vector<WEntry>> rows(nac);
+    std::vector<RivEntry> riv;
+    std::vector<uint8_t> layer_used(npt, 0);
+    size_t tro = 0, wo = 0;
+    for (int ia = 0; ia < nac; ++ia) {
+        HruStatic &h = hru[ia];
+        std::memset(&h, 0, sizeof(h));
+        h.ac = d->ac[ia]; h.st = d->st[ia]; h.cosm = std::cos(d->mslp[ia]);
+        h.ippt = d->ippt[ia] - 1; h.ipet = d->ipet[ia] - 1; h.ipar = d->ipar[ia] - 1; h.ipriv = d->ipriv[ia] - 1;
+        h.ims_rz = d->ims_rz[ia]; h.ims_uz = d->ims_uz[ia];
+        if (h.ippt < 0 || h.ippt >= d->ngp || h.ipet < 0 || h.ipet >= d->nge || h.ipar < 0 || h.ipar >= npt ||
+            h.ipriv < 0 || h.ipriv >= nriv)
+            return fail(DCP_ERR_INVALID, "HRU %d: ippt/ipet/ipar/ipriv out of range", ia + 1);
+        layer_used[h.ipar] = 1;
+        const int nt = d->ntrans[ia];
+        if (nt < 0) return fail(DCP_ERR_INVALID, "HRU %d: ntrans < 0", ia + 1);
+        if (nt > 0 && !d->itrans) return fail(DCP_ERR_INVALID, "itrans is null");
+        for (int iw = 0; iw < nt; ++iw) {
+            const int tgt = d->itrans[tro + iw] - 1;
+            if (tgt < 0 || tgt >= nac) return fail(DCP_ERR_INVALID, "HRU %d: itrans(%d) out of range", ia + 1, iw + 1);
+            WEntry e; e.w = d->wtrans[wo + iw]; e.ac_src = d->ac[ia]; e.src = ia; e.pad = 0;
+            rows[tgt].push_back(e);        // sources arrive in ascending ia, iw: the reference's scatter order
+        }
+        h.w_riv = d->wtrans[wo + nt];
+        tro += nt; wo += nt + 1;
+        h.riv_beg = (int)riv.size();
+        for (int r = 0; r < nriv; ++r) {
+            const double sh = d->rivers[(size_t)r * nac + ia];
+            if (sh != 0.0) { RivEntry e; e.share = sh; e.r = r; e.pad = 0; riv.push_back(e); }
+        }
+        h.riv_end = (int)riv.size();
+    }
+    std::vector<WEntry> w;
+    for (int ia = 0; ia < nac; ++ia) {
+        hru[ia].row_beg = (int)w.size();
+        w.insert(w.end(), rows[ia].begin(), rows[ia].end());
+        hru[ia].row_end = (int)w.size();
+    }
+
+    // river network (DTA/dta_route_processing.f90:184-243, member-independent parts)
+    int n_gauge = 0;
+    for (int n = 0; n < nnode; ++n) if (d->node_type[n] == 2) ++n_gauge;
+    if (n_gauge != nriv)   // size check of route_process_run_step (:663-668) would STOP
+        return fail(DCP_ERR_INVALID, "routing: %d gauge nodes but %d rivers (reference stops: size mismatch)", n_gauge, nriv);
+    auto rd = [&](int cell, int col) { return d->river_data[(size_t)(col - 1) * ncell + cell]; };
+    double min_outlet = rd(0, 7);
+    for (int j = 1; j < ncell; ++j) min_outlet = std::min(min_outlet, rd(j, 7));
+    std::vector<int32_t> cbeg(nnode, -1), cend(nnode, -1);
+    std::vector<double> reach_dist(nnode, 0.0), down_dist(nnode, 0.0), cell_a(ncell), cell_b(ncell), cell_area(ncell);
+    for (int n = 0; n < nnode; ++n) {
+        int s = 0, e = ncell;
+        for (int j = 1; j <= ncell; ++j) {
+            const int id = (int)std::lround(rd(j - 1, 1));
+            if (s == 0) { if (id == d->node_gauge_id[n]) s = j; }
+            else if (id != d->node_gauge_id[n]) { e = j - 1; break; }
+        }
+        if (s == 0)
+            return fail(DCP_ERR_UNSUPPORTED, "routing node %d (id %d) has no river cells (stale delays upstream, "
+                        "dta_route_processing.f90:204-212)", n + 1, d->node_gauge_id[n]);
+        cbeg[n] = s - 1; cend[n] = e;
+        double mx = rd(s - 1, 3), mn = rd(s - 1, 7);
+        for (int j = s; j <= e; ++j) { mx = std::max(mx, rd(j - 1, 3)); mn = std::min(mn, rd(j - 1, 7)); }
+        reach_dist[n] = mx - mn;
+        down_dist[n] = mn - min_outlet;
+    }
+    for (int j = 0; j < ncell; ++j) {
+        const double cell_dist = rd(j, 3) - rd(j, 7);          // :325
+        cell_a[j] = rd(j, 4);                                  // :333
+        cell_b[j] = cell_a[j] + cell_dist;                     // :334
+        cell_area[j] = rd(j, 2);
+        if (cell_a[j] < 0 || cell_b[j] < 0) return fail(DCP_ERR_INVALID, "river cell %d: negative section distance", j + 1);
+    }
+    std::vector<int32_t> node_input(nnode, -1), up_beg(nnode + 1, 0), up_idx;
+    std::vector<double> frac(nriv);
+    for (int r = 0; r < nriv; ++r) {
+        const int n = d->node_to_flow_mapping[r] - 1;
+        if (n < 0 || n >= nnode) return fail(DCP_ERR_INVALID, "node_to_flow_mapping(%d) out of range", r + 1);
+        node_input[n] = r;
+        frac[r] = d->frac_sub_area[n];
+    }
+    for (int n = 0; n < nnode; ++n) {
+        const int cnt = d->uptree_count[n];
+        if (cnt < 0 || (cnt > 0 && !d->uptree_index)) return fail(DCP_ERR_INVALID, "bad upstream tree");
+        for (int k = 0; k < cnt; ++k) {
+            const int u = d->uptree_index[up_beg[n] + k] - 1;
+            if (u < 0 || u >= nnode) return fail(DCP_ERR_INVALID, "upstream index out of range");
+            up_idx.push_back(u);
+        }
+        up_beg[n + 1] = up_beg[n] + cnt;
+    }
+
+    // member-independent reach totals (dyna_write_output.f90:61-77; sum_pptin/sum_pein of dyna_root_zone1.f90:40,63)
+    std::vector<double> sum_p(d->ngp, 0.0), sum_e(d->nge, 0.0), tot_ppt(nriv, 0.0), tot_pet(nriv, 0.0), tot_frac(nriv, 0.0);
+    for (int g = 0; g < d->ngp; ++g)
+        for (int t = 0; t < d->nstep; ++t) sum_p[g] = sum_p[g] + d->rain[(size_t)t * d->ngp + g];
+    for (int g = 0; g < d->nge; ++g)
+        for (int t = 0; t < d->nstep; ++t) {
+            const double ep = d->pet[(size_t)t * d->nge + g];
+            if (ep > 0) sum_e[g] = sum_e[g] + ep;
+        }
+    for (int ia = 0; ia < nac; ++ia) {
+        const HruStatic &h = hru[ia];
+        const double sp = h.ims_rz == 1 ? sum_p[h.ippt] : 0.0, se = h.ims_rz == 1 ? sum_e[h.ipet] : 0.0;
+        tot_ppt[h.ipriv] = tot_ppt[h.ipriv] + (sp * h.ac);
+        tot_pet[h.ipriv] = tot_pet[h.ipriv] + (se * h.ac);
+        tot_frac[h.ipriv] = tot_frac[h.ipriv] + h.ac;
+    }
+
+    // observed-flow statistics of the NSE / log-NSE extension (definition: DESIGN.md "Objective")
+    std::vector<ObsStat> obs(nriv);
+    std::vector<double> qobs;
+    const bool has_qobs = d->qobs != nullptr && d->nstep_obs > 0;
+    if (has_qobs) {
+        qobs.assign(d->qobs, d->qobs + (size_t)nriv * d->nstep_obs);
+        const int n_t = std::min(d->nstep, d->nstep_obs);
+        auto lclip = [](double x, double eps) { return std::log(x > eps ? x : eps); };
+        for (int g = 0; g < nriv; ++g) {
+            ObsStat s{};
+            double sum = 0;
+            for (int t = d->t_warm; t < n_t; ++t) {
+                const double o = qobs[(size_t)t * nriv + g];
+                if (o != d->flow_err) { sum = sum + o; s.n++; }
+            }
+            if (s.n > 0) {
+                s.mean = sum / s.n; s.eps = s.mean / 100;
+                double lsum = 0;
+                for (int t = d->t_warm; t < n_t; ++t) {
+                    const double o = qobs[(size_t)t * nriv + g];
+                    if (o != d->flow_err) { s.sst = s.sst + (o - s.mean) * (o - s.mean); lsum = lsum + lclip(o, s.eps); }
+                }
+                s.lmean = lsum / s.n;
+                for (int t = d->t_warm; t < n_t; ++t) {
+                    const double o = qobs[(size_t)t * nriv + g];
+                    if (o != d->flow_err) { const double lo = lclip(o, s.eps); s.lsst = s.lsst + (lo - s.lmean) * (lo - s.lmean); }
+                }
+            }
+            obs[g] = s;
+        }
+    }
+
+    // ---------------- upload ----------------
+    dcp_catchment *c = new dcp_catchment();
+    cudaGetDevice(&c->device);
+    DevCatchment &C = c->C;
+    C.nac = nac; C.nriv = nriv; C.npt = npt; C.nstep = d->nstep; C.ngp = d->ngp; C.nge = d->nge; C.ntt = d->ntt;
+    C.nnode = nnode; C.ncell = ncell;
+    C.dt = d->dt; C.dtt = d->dt / (double)d->ntt; C.log_dt = std::log(d->dt);
+    C.nstep_obs = has_qobs ? d->nstep_obs : 0; C.t_warm = d->t_warm; C.flow_err = d->flow_err;
+    c->has_qobs = has_qobs;
+    c->node_reach_dist = reach_dist; c->node_down_dist = down_dist;
+    std::vector<double> rain(d->rain, d->rain + (size_t)d->ngp * d->nstep), pet(d->pet, d->pet + (size_t)d->nge * d->nstep);
+    std::vector<double> sum_ac_riv(d->sum_ac_riv, d->sum_ac_riv + nriv), qobs_start(d->qobs_start, d->qobs_start + nriv);
+    cudaError_t e = cudaSuccess;
+    auto up = [&](auto &vec, auto **dst) { if (e == cudaSuccess) e = upload(vec, dst, c->owned); };
+    up(hru, &C.hru); up(w, &C.w); up(riv, &C.riv); up(rain, &C.rain); up(pet, &C.pet);
+    up(sum_ac_riv, &C.sum_ac_riv); up(qobs_start, &C.qobs_start); up(layer_used, &C.layer_used);
+    up(cbeg, &C.node_cell_beg); up(cend, &C.node_cell_end); up(reach_dist, &C.node_reach_dist);
+    up(down_dist, &C.node_down_dist); up(cell_a, &C.cell_a); up(cell_b, &C.cell_b); up(cell_area, &C.cell_area);
+    up(node_input, &C.node_input); up(up_beg, &C.up_beg); up(up_idx, &C.up_idx); up(frac, &C.frac_sub_area);
+    up(obs, &C.obs); up(tot_ppt, &C.tot_ppt); up(tot_pet, &C.tot_pet); up(tot_frac, &C.tot_frac);
+    if (has_qobs) up(qobs, &C.qobs); else C.qobs = nullptr;
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        const int code = fail(e == cudaErrorMemoryAllocation ? DCP_ERR_NOMEM : DCP_ERR_CUDA, "catchment upload failed: %s",
+                              cudaGetErrorString(e));
+        dcp_catchment_destroy(c);
+        return code;
+    }
+    *out = c;
+    return DCP_OK;
+}
+
+int dcp_get_run_stats(const dcp_catchment *c, dcp_run_stats *out) {
+    if (!c || !out) return fail(DCP_ERR_INVALID, "null argument");
+    *out = c->stats;
+    return DCP_OK;
+}
+
+}  // extern "C"
+
+namespace {
+
+struct Carver {                     // carves a slab into aligned arrays
+    char *base; size_t off = 0;
+    explicit Carver(void *p) : base((char *)p) {}
+    template <class T> T *take(size_t n) {
+        off = (off + 255) & ~(size_t)255;
+        T *r = base ? (T *)(base + off) : nullptr;
+        off += n * sizeof(T);
+        return r;
+    }
+};
+
+// lays the batch workspace out (base == nullptr: size query only)
+size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, bool aet) {
+    Carver cv(base);
+    const size_t B = W.B, nac = C.nac;
+    W.par = cv.take<double>(7 * C.npt * B);
+    W.t0dt = cv.take<double>(C.npt * B);
+    W.sd = cv.take<double>(nac * B); W.suz = cv.take<double>(nac * B); W.srz = cv.take<double>(nac * B);
+    W.qint1 = cv.take<double>(nac * B); W.qbf0 = cv.take<double>(nac * B); W.qbf1 = cv.take<double>(nac * B);
+    W.q0 = cv.take<double>(nac * B); W.q2 = cv.take<double>(nac * B);
+    W.aet = (aet || check) ? cv.take<double>(nac * B) : nullptr;
+    if (check) {
+        W.sum_pptin = cv.take<double>(nac * B); W.sum_pein = cv.take<double>(nac * B);
+        W.sumexs = cv.take<double>(nac * B); W.sumexus = cv.take<double>(nac * B);
+        W.sdini = cv.take<double>(nac * B); W.srzini = cv.take<double>(nac * B); W.qbfini = cv.take<double>(nac * B);
+        W.riv_sums = cv.take<double>(3 * C.nriv * B);
+    } else {
+        W.sum_pptin = W.sum_pein = W.sumexs = W.sumexus = W.sdini = W.srzini = W.qbfini = W.riv_sums = nullptr;
+    }
+    W.dh = cv.take<double>((size_t)C.nnode * W.Lcap * B);
+    W.hstart = cv.take<int32_t>(C.nnode * B);
+    W.hbins = cv.take<int32_t>(C.nnode * B);
+    W.qout = cv.take<double>((size_t)W.R * C.nriv * B);
+    W.y = cv.take<double>((size_t)W.R * C.nnode * B);
+    W.sse = cv.take<double>(C.nriv * B); W.lsse = cv.take<double>(C.nriv * B);
+    W.bad = cv.take<int32_t>(C.nriv * B);
+    W.status = cv.take<int32_t>(B);
+    W.diag = cv.take<double>(3 * B);
+    return cv.off + 256;
+}
+
+struct EventTimer {                 // sums the elapsed time of many (start, stop) pairs on one stream
+    std::vector<cudaEvent_t> ev;
+    std::vector<int> tag;
+    cudaStream_t s;
+    explicit EventTimer(cudaStream_t st) : s(st) {}
+    void mark(int t) {
+        cudaEvent_t e; cudaEventCreate(&e); cudaEventRecord(e, s);
+        ev.push_back(e); tag.push_back(t);
+    }
+    // consecutive marks delimit intervals; interval i carries tag[i]
+    void collect(double *sums, int ntags) {
+        for (int i = 0; i < ntags; ++i) sums[i] = 0;
+        for (size_t i = 0; i + 1 < ev.size(); ++i) {
+            float ms = 0; cudaEventElapsedTime(&ms, ev[i], ev[i + 1]);
+            if (tag[i] >= 0 && tag[i] < ntags) sums[tag[i]] += ms;
+        }
+    }
+    double total() { float ms = 0; if (ev.size() >= 2) cudaEventElapsedTime(&ms, ev.front(), ev.back()); return ms; }
+    ~EventTimer() { for (auto e : ev) cudaEventDestroy(e); }
+};
+enum { T_H2D = 0, T_INIT, T_PHYS, T_ROUTE, T_FIN, T_D2H, T_OTHER, T_NTAGS };
+
+}  // namespace
+
+extern "C" {
+
+int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, double *mcpar,
+                     const dcp_run_opts *opts, double *q_out, double *perf_out, double *reach_totals,
+                     double *init_diag, int32_t *status) {
+    (void)first_member;
+    if (!c || !mcpar) return fail(DCP_ERR_INVALID, "null handle or mcpar");
+    if (n_member < 1) return fail(DCP_ERR_INVALID, "n_member < 1");
+    dcp_run_opts o{};
+    o.struct_size = sizeof(dcp_run_opts);
+    if (opts) {
+        if (opts->struct_size != (int)sizeof(dcp_run_opts)) return fail(DCP_ERR_INVALID, "dcp_run_opts.struct_size mismatch");
+        o = *opts;
+    }
+    if (o.kernel == DCP_KERNEL_RESIDENT) return fail(DCP_ERR_UNSUPPORTED, "resident kernel not built yet");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const DevCatchment &C = c->C;
+    const bool dev_io = (o.flags & DCP_OPT_DEVICE_BUFFERS) != 0;
+    const bool check = (o.flags & DCP_OPT_CHECK_BALANCE) != 0;
+    const bool fast = (o.flags & DCP_OPT_FAST_MATH) != 0;
+    const bool aet = reach_totals != nullptr;
+    const bool want_perf = perf_out != nullptr;
+    cudaStream_t s = c->stream;
+    const size_t par_per_member = (size_t)C.npt * 7;
+
+    // ---- batch size from free memory ----
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->ws.cap + c->io.cap;            // our own slabs are reusable
+    int tile = o.steps_per_tile > 0 ? o.steps_per_tile : 1024;
+    tile = std::min(tile, C.nstep);
+    int64_t Bmax = o.members_per_batch > 0 ? o.members_per_batch : 131072;
+    Bmax = std::min<int64_t>(Bmax, n_member);
+
+    c->stats = dcp_run_stats{};
+    c->stats.kernel_used = DCP_KERNEL_STREAMED;
+    EventTimer tm(s);
+    int64_t n_launch = 0, n_phys = 0;
+    int hist_len_max = 0;
+    DevBuf vmin_buf;
+    CUDA_TRY(vmin_buf.reserve(sizeof(double)));
+
+    for (int64_t m0 = 0; m0 < n_member;) {
+        int64_t Bn = std::min<int64_t>(Bmax, n_member - m0);
+        // ---- stage parameters ----
+        tm.mark(T_H2D);
+        double *d_mcpar = nullptr;
+        size_t io_bytes = 0;
+        auto io_size = [&](int64_t B) {
+            size_t b = 256;
+            if (!dev_io) {
+                b += par_per_member * B * 8 + 256;
+                if (q_out) b += (size_t)C.nriv * C.nstep * B * 8 + 256;
+                if (want_perf) b += (size_t)DCP_NMEASURE * C.nriv * B * 8 + 256;
+                if (reach_totals) b += (size_t)3 * C.nriv * B * 8 + 256;
+                if (init_diag) b += (size_t)3 * B * 8 + 256;
+                if (status) b += (size_t)B * 4 + 256;
+            }
+            return b;
+        };
+        // v_min needs the parameters on the device: size io for the current guess of Bn first
+        {
+            // shrink Bn until the (io + workspace) estimate with a pessimistic ring fits; exact sizes follow
+            const double mem_budget = 0.85 * (double)free_b;
+            for (;;) {
+                DevBatch Wq{}; Wq.B = (int)Bn; Wq.Lcap = 1; Wq.R = 1;
+                const size_t fixed = carve_batch(nullptr, C, Wq, check, aet) + io_size(Bn);
+                if ((double)fixed < 0.6 * mem_budget || Bn <= 32) break;
+                Bn = std::max<int64_t>(32, Bn / 2);
+            }
+        }
+        io_bytes = io_size(Bn);
+        CUDA_TRY(c->io.reserve(io_bytes));
+        Carver iocv(c->io.p);
+        double *d_q = nullptr, *d_perf = nullptr, *d_tot = nullptr, *d_diag = nullptr;
+        int32_t *d_status = nullptr;
+        if (dev_io) {
+            d_mcpar = mcpar + m0 * par_per_member;
+            d_q = q_out ? q_out + (size_t)m0 * C.nriv * C.nstep : nullptr;
+            d_perf = perf_out ? perf_out + (size_t)m0 * DCP_NMEASURE * C.nriv : nullptr;
+            d_tot = reach_totals ? reach_totals + (size_t)m0 * 3 * C.nriv : nullptr;
+            d_diag = init_diag ? init_diag + (size_t)m0 * 3 : nullptr;
+            d_status = status ? status + m0 : nullptr;
+        } else {
+            d_mcpar = iocv.take<double>(par_per_member * Bn);
+            if (q_out) d_q = iocv.take<double>((size_t)C.nriv * C.nstep * Bn);
+            if (want_perf) d_perf = iocv.take<double>((size_t)DCP_NMEASURE * C.nriv * Bn);
+            if (reach_totals) d_tot = iocv.take<double>((size_t)3 * C.nriv * Bn);
+            if (init_diag) d_diag = iocv.take<double>((size_t)3 * Bn);
+            if (status) d_status = iocv.take<int32_t>(Bn);
+            CUDA_TRY(cudaMemcpyAsync(d_mcpar, mcpar + m0 * par_per_member, par_per_member * Bn * 8,
+                                     cudaMemcpyHostToDevice, s));
+        }
+        // ---- slowest channel velocity of the batch sizes the histograms ----
+        tm.mark(T_OTHER);
+        const unsigned long long big = 0x7fefffffffffffffull;
+        CUDA_TRY(cudaMemcpyAsync(vmin_buf.p, &big, 8, cudaMemcpyHostToDevice, s));
+        dcp_launch_min_chv(d_mcpar, C.npt, Bn, (double *)vmin_buf.p, s); ++n_launch;
+        double chv_min = 0;
+        CUDA_TRY(cudaMemcpyAsync(&chv_min, vmin_buf.p, 8, cudaMemcpyDeviceToHost, s));
+        CUDA_TRY(cudaStreamSynchronize(s));
+        const double v_min = chv_min * C.dt;
+        if (!(v_min > 0) || !std::isfinite(v_min))
+            return fail(DCP_ERR_INVALID, "channel velocity chv(1)*dt must be positive and finite for every member (min %g)", v_min);
+        double max_reach = 0, max_full = 0;
+        for (int n = 0; n < C.nnode; ++n) {
+            max_reach = std::max(max_reach, c->node_reach_dist[n] / v_min);
+            max_full = std::max(max_full, (c->node_reach_dist[n] + c->node_down_dist[n]) / v_min);
+        }
+        if (max_full > 4.0e6) return fail(DCP_ERR_INVALID, "routing histogram would need %g bins (chv too small)", max_full);
+        DevBatch W{};
+        W.B = (int)Bn;
+        W.Lcap = (int)std::ceil(max_reach) + 3;
+        const int Tcap = (int)std::ceil(max_full) + 3;
+        hist_len_max = std::max(hist_len_max, Tcap - 2);
+        int R = 1;
+        while (R < tile + Tcap + 1) R <<= 1;
+        W.R = R;
+        const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet);
+        if ((double)(ws_bytes + io_bytes) > 0.92 * (double)free_b) {
+            if (Bn <= 32) return fail(DCP_ERR_NOMEM, "batch of 32 members needs %zu MB, device has %zu MB free",
+                                      (ws_bytes + io_bytes) >> 20, free_b >> 20);
+            Bmax = std::max<int64_t>(32, Bn / 2);   // retry this batch smaller
+            continue;
+        }
+        CUDA_TRY(c->ws.reserve(ws_bytes));
+        carve_batch(c->ws.p, C, W, check, aet);
+
+        tm.mark(T_INIT);
+        dcp_launch_init(C, W, d_mcpar, check, s); ++n_launch;
+        for (int t0 = 0; t0 < C.nstep; t0 += tile) {
+            const int t1 = std::min(C.nstep, t0 + tile);
+            tm.mark(T_PHYS);
+            dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s); ++n_launch; ++n_phys;
+            tm.mark(T_ROUTE);
+            dcp_launch_route(C, W, t0, t1, d_q, s); n_launch += 2;
+        }
+        tm.mark(T_FIN);
+        dcp_launch_finalize(C, W, d_perf, d_tot, d_diag, d_status, s); ++n_launch;
+        tm.mark(T_D2H);
+        if (!dev_io) {
+            CUDA_TRY(cudaMemcpyAsync(mcpar + m0 * par_per_member, d_mcpar, par_per_member * Bn * 8, cudaMemcpyDeviceToHost, s));
+            if (q_out) CUDA_TRY(cudaMemcpyAsync(q_out + (size_t)m0 * C.nriv * C.nstep, d_q, (size_t)C.nriv * C.nstep * Bn * 8, cudaMemcpyDeviceToHost, s));
+            if (want_perf) CUDA_TRY(cudaMemcpyAsync(perf_out + (size_t)m0 * DCP_NMEASURE * C.nriv, d_perf, (size_t)DCP_NMEASURE * C.nriv * Bn * 8, cudaMemcpyDeviceToHost, s));
+            if (reach_totals) CUDA_TRY(cudaMemcpyAsync(reach_totals + (size_t)m0 * 3 * C.nriv, d_tot, (size_t)3 * C.nriv * Bn * 8, cudaMemcpyDeviceToHost, s));
+            if (init_diag) CUDA_TRY(cudaMemcpyAsync(init_diag + (size_t)m0 * 3, d_diag, (size_t)3 * Bn * 8, cudaMemcpyDeviceToHost, s));
+            if (status) CUDA_TRY(cudaMemcpyAsync(status + m0, d_status, (size_t)Bn * 4, cudaMemcpyDeviceToHost, s));
+        }
+        tm.mark(-1);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaGetLastError());
+        m0 += Bn;
+    }
+    vmin_buf.release();
+    double sums[T_NTAGS];
+    tm.collect(sums, T_NTAGS);
+    c->stats.ms_total = tm.total();
+    c->stats.ms_h2d = sums[T_H2D];
+    c->stats.ms_init = sums[T_INIT];
+    c->stats.ms_physics = sums[T_PHYS];
+    c->stats.ms_route = sums[T_ROUTE] + sums[T_FIN];
+    c->stats.ms_d2h = sums[T_D2H];
+    c->stats.n_physics_launches = n_phys;
+    c->stats.n_launches = n_launch;
+    c->stats.hist_len = hist_len_max;
+    return DCP_OK;
+}
+
+int dcp_measure_fp64_peak(double *tflops, double *ms_out) {
+    if (dcp_device_count() < 1) return fail(DCP_ERR_NO_DEVICE, "no CUDA device");
+    cudaDeviceProp prop;
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    CUDA_TRY(cudaGetDeviceProperties(&prop, dev));
+    const int blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    double *buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, (size_t)blocks * 256 * 8));
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(a, 0);
+        dcp_launch_fp64_peak(buf, iters, blocks, 0);
+        cudaEventRecord(b, 0);
+        CUDA_TRY(cudaEventSynchronize(b));
+        float ms = 0; cudaEventElapsedTime(&ms, a, b);
+        if (rep > 0) best = std::min(best, ms);
+    }
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    cudaFree(buf);
+    const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * 256.0;
+    if (tflops) *tflops = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return DCP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,106 @@
+// dcp_device.cuh — device-side data model of the ensemble path.
+//
+// Layout rule: every per-member quantity is stored MEMBER-FASTEST ("ensemble members are mapped
+// across threads"): element (x, m) of a [X][B] array lives at x*B + m, so a warp whose lanes are 32
+// consecutive members reads/writes one 256-byte line per access, and every per-HRU / per-river /
+// per-cell structure (weights, indices, forcing) is warp-uniform and comes through the read-only
+// path as a broadcast.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/decipher_b200.h"
+
+// float32 literals of the reference widened to double
+#define DCP_F32_1EM10 ((double)0.0000000001f)
+#define DCP_F32_1EM6  ((double)0.000001f)
+#define DCP_F32_1EM4  ((double)0.0001f)
+#define DCP_F32_1EM2  ((double)0.01f)
+#define DCP_F32_1EM9  ((double)1e-9f)
+
+// Static per-HRU record (warp-uniform reads). 64 bytes.
+struct __align__(16) HruStatic {
+    double ac;        // fractional area
+    double st;        // topographic index
+    double cosm;      // cos(mslp), computed once on the host (dyna_satzone_analyticalsolver.f90:49)
+    double w_riv;     // wtrans(ntrans+1)
+    int32_t ippt, ipet, ipar, ipriv;      // 0-based here
+    int32_t row_beg, row_end;             // destination-major W row (gather form of dynamic_dist)
+    int32_t riv_beg, riv_end;             // non-zero entries of rivers(ia, :)
+    int32_t ims_rz, ims_uz;
+    int32_t pad0, pad1;
+};
+
+// One non-zero of the gather matrix: qin(dest) += (qbf(src) * w) * ac(src)   (dyna_dynamic_dist.f90:49-52)
+struct __align__(8) WEntry {
+    double w;
+    double ac_src;
+    int32_t src;
+    int32_t pad;
+};
+
+struct __align__(8) RivEntry {      // rivers(ia, r) != 0
+    double share;
+    int32_t r;
+    int32_t pad;
+};
+
+struct ObsStat {                    // per gauge, host-computed once (member independent)
+    double mean, sst, eps, lmean, lsst;
+    int32_t n;
+    int32_t pad;
+};
+
+// Everything a kernel needs; passed by value (fits in the 4 KB parameter space).
+struct DevCatchment {
+    int32_t nac, nriv, npt, nstep, ngp, nge, ntt, nnode, ncell;
+    double dt, dtt, log_dt;
+    const HruStatic *hru;           // [nac]
+    const WEntry *w;                // gather CSR
+    const RivEntry *riv;            // river CSR
+    const double *rain, *pet;       // [ngp x nstep], [nge x nstep]
+    const double *sum_ac_riv, *qobs_start;   // [nriv]
+    const uint8_t *layer_used;      // [npt] some HRU references the layer (srinit clip, dyna_init_satzone.f90:203)
+    // routing, member independent parts of route_processing_build_hist
+    const int32_t *node_cell_beg, *node_cell_end;  // [nnode] cell range (0-based, end exclusive), beg<0: no cells
+    const double *node_reach_dist;  // [nnode]  max(dist) - min(ds_dist)          (dta_route_processing.f90:226)
+    const double *node_down_dist;   // [nnode]  min(ds_dist) - global min ds_dist (:238)
+    const double *cell_a, *cell_b, *cell_area;     // [ncell]  section_dist, section_dist + cell length, area
+    const int32_t *node_input;      // [nnode] river index feeding the node (inverse of node_to_flow_mapping), -1 none
+    const int32_t *up_beg;          // [nnode+1] upstream-tree CSR
+    const int32_t *up_idx;          // 0-based node indexes
+    const double *frac_sub_area;    // [nriv] frac_sub_area(node_to_flow_mapping(iriv))
+    // objective
+    const double *qobs;             // [nriv x nstep_obs] or null
+    const ObsStat *obs;             // [nriv]
+    int32_t nstep_obs, t_warm;
+    double flow_err;
+    // member-independent reach totals of precipitation / PET (dyna_write_output.f90:61-77)
+    const double *tot_ppt, *tot_pet, *tot_frac;    // [nriv]
+};
+
+// Per-batch workspace (B members, member fastest).
+struct DevBatch {
+    int32_t B;                      // members in this batch
+    int32_t Lcap;                   // bins reserved per node histogram
+    int32_t R;                      // ring length (power of two) of qout / y in time
+    double *par;                    // [7][npt][B]  szm,lnto,srmax,srinit,chv,td,smax
+    double *t0dt;                   // [npt][B]
+    // state [nac][B]
+    double *sd, *suz, *srz, *qint1, *qbf0, *qbf1, *q0, *q2, *aet;
+    // checked-mode extras [nac][B] (null otherwise)
+    double *sum_pptin, *sum_pein, *sumexs, *sumexus, *sdini, *srzini, *qbfini;
+    double *riv_sums;               // [3][nriv][B]  sumqb, sumqof, sumqout (checked mode)
+    // routing
+    double *dh;                     // [nnode][Lcap][B] normalised delay histograms
+    int32_t *hstart;                // [nnode][B]  node_hist_indexes(:,1)
+    int32_t *hbins;                 // [nnode][B]  bin count
+    double *qout;                   // [R][nriv][B]
+    double *y;                      // [R][nnode][B]
+    // objective accumulators [nriv][B]
+    double *sse, *lsse;
+    int32_t *bad;                   // [nriv][B] non-finite flow seen
+    // per member
+    int32_t *status;                // [B]
+    double *diag;                   // [3][B]
+};

@@ -1,0 +1,599 @@
+// dcp_kernels.cu — member-per-thread kernels of the ensemble path (sm_100a).
+//
+//   k_init_members      param_setup + init_satzone + route_processing_build_hist, one thread per member
+//   k_physics_streamed  Topmod time loop over a time tile, state streamed through L2/HBM
+//   k_route_conv        time-delay-histogram convolution of every node's own reach
+//   k_route_gauge       upstream-tree summation, /frac_sub_area, flow output, NSE / log-NSE sums
+//   k_finalize          reach totals + performance measures into the ABI's output layouts
+//
+// All per-member data are member-fastest, so every global access of a warp is one coalesced line and
+// every catchment structure (W rows, river entries, forcing) is warp-uniform.
+#include "dcp_device.cuh"
+#include "dcp_physics.cuh"
+#include "dcp_kernels.h"
+
+#include <cfloat>
+#include <cmath>
+
+#define LDG(p) __ldg(p)
+
+// ------------------------------------------------------------------------------------------------
+// minimum over the batch of chv(layer 1): sizes the histogram buffers (slowest member = longest delay)
+// ------------------------------------------------------------------------------------------------
+__global__ void k_min_chv(const double *__restrict__ mcpar, int npt, int64_t n_member, double *out) {
+    double v = DBL_MAX;
+    for (int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; m < n_member;
+         m += (int64_t)gridDim.x * blockDim.x) {
+        const double x = mcpar[m * npt * 7 + 4 * npt + 0];
+        v = (x < v) ? x : v;                     // NaN never selected
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const double w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = (w < v) ? w : v;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        // v > 0 for valid input: positive doubles order like their bit patterns
+        if (v > 0.0) atomicMin((unsigned long long *)out, (unsigned long long)__double_as_longlong(v));
+        else atomicMin((unsigned long long *)out, 0ull);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K1: per-member initialisation
+// ------------------------------------------------------------------------------------------------
+// calculate_qb (RRMODEL/dyna_init_satzone.f90:266-294) without storing: returns qb_tmp
+template <bool STORE>
+__device__ __forceinline__ double calc_qb(const DevCatchment &C, const DevBatch &W, int m, double D,
+                                          double meanatb, double meanT0DT) {
+    const int B = W.B, npt = C.npt;
+    double qb_tmp = 0.0;
+    for (int ia = 0; ia < C.nac; ++ia) {
+        const HruStatic h = C.hru[ia];
+        const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
+        const double smax = W.par[(6 * npt + h.ipar) * (size_t)B + m];
+        const double t0 = W.t0dt[h.ipar * (size_t)B + m];
+        const double q0 = W.q0[ia * (size_t)B + m];
+        double sd = D + szm * ((meanatb - h.st) + (t0 - meanT0DT));           // :268
+        double qbf = q0 * exp(-sd / szm);                                     // :269
+        if (sd < 0.0) {
+            sd = 0.0;
+            qbf = q0;                 // exp(T0DT - st) again (:273): same expression as q0, same bits
+        } else if (sd >= smax) {
+            sd = smax;
+            qbf = 0.0;
+        }
+        if (STORE) {
+            W.sd[ia * (size_t)B + m] = sd;
+            W.qbf0[ia * (size_t)B + m] = qbf;
+        }
+        const double base = C.dt * qbf * h.w_riv;                             // :289  (dt*qbf)*w
+        for (int e = h.riv_beg; e < h.riv_end; ++e) {
+            const RivEntry r = C.riv[e];
+            qb_tmp = qb_tmp + (base * r.share * h.ac);
+        }
+    }
+    return qb_tmp;
+}
+
+template <bool CHECK>
+__global__ void __launch_bounds__(128)
+k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7 x B]*/) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = W.B;
+    if (m >= B) return;
+    const int npt = C.npt, nac = C.nac;
+    int status = 0;
+
+    // ---- param_setup (RRMODEL/dyna_param_setup.f90:58-70) ----
+    double *mp = mcpar + (size_t)m * npt * 7;
+    for (int i = 0; i < npt; ++i) {
+        for (int p = 0; p < 7; ++p) W.par[(p * npt + i) * (size_t)B + m] = mp[p * npt + i];
+        W.t0dt[i * (size_t)B + m] = mp[1 * npt + i] + C.log_dt;
+    }
+    const double chvdt1 = mp[4 * npt + 0] * C.dt;                             // dyna_init_satzone.f90:85
+
+    // ---- route_processing_build_hist (DTA/dta_route_processing.f90:154-354), v = chvdt(1) ----
+    for (int n = 0; n < C.nnode; ++n) {
+        const int cb = C.node_cell_beg[n], ce = C.node_cell_end[n];
+        int hstart = 0, bins = 0;
+        if (cb >= 0) {
+            const double reach_delay = C.node_reach_dist[n] / chvdt1;         // :231
+            const double tdd = C.node_down_dist[n] / chvdt1;                  // :241
+            const double full_delay = reach_delay + tdd;                      // :256
+            hstart = (int)floor(tdd) + 1;                                     // :259
+            const int hend = (int)ceil(full_delay) + 1;                       // :260
+            bins = (hend - hstart) + 1;                                       // :312
+            if (bins > W.Lcap || bins < 1) {                                  // sized from the slowest member
+                status |= DCP_ST_HIST_DROPPED;
+                bins = bins < 1 ? 0 : W.Lcap;
+            }
+            double *dh = W.dh + (size_t)n * W.Lcap * B + m;
+            for (int k = 0; k < bins; ++k) dh[(size_t)k * B] = 0.0;
+            for (int j = cb; j < ce; ++j) {
+                const double cur_a = C.cell_a[j] / chvdt1;                    // :337
+                const double cur_b = C.cell_b[j] / chvdt1;                    // :339
+                const double value = C.cell_area[j];
+                const int hist_a = (int)floor(cur_a) + 1;                     // hist_add_value :369-370
+                const int hist_b = (int)floor(cur_b) + 1;
+                if (hist_b > bins || hist_a < 1) {                            // :378-382 drops the cell
+                    status |= DCP_ST_HIST_DROPPED;
+                    continue;
+                }
+                if (hist_a == hist_b) {
+                    const double fr = cur_b - cur_a;
+                    dh[(size_t)(hist_a - 1) * B] = dh[(size_t)(hist_a - 1) * B] + value * fr;
+                } else {
+                    for (int k = hist_a + 1; k <= hist_b - 1; ++k)
+                        dh[(size_t)(k - 1) * B] = dh[(size_t)(k - 1) * B] + value;
+                    double fr = (1.0 - (cur_a - (double)hist_a + 1.0));       // :410
+                    dh[(size_t)(hist_a - 1) * B] = dh[(size_t)(hist_a - 1) * B] + (value * fr);
+                    fr = (cur_b - (double)hist_b + 1.0);                      // :413
+                    dh[(size_t)(hist_b - 1) * B] = dh[(size_t)(hist_b - 1) * B] + (value * fr);
+                }
+            }
+            double s = 0.0;                                                   // :347
+            for (int k = 0; k < bins; ++k) s += dh[(size_t)k * B];
+            for (int k = 0; k < bins; ++k) dh[(size_t)k * B] = dh[(size_t)k * B] / s;
+        }
+        W.hstart[n * (size_t)B + m] = hstart;
+        W.hbins[n * (size_t)B + m] = bins;
+    }
+
+    // ---- init_satzone (RRMODEL/dyna_init_satzone.f90:92-213) ----
+    double mean_q = 0.0;
+    for (int r = 0; r < C.nriv; ++r) mean_q = mean_q + C.qobs_start[r] * C.sum_ac_riv[r];
+    double meanatb = 0.0, meanT0DT = 0.0, meanSZM = 0.0;
+    for (int ia = 0; ia < nac; ++ia) {
+        const HruStatic h = C.hru[ia];
+        const double t0 = W.t0dt[h.ipar * (size_t)B + m];
+        const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
+        const double smax = W.par[(6 * npt + h.ipar) * (size_t)B + m];
+        meanatb = meanatb + (h.st * h.ac);
+        meanT0DT = meanT0DT + (t0 * h.ac);
+        meanSZM = meanSZM + (szm * h.ac);
+        const double q0 = exp(t0 - h.st);                                     // :108
+        W.q0[ia * (size_t)B + m] = q0;
+        // q2 of dyna_satzone_analyticalsolver.f90:50-51 is time invariant: hoisted here
+        W.q2[ia * (size_t)B + m] = q0 * h.cosm * exp(-1.0 * h.cosm * smax / szm);
+    }
+    const double q0bar = exp(meanT0DT - meanatb);                             // :112
+    double D = -meanSZM * log(mean_q / q0bar);                                // :113
+    double guess = mean_q, ndiff = DCP_F32_1EM4, qb_diff = 1.0, qb_diff_prev;
+    int sol_flag = 1;
+
+    // calculate_qbmax (:324-345): sd = 0, qbf = q0
+    double qb_tmp = 0.0;
+    for (int ia = 0; ia < nac; ++ia) {
+        const HruStatic h = C.hru[ia];
+        const double base = C.dt * W.q0[ia * (size_t)B + m] * h.w_riv;
+        for (int e = h.riv_beg; e < h.riv_end; ++e) qb_tmp = qb_tmp + (base * C.riv[e].share * h.ac);
+    }
+    bool use_max = true;          // state currently defined by calculate_qbmax
+    double D_last = 0.0;
+    if (qb_tmp <= mean_q) { qb_diff = 0.0; sol_flag = 2; }                    // :126-131
+    int iter = 0;
+    while (fabs(qb_diff) > DCP_F32_1EM2) {                                    // :134
+        if (++iter > DCP_INIT_MAX_ITER) { status |= DCP_ST_INIT_ITERCAP; break; }
+        qb_tmp = calc_qb<false>(C, W, m, D, meanatb, meanT0DT);
+        use_max = false; D_last = D;
+        qb_diff_prev = qb_diff;
+        qb_diff = (qb_tmp - mean_q) * 1000.0;                                 // :140
+        if (qb_diff > DCP_F32_1EM2) guess = guess - ndiff;
+        else if (qb_diff < -DCP_F32_1EM2) guess = guess + ndiff;
+        D = -meanSZM * log(guess / q0bar);                                    // :153
+        if ((qb_diff_prev > 0.0) && (qb_diff < 0.0)) {                        // :156-172
+            if (ndiff > DCP_F32_1EM9) {
+                ndiff = ndiff / 10.0;
+            } else {
+                sol_flag = 0;
+                if (fabs(qb_diff) < fabs(qb_diff_prev)) break;
+                qb_tmp = calc_qb<false>(C, W, m, D, meanatb, meanT0DT);
+                D_last = D;
+                break;
+            }
+        }
+    }
+    status |= (sol_flag & DCP_ST_SOLFLAG_MASK);
+    W.diag[0 * (size_t)B + m] = mean_q;
+    W.diag[1 * (size_t)B + m] = qb_tmp;
+    W.diag[2 * (size_t)B + m] = guess;
+
+    // final state = that of the last calculate_qb / calculate_qbmax call
+    if (use_max) {
+        for (int ia = 0; ia < nac; ++ia) {
+            W.sd[ia * (size_t)B + m] = 0.0;
+            W.qbf0[ia * (size_t)B + m] = W.q0[ia * (size_t)B + m];
+        }
+    } else {
+        (void)calc_qb<true>(C, W, m, D_last, meanatb, meanT0DT);
+    }
+    // srinit clip (:203-206): only layers some HRU references are touched
+    for (int i = 0; i < npt; ++i) {
+        if (!C.layer_used[i]) continue;
+        const double srmax = W.par[(2 * npt + i) * (size_t)B + m];
+        if (W.par[(3 * npt + i) * (size_t)B + m] > srmax) {
+            W.par[(3 * npt + i) * (size_t)B + m] = srmax;
+            mp[3 * npt + i] = srmax;
+        }
+    }
+    for (int ia = 0; ia < nac; ++ia) {                                        // :194-213
+        const HruStatic h = C.hru[ia];
+        const size_t o = ia * (size_t)B + m;
+        const double qbf = W.qbf0[o];
+        W.qint1[o] = qbf * h.ac;
+        W.suz[o] = 0.0;
+        const double srz = W.par[(2 * npt + h.ipar) * (size_t)B + m] - W.par[(3 * npt + h.ipar) * (size_t)B + m];
+        W.srz[o] = srz;
+        if (W.aet) W.aet[o] = 0.0;
+        if (CHECK) {
+            W.sum_pptin[o] = 0.0; W.sum_pein[o] = 0.0; W.sumexs[o] = 0.0; W.sumexus[o] = 0.0;
+            W.sdini[o] = W.sd[o]; W.srzini[o] = srz; W.qbfini[o] = qbf;
+        }
+    }
+    if (CHECK)
+        for (int r = 0; r < 3 * C.nriv; ++r) W.riv_sums[r * (size_t)B + m] = 0.0;
+    for (int r = 0; r < C.nriv; ++r) {
+        W.sse[r * (size_t)B + m] = 0.0;
+        W.lsse[r * (size_t)B + m] = 0.0;
+        W.bad[r * (size_t)B + m] = 0;
+    }
+    W.status[m] = status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2 (streamed): Topmod time loop (RRMODEL/dyna_topmod.f90:92-233) for steps [t0, t1)
+// ------------------------------------------------------------------------------------------------
+// Thread = member.  Per step the thread walks the HRUs in ascending order, exactly like the
+// reference, so every accumulation (qin gather, qb, qof, the results_ts sums) has the reference's
+// summation order and needs no cross-thread reduction.  qbf is double buffered in time
+// (dynamic_dist reads last step's values of ALL HRUs before any is updated).
+template <bool FAST, bool CHECK, bool AET, bool NPT1>
+__global__ void __launch_bounds__(DCP_STREAM_THREADS)
+k_physics_streamed(DevCatchment C, DevBatch W, int t0, int t1) {
+    extern __shared__ double s_acc[];              // [2*nriv (+3*nriv)][blockDim] river accumulators
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = W.B;
+    if (m >= B) return;
+    const int nac = C.nac, nriv = C.nriv, npt = C.npt;
+    const int nthr = blockDim.x;
+    double *s_qb = s_acc + threadIdx.x;            // s_qb[r*nthr], s_qof[(nriv+r)*nthr]
+    double *s_qof = s_acc + (size_t)nriv * nthr + threadIdx.x;
+
+    StepConst g;
+    g.dt = C.dt; g.dtt = C.dtt; g.inv_dtt = 1.0 / C.dtt; g.ntt = C.ntt;
+
+    // parameters of layer 0 hoisted when there is a single layer
+    double p_szm = 0, p_srmax = 0, p_td = 0, p_smax = 0;
+    if (NPT1) {
+        p_szm = W.par[(0 * npt) * (size_t)B + m];
+        p_srmax = W.par[(2 * npt) * (size_t)B + m];
+        p_td = W.par[(5 * npt) * (size_t)B + m];
+        p_smax = W.par[(6 * npt) * (size_t)B + m];
+    }
+    const double inv_szm = 1.0 / p_szm, inv_srmax = 1.0 / p_srmax;
+    int status = 0;
+
+    for (int t = t0; t < t1; ++t) {
+        const double *__restrict__ qbf_old = (t & 1) ? W.qbf1 : W.qbf0;
+        double *__restrict__ qbf_new = (t & 1) ? W.qbf0 : W.qbf1;
+        for (int r = 0; r < nriv; ++r) { s_qb[r * nthr] = 0.0; s_qof[r * nthr] = 0.0; }
+        const double *rain_t = C.rain + (size_t)t * C.ngp;
+        const double *pet_t = C.pet + (size_t)t * C.nge;
+
+        // results_ts running sums (dyna_results_ts.f90:56-71), CHECK only
+        double c_qbf = 0, c_qbfini = 0, c_sd = 0, c_srz = 0, c_suz = 0, c_sdini = 0, c_srzini = 0,
+               c_catin = 0, c_eout = 0, c_exs = 0, c_exus = 0;
+
+        for (int ia = 0; ia < nac; ++ia) {
+            const HruStatic h = C.hru[ia];
+            const size_t o = ia * (size_t)B + m;
+            const double qbf_o = qbf_old[o];
+            // dynamic_dist, river part (dyna_dynamic_dist.f90:57-66): (((dtt*qbf)*w_riv)*rivers)*ac
+            {
+                const double base = C.dtt * qbf_o * h.w_riv;
+                for (int e = h.riv_beg; e < h.riv_end; ++e) {
+                    const RivEntry re = C.riv[e];
+                    s_qb[re.r * nthr] = s_qb[re.r * nthr] + base * re.share * h.ac;
+                }
+            }
+            // dynamic_dist, HRU part in gather form: sources ascending == reference's scatter order
+            double qin = 0.0;
+            for (int e = h.row_beg; e < h.row_end; ++e) {
+                const WEntry we = C.w[e];
+                qin = qin + qbf_old[we.src * (size_t)B + m] * we.w * we.ac_src;
+            }
+            HruConst c;
+            double szm;
+            if (NPT1) {
+                szm = p_szm; c.srmax = p_srmax; c.td = p_td; c.smax = p_smax;
+                c.inv_srmax = inv_srmax;
+                c.inv_m2 = h.cosm * inv_szm;
+            } else {
+                szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
+                c.srmax = W.par[(2 * npt + h.ipar) * (size_t)B + m];
+                c.td = W.par[(5 * npt + h.ipar) * (size_t)B + m];
+                c.smax = W.par[(6 * npt + h.ipar) * (size_t)B + m];
+                if (FAST) { c.inv_srmax = 1.0 / c.srmax; c.inv_m2 = h.cosm / szm; }
+            }
+            c.ac = h.ac;
+            if (FAST) c.inv_ac = 1.0 / h.ac;
+            c.q0 = W.q0[o];
+            c.q1 = c.q0 * h.cosm;
+            c.q2 = W.q2[o];
+            c.m2 = szm / h.cosm;
+            c.ims_rz = h.ims_rz; c.ims_uz = h.ims_uz;
+
+            HruState s;
+            s.sd = W.sd[o]; s.suz = W.suz[o]; s.srz = W.srz[o]; s.qint1 = W.qint1[o];
+            const double p = LDG(rain_t + h.ippt), ep = LDG(pet_t + h.ipet);
+            HruFlux f;
+            hru_step<FAST, CHECK>(c, g, p, ep, qin, s, f);
+
+            W.sd[o] = s.sd; W.suz[o] = s.suz; W.srz[o] = s.srz; W.qint1[o] = s.qint1;
+            qbf_new[o] = f.qbf;
+            if (AET) { if (h.ims_rz == 1 && ep > 0.0) W.aet[o] = W.aet[o] + f.ea; }
+            if (f.ex > 0.0) s_qof[h.ipriv * nthr] = s_qof[h.ipriv * nthr] + f.ex * h.ac;   // dyna_results_ac.f90:35-38
+
+            if (CHECK) {
+                if (f.rz_bad) status |= DCP_ST_RZ_BALANCE;
+                double sp = W.sum_pptin[o], se = W.sum_pein[o], sx = W.sumexs[o], su = W.sumexus[o];
+                if (h.ims_rz == 1) { sp = sp + p; if (ep > 0.0) se = se + ep; }
+                if (f.exus > 0.0 || f.exus < 0.0) su = su + (f.exus * h.ac);
+                if (f.exs1 != 0.0) sx = sx + (f.exs1 * h.ac);
+                if (f.exs2 != 0.0) sx = sx + (f.exs2 * h.ac);
+                W.sum_pptin[o] = sp; W.sum_pein[o] = se; W.sumexs[o] = sx; W.sumexus[o] = su;
+                c_qbf = c_qbf + f.qbf * h.ac;
+                c_qbfini = c_qbfini + (W.qbfini[o] * h.ac);
+                c_sd = c_sd - (s.sd * h.ac);
+                c_srz = c_srz + s.srz * h.ac;
+                c_suz = c_suz + s.suz * h.ac;
+                c_srzini = c_srzini + (W.srzini[o] * h.ac);
+                c_sdini = c_sdini - (W.sdini[o] * h.ac);
+                c_catin = c_catin + sp * h.ac;
+                c_eout = c_eout + (AET ? W.aet[o] : 0.0) * h.ac;
+                c_exs = c_exs + sx;
+                c_exus = c_exus + su;
+            }
+        }
+        // river (dyna_river.f90:42-49): qout = qb + qof
+        double *qo = W.qout + ((size_t)(t & (W.R - 1)) * nriv) * B + m;
+        double k_qb = 0, k_qof = 0, k_out = 0;
+        for (int r = 0; r < nriv; ++r) {
+            const double qb = s_qb[r * nthr], qof = s_qof[r * nthr];
+            const double qout = qb + qof;
+            qo[(size_t)r * B] = qout;
+            if (CHECK) {
+                double *rs = W.riv_sums + m;
+                const double a = rs[(0 * nriv + r) * (size_t)B] + qb;     // sumqb (dyna_dynamic_dist.f90:63-65)
+                const double b = rs[(1 * nriv + r) * (size_t)B] + qof;    // sumqof
+                const double c2 = rs[(2 * nriv + r) * (size_t)B] + qout;  // sumqout
+                rs[(0 * nriv + r) * (size_t)B] = a;
+                rs[(1 * nriv + r) * (size_t)B] = b;
+                rs[(2 * nriv + r) * (size_t)B] = c2;
+                k_qb = k_qb + a; k_qof = k_qof + b; k_out = k_out + c2;
+            }
+        }
+        if (CHECK) {   // dyna_results_ts.f90:73-101 (suzini = 0)
+            const double sumallini = c_srzini + 0.0 + c_sdini;
+            const double wbal = sumallini + c_catin - c_eout - k_out - (c_srz + c_suz + c_sd)
+                                + ((c_qbfini - c_qbf) * C.dtt);
+            if (fabs((c_exs + c_exus + k_qb) - k_out) > DCP_F32_1EM6) status |= DCP_ST_TS_OUTSUM;
+            if (fabs(wbal) > DCP_F32_1EM6) status |= DCP_ST_TS_WBAL;
+            (void)k_qof;
+        }
+    }
+    if (CHECK && status) W.status[m] |= status;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3a: y_n(t) = flow_matrix(n, node_hist_indexes(n,1)) at step t
+//      = sum_k delay_hist_n(k) * qout_n(t-k), accumulated oldest first exactly like the reference's
+//        add-then-shift matrix (DTA/dta_route_processing.f90:671-681, 723-727).
+// Thread = (member, node); sequential over the tile's steps.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_route_conv(DevCatchment C, DevBatch W, int t0, int t1) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = blockIdx.y;
+    const int B = W.B;
+    if (m >= B) return;
+    const int riv = C.node_input[n];
+    const int bins = W.hbins[n * (size_t)B + m];
+    const double *dh = W.dh + (size_t)n * W.Lcap * B + m;
+    const int Rm = W.R - 1;
+    for (int t = t0; t < t1; ++t) {
+        double y = 0.0;
+        if (riv >= 0) {
+            int k = bins - 1;
+            if (k > t) k = t;
+            for (; k >= 0; --k) {
+                const double q = W.qout[((size_t)((t - k) & Rm) * C.nriv + riv) * B + m];
+                y = y + dh[(size_t)k * B] * q;
+            }
+        }
+        W.y[((size_t)(t & Rm) * C.nnode + n) * B + m] = y;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3b: q(iriv, t) = sum over {node, upstream tree} of flow_matrix(node', c_i), / frac_sub_area
+//      (DTA/dta_route_processing.f90:685-714, RRMODEL/dyna_river.f90:57-59), then the objective sums.
+// For an upstream row u, column c_i lies before u's own histogram, so flow_matrix(u, c_i)(t) is
+// y_u delayed by (hstart_u - c_i) steps; the general case (c_i inside u's histogram) is summed directly.
+// Thread = (member, gauge).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double node_at_column(const DevCatchment &C, const DevBatch &W, int m, int u,
+                                                 int col, int t) {
+    const int B = W.B, Rm = W.R - 1;
+    const int hs = W.hstart[u * (size_t)B + m];
+    const int bins = W.hbins[u * (size_t)B + m];
+    if (bins <= 0) return 0.0;
+    const int d = hs - col;
+    if (d >= 0) {
+        if (t - d < 0) return 0.0;
+        return W.y[((size_t)((t - d) & Rm) * C.nnode + u) * B + m];
+    }
+    // column inside (or past) the histogram of u: partial sum, oldest first
+    const int riv = C.node_input[u];
+    if (riv < 0) return 0.0;
+    const int o = -d;
+    double y = 0.0;
+    int k = bins - 1 - o;
+    if (k > t) k = t;
+    const double *dh = W.dh + (size_t)u * W.Lcap * B + m;
+    for (; k >= 0; --k)
+        y = y + dh[(size_t)(k + o) * B] * W.qout[((size_t)((t - k) & Rm) * C.nriv + riv) * B + m];
+    return y;
+}
+
+__global__ void __launch_bounds__(128)
+k_route_gauge(DevCatchment C, DevBatch W, int t0, int t1, double *__restrict__ q_out /*[nriv x nstep x B] or null*/) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;                      // river / output index; flow_output_indexes(i) = i
+    const int B = W.B;
+    if (m >= B) return;
+    const int col = W.hstart[i * (size_t)B + m];   // sum_index
+    const double frac = C.frac_sub_area[i];
+    double sse = W.sse[i * (size_t)B + m], lsse = W.lsse[i * (size_t)B + m];
+    int bad = W.bad[i * (size_t)B + m];
+    const bool obj = (C.qobs != nullptr);
+    ObsStat os;
+    if (obj) os = C.obs[i];
+    const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
+    for (int t = t0; t < t1; ++t) {
+        double q_sum = 0.0;
+        q_sum = q_sum + node_at_column(C, W, m, i, col, t);
+        for (int e = C.up_beg[i]; e < C.up_beg[i + 1]; ++e)
+            q_sum = q_sum + node_at_column(C, W, m, C.up_idx[e], col, t);
+        const double q = q_sum / frac;
+        if (q_out) q_out[((size_t)m * C.nstep + t) * C.nriv + i] = q;
+        if (!isfinite(q)) bad = 1;
+        if (obj && t >= C.t_warm && t < n_t) {
+            const double o = C.qobs[(size_t)t * C.nriv + i];
+            if (o != C.flow_err) {
+                sse = sse + (q - o) * (q - o);
+                const double dl = log(q > os.eps ? q : os.eps) - log(o > os.eps ? o : os.eps);
+                lsse = lsse + dl * dl;
+            }
+        }
+    }
+    W.sse[i * (size_t)B + m] = sse;
+    W.lsse[i * (size_t)B + m] = lsse;
+    W.bad[i * (size_t)B + m] = bad;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: outputs in the ABI's layouts (member slowest)
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_finalize(DevCatchment C, DevBatch W, double *__restrict__ perf, double *__restrict__ totals,
+           double *__restrict__ diag, int32_t *__restrict__ status) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int B = W.B;
+    if (m >= B) return;
+    const int nriv = C.nriv;
+    int st = W.status[m];
+    const double nan = __longlong_as_double(0x7ff8000000000000ll);
+    for (int g = 0; g < nriv; ++g) {
+        const int bad = W.bad[g * (size_t)B + m];
+        if (bad) st |= DCP_ST_NONFINITE;
+        if (perf) {
+            double nse = nan, lnse = nan;
+            if (C.qobs && !bad && C.obs[g].n > 0) {
+                nse = 1.0 - W.sse[g * (size_t)B + m] / C.obs[g].sst;
+                lnse = 1.0 - W.lsse[g * (size_t)B + m] / C.obs[g].lsst;
+            }
+            perf[((size_t)m * nriv + g) * DCP_NMEASURE + 0] = nse;
+            perf[((size_t)m * nriv + g) * DCP_NMEASURE + 1] = lnse;
+        }
+    }
+    if (totals) {
+        // dyna_write_output.f90:61-77: per reach sum(sum_x*ac)/sum(ac)*1000; ppt and pet are member independent
+        for (int g = 0; g < nriv; ++g) {
+            totals[((size_t)m * nriv + g) * 3 + 0] = (C.tot_ppt[g] / C.tot_frac[g]) * 1000.0;
+            totals[((size_t)m * nriv + g) * 3 + 1] = (C.tot_pet[g] / C.tot_frac[g]) * 1000.0;
+        }
+        for (int g = 0; g < nriv; ++g) {
+            double a = 0.0;
+            for (int ia = 0; ia < C.nac; ++ia)
+                if (C.hru[ia].ipriv == g) a = a + (W.aet[ia * (size_t)B + m] * C.hru[ia].ac);
+            totals[((size_t)m * nriv + g) * 3 + 2] = (a / C.tot_frac[g]) * 1000.0;
+        }
+    }
+    if (diag)
+        for (int k = 0; k < 3; ++k) diag[(size_t)m * 3 + k] = W.diag[k * (size_t)B + m];
+    if (status) status[m] = st;
+    W.status[m] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
+// FP64 pipe peak: 8 independent DFMA chains per thread, no memory traffic
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch wrappers (called from dcp_api.cu)
+// ------------------------------------------------------------------------------------------------
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+void dcp_launch_min_chv(const double *mcpar, int npt, int64_t n_member, double *out, cudaStream_t s) {
+    k_min_chv<<<148, 256, 0, s>>>(mcpar, npt, n_member, out);
+}
+
+void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bool check, cudaStream_t s) {
+    const int grid = cdiv(W.B, 128);
+    if (check) k_init_members<true><<<grid, 128, 0, s>>>(C, W, mcpar);
+    else k_init_members<false><<<grid, 128, 0, s>>>(C, W, mcpar);
+}
+
+template <bool FAST, bool CHECK, bool AET>
+static void launch_streamed2(const DevCatchment &C, const DevBatch &W, int t0, int t1, cudaStream_t s) {
+    const int threads = DCP_STREAM_THREADS;
+    const int grid = cdiv(W.B, threads);
+    const size_t smem = (size_t)2 * C.nriv * threads * sizeof(double);
+    if (C.npt == 1) {
+        auto k = k_physics_streamed<FAST, CHECK, AET, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, threads, smem, s>>>(C, W, t0, t1);
+    } else {
+        auto k = k_physics_streamed<FAST, CHECK, AET, false>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, threads, smem, s>>>(C, W, t0, t1);
+    }
+}
+
+void dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,
+                                 bool check, bool aet, cudaStream_t s) {
+    if (check) {            // checked mode always tracks aet (results_ts needs sum_aeout)
+        if (fast) launch_streamed2<true, true, true>(C, W, t0, t1, s);
+        else launch_streamed2<false, true, true>(C, W, t0, t1, s);
+    } else if (aet) {
+        if (fast) launch_streamed2<true, false, true>(C, W, t0, t1, s);
+        else launch_streamed2<false, false, true>(C, W, t0, t1, s);
+    } else {
+        if (fast) launch_streamed2<true, false, false>(C, W, t0, t1, s);
+        else launch_streamed2<false, false, false>(C, W, t0, t1, s);
+    }
+}
+
+void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s) {
+    dim3 g1(cdiv(W.B, 128), C.nnode), g2(cdiv(W.B, 128), C.nriv);
+    k_route_conv<<<g1, 128, 0, s>>>(C, W, t0, t1);
+    k_route_gauge<<<g2, 128, 0, s>>>(C, W, t0, t1, q_out);
+}
+
+void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,
+                         int32_t *status, cudaStream_t s) {
+    k_finalize<<<cdiv(W.B, 128), 128, 0, s>>>(C, W, perf, totals, diag, status);
+}
+
+void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s) {
+    k_fp64_peak<<<blocks, 256, 0, s>>>(out, iters, 0.999999, 1e-9);
+}

@@ -1,0 +1,14 @@
+// dcp_kernels.h — launch wrappers shared between the kernel TUs and the C-ABI host code.
+#pragma once
+#include "dcp_device.cuh"
+
+#define DCP_STREAM_THREADS 128
+
+void dcp_launch_min_chv(const double *mcpar, int npt, int64_t n_member, double *out, cudaStream_t s);
+void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bool check, cudaStream_t s);
+void dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,
+                                 bool check, bool aet, cudaStream_t s);
+void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s);
+void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,
+                         int32_t *status, cudaStream_t s);
+void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s);

@@ -1,0 +1,155 @@
+// dcp_physics.cuh — one HRU, one timestep: root zone -> unsaturated zone -> analytical
+// saturated-zone solver -> results_ac.  Shared by the streamed and the resident kernels.
+//
+// Two arithmetic policies:
+//   EXACT (FAST=false): the reference's operations in the reference's order, IEEE division, no FMA
+//          contraction (the TU is built with -fmad=false).  Differs from the CPU only through
+//          CUDA's exp/log (<= 1 ulp each).
+//   FAST  (FAST=true):  divisions by per-run / per-HRU constants become multiplications by hoisted
+//          reciprocals and 1/exp(-x) becomes exp(x).  Each substitution is <= ~1.5 ulp; measured
+//          drift on flows stays far inside the 1e-9 contract (tests/test_gpu_parity.py).
+#pragma once
+#include "dcp_device.cuh"
+
+struct HruConst {            // per (HRU, member) constants for one step
+    double ac, inv_ac;       // area, 1/area (FAST only)
+    double q0, q1, q2;       // q0, q0*cos, q0*cos*exp(-cos*smax/szm)  (dyna_satzone_analyticalsolver.f90:49-51)
+    double m2, inv_m2;       // szm/cos (:52), cos/szm (FAST only)
+    double srmax, inv_srmax, td, smax;
+    int ims_rz, ims_uz;
+};
+
+struct StepConst {
+    double dt, dtt, inv_dtt;
+    int ntt;
+};
+
+struct HruState {
+    double sd, suz, srz, qint1;
+};
+
+struct HruFlux {             // outputs of one step
+    double qbf;              // new baseflow per unit area
+    double ex;               // exs + exus   (dyna_results_ac.f90:34)
+    double ea;               // actual evapotranspiration of the step
+    double pex;              // root-zone excess
+    double exs1, exs2, exus; // checked mode: -sd part, (qbf-q0)*dtt part (dyna_satzone_analyticalsolver.f90:107-119)
+    int rz_bad;              // root-zone balance STOP condition (dyna_root_zone1.f90:73-77)
+};
+
+template <bool FAST, bool CHECK>
+__device__ __forceinline__ void hru_step(const HruConst &c, const StepConst &g, double p, double ep,
+                                         double qin, HruState &s, HruFlux &f) {
+    // ---------------- root_zone1 (RRMODEL/dyna_root_zone1.f90:32-77) ----------------
+    double pex = 0.0, ea = 0.0;
+    f.rz_bad = 0;
+    if (c.ims_rz == 1) {
+        const double storeini = s.srz;
+        double srz = s.srz + p;
+        if (srz > c.srmax) {
+            pex = srz - c.srmax;
+            srz = c.srmax;
+        }
+        double storeout = pex;
+        if (ep > 0.0) {
+            ea = FAST ? ep * (srz * c.inv_srmax) : ep * (srz / c.srmax);
+            if (ea > ep) ea = ep;
+            if (ea >= srz) ea = srz;
+            srz = srz - ea;
+            storeout = storeout + ea;
+        }
+        if (CHECK) {
+            const double storebal = storeini + p - storeout - srz;
+            if (storebal > DCP_F32_1EM10 || storebal < -1.0) f.rz_bad = 1;
+        }
+        s.srz = srz;
+    }
+    // ---------------- unsat_zone1 (RRMODEL/dyna_unsat_zone1.f90:40-86) ----------------
+    double uz = 0.0, exus = 0.0;
+    if (c.ims_uz == 1) {
+        double uz2 = 0.0;
+        double suz = s.suz + pex;
+        const double sd = s.sd;
+        if (sd <= 0.0 && suz > 0.0) {
+            exus = suz;
+            suz = 0.0;
+        } else if (sd > 0.0 && suz > sd) {
+            exus = suz - sd;
+            suz = sd;
+        }
+        if (sd > 0.0 && suz > 0.0) {
+            uz2 = g.dt * (suz / (sd * c.td));
+            if (uz2 > suz) uz2 = suz;
+            suz = suz - uz2;
+            if (suz < 0.0000001) {
+                uz2 = uz2 + suz;
+                suz = 0.0;
+            }
+        }
+        if (uz2 > 0.0) uz = FAST ? uz2 * g.inv_dtt : uz2 / g.dtt;
+        s.suz = suz;
+    }
+    // ---------------- satzone_analyticalsolver (RRMODEL/dyna_satzone_analyticalsolver.f90:49-131) ----
+    const double storeini = s.sd;
+    double sd = s.sd, qbf = 0.0;
+    const double qin_ac = FAST ? qin * c.inv_ac : qin / c.ac;
+    for (int itt = 1; itt <= g.ntt; ++itt) {
+        double qin2;
+        if (FAST)
+            qin2 = (g.ntt == 1) ? (s.qint1 + (qin - s.qint1)) * c.inv_ac
+                                : (s.qint1 + (double)itt * (qin - s.qint1) / (double)g.ntt) * c.inv_ac;
+        else
+            qin2 = (s.qint1 + (double)itt * (qin - s.qint1) / (double)g.ntt) / c.ac;      // :63
+        const double u = qin2 + uz;
+        const double u2 = c.q2 + u;
+        if (sd <= c.smax) {
+            if (u2 > 0.0) {
+                const double a = FAST ? (u2 * g.dtt) * c.inv_m2 : u2 * g.dtt / c.m2;
+                const double e1 = FAST ? exp(sd * c.inv_m2) : 1.0 / exp(-sd / c.m2);
+                if (a < DCP_F32_1EM10) {                                                   // :72-77
+                    const double b = FAST ? (c.q1 * g.dtt) * c.inv_m2 : c.q1 * g.dtt / c.m2;
+                    const double hb = FAST ? 0.5 * b : 0.5 * c.q1 * g.dtt / c.m2;
+                    sd = c.m2 * log((e1 + b) - a * (e1 - hb));
+                } else {                                                                   // :80
+                    const double r = c.q1 / u2;
+                    sd = c.m2 * log(r + (e1 - r) * exp(-a));
+                }
+            } else {                                                                       // :84
+                const double b = FAST ? (c.q1 * g.dtt) * c.inv_m2 : c.q1 * g.dtt / c.m2;
+                sd = c.m2 * log((FAST ? exp(sd * c.inv_m2) : exp(sd / c.m2)) + b);
+            }
+        } else {                                                                           // :86-95
+            const double tc = (sd - c.smax) / u;
+            if (tc > g.dtt) {
+                sd = sd - u * g.dtt;
+            } else {
+                const double t_temp = g.dtt - tc;
+                const double r = c.q1 / u2;
+                const double e1 = FAST ? exp(c.smax * c.inv_m2) : 1.0 / exp(-c.smax / c.m2);
+                const double a = FAST ? (u2 * t_temp) * c.inv_m2 : u2 * t_temp / c.m2;
+                sd = c.m2 * log(r + (e1 - r) * exp(-a));
+            }
+        }
+        qbf = (FAST ? (sd - storeini) * g.inv_dtt : (sd - storeini) / g.dtt) + uz + qin_ac;   // :98
+    }
+    double exs = 0.0, exs1 = 0.0, exs2 = 0.0;
+    if (sd < 0.0) {                                                                        // :107-112
+        exs = 0.0 - sd;
+        exs1 = exs;
+        sd = 0.0;
+    }
+    if (qbf > c.q0) {                                                                      // :115-119
+        exs2 = (qbf - c.q0) * g.dtt;
+        exs = exs + exs2;
+        qbf = c.q0;
+    }
+    s.sd = sd;
+    s.qint1 = qin;                                                                         // dyna_results_ac.f90:27
+    f.qbf = qbf;
+    f.ex = exs + exus;
+    f.ea = ea;
+    f.pex = pex;
+    f.exs1 = exs1;
+    f.exs2 = exs2;
+    f.exus = exus;
+}

@@ -1,0 +1,44 @@
+"""Comparators for GPU-vs-oracle parity (tolerances of BASELINE.md §5)."""
+import numpy as np
+
+RTOL = 1e-9      # north_star: flows and NSE/log-NSE within 1e-9 relative in FP64
+
+
+def compare_flows(q_gpu, q_ref, rtol=RTOL):
+    """q: (nriv, nstep, M).  Members whose oracle flows are non-finite are compared by class
+    (finite / non-finite per member) only.  Returns a dict of diagnostics; raises AssertionError."""
+    assert q_gpu.shape == q_ref.shape
+    M = q_ref.shape[2]
+    fin_ref = np.isfinite(q_ref).all(axis=(0, 1))
+    fin_gpu = np.isfinite(q_gpu).all(axis=(0, 1))
+    assert np.array_equal(fin_ref, fin_gpu), f"finite-class mismatch: ref {np.where(~fin_ref)[0]}, gpu {np.where(~fin_gpu)[0]}"
+    worst = 0.0
+    for m in np.where(fin_ref)[0]:
+        a, b = q_gpu[:, :, m], q_ref[:, :, m]
+        scale = np.abs(b).mean(axis=1, keepdims=True)            # per gauge series scale
+        err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * scale + 1e-300)
+        worst = max(worst, float(err.max()))
+    assert worst <= rtol, f"max relative flow error {worst:.3e} > {rtol:.1e}"
+    return dict(max_rel=worst, n_finite=int(fin_ref.sum()), n_members=M)
+
+
+def compare_perf(p_gpu, p_ref, rtol=RTOL):
+    nan_ref, nan_gpu = np.isnan(p_ref), np.isnan(p_gpu)
+    assert np.array_equal(nan_ref, nan_gpu), "NaN pattern of performance measures differs"
+    ok = ~nan_ref
+    if not ok.any():
+        return dict(max_rel=0.0)
+    # NSE = 1 - sse/sst: the contract is on the measure; compare 1-NSE (the accumulated ratio) relatively
+    a, b = 1.0 - p_gpu[ok], 1.0 - p_ref[ok]
+    err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    assert err.max() <= rtol, f"max relative error of (1 - measure) {err.max():.3e} > {rtol:.1e}"
+    return dict(max_rel=float(err.max()))
+
+
+def compare_close(a, b, rtol=RTOL, what=""):
+    a, b = np.asarray(a), np.asarray(b)
+    both_bad = ~np.isfinite(a) & ~np.isfinite(b)
+    err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
+    err = np.where(both_bad, 0.0, err)
+    assert np.nanmax(err) <= rtol and not np.isnan(err).any(), f"{what}: max rel err {np.nanmax(err):.3e}"
+    return float(np.nanmax(err))

@@ -1,0 +1,92 @@
+"""GPU (C ABI) vs CPU oracle on the same seeded inputs.  Tolerance: 1e-9 relative on flows and
+performance measures; sampled parameters, status words and srinit clipping bit-exact."""
+import numpy as np
+import pytest
+
+from decipher_b200 import synth
+from decipher_b200.capi import (DeviceCatchment, KERNEL_STREAMED, OPT_CHECK_BALANCE, OPT_FAST_MATH)
+from oracle_binding import oracle_run
+from parity import compare_close, compare_flows, compare_perf
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_both(cat, M, flags=0, kernel=KERNEL_STREAMED, **kw):
+    mc = synth.sample_parameters(cat.npt, M)
+    ref = oracle_run(cat, mc.copy(order="F"), flags=flags & OPT_CHECK_BALANCE, n_threads=8)
+    dev = DeviceCatchment(cat)
+    out = dev.run(mc.copy(order="F"), flags=flags, kernel=kernel, want_q=True, want_perf=True, want_totals=True, **kw)
+    dev.close()
+    return ref, out
+
+
+def _check(ref, out, rtol=1e-9, exact_status=True):
+    assert np.array_equal(ref["mcpar"], out["mcpar"]), "parameter sets (incl. srinit clip) must be bit-exact"
+    if exact_status:
+        assert np.array_equal(ref["status"], out["status"]), (ref["status"], out["status"])
+    d = compare_flows(out["q"], ref["q"], rtol)
+    compare_perf(out["perf"], ref["perf"], rtol)
+    fin = np.isfinite(ref["q"]).all(axis=(0, 1))
+    compare_close(out["reach_totals"][:, :, fin], ref["reach_totals"][:, :, fin], rtol, "reach totals")
+    compare_close(out["init_diag"][:, fin], ref["init_diag"][:, fin], rtol, "init diagnostics")
+    return d
+
+
+def test_c1_streamed_exact_checked():
+    """Config 1: example-like project, 10 members with the shipped seeds, balance checks on."""
+    cat = synth.synth_catchment("C1")
+    ref, out = _run_both(cat, 10, flags=OPT_CHECK_BALANCE)
+    d = _check(ref, out)
+    print("C1 exact:", d)
+    assert d["max_rel"] < 1e-10
+
+
+def test_c1_streamed_small_tiles():
+    """Time tiling must not change results (ring buffer + halo of the routing convolution)."""
+    cat = synth.synth_catchment("C1", nstep=3000)
+    ref, out = _run_both(cat, 10, steps_per_tile=97)
+    _check(ref, out)
+
+
+def test_c1_fast_math():
+    cat = synth.synth_catchment("C1")
+    ref, out = _run_both(cat, 10, flags=OPT_FAST_MATH)
+    d = _check(ref, out)
+    print("C1 fast:", d)
+
+
+def test_c2_subset_streamed():
+    """Config 2 catchment (500 HRUs, kW=8, 3 reaches), 2000 steps, 96 members, batches of 40."""
+    cat = synth.synth_catchment("C2", nstep=2000)
+    ref, out = _run_both(cat, 96, members_per_batch=40)
+    d = _check(ref, out)
+    print("C2 exact:", d)
+    ref, out = _run_both(cat, 96, flags=OPT_FAST_MATH)
+    d = _check(ref, out)
+    print("C2 fast:", d)
+
+
+def test_tree_network_multilayer_ntt():
+    """Branching river tree, 3 parameter layers, ntt = 3 sub-steps, daily timestep (dt = 24)."""
+    cat = synth.synth_catchment(nac=60, nriv=5, npt=3, ngp=3, nge=2, nstep=1500, kW=5, seed=77, tree=True, ntt=3, dt=24.0)
+    ref, out = _run_both(cat, 24, flags=OPT_CHECK_BALANCE)
+    _check(ref, out)
+
+
+def test_device_buffers_and_stats():
+    import torch
+    cat = synth.synth_catchment("C1", nstep=1000)
+    M = 64
+    mc = synth.sample_parameters(cat.npt, M)
+    ref = oracle_run(cat, mc.copy(order="F"), want_q=False, want_totals=False)
+    dev = DeviceCatchment(cat)
+    t_mc = torch.from_numpy(np.ascontiguousarray(mc.transpose(2, 1, 0))).cuda()     # (M, 7, npt) C-order == (npt,7,M) F-order
+    t_perf = torch.empty((M, cat.nriv, 2), dtype=torch.float64, device="cuda")
+    t_status = torch.empty(M, dtype=torch.int32, device="cuda")
+    st = dev.run_device(t_mc.data_ptr(), M, perf_ptr=t_perf.data_ptr(), status_ptr=t_status.data_ptr())
+    torch.cuda.synchronize()
+    perf = t_perf.cpu().numpy().transpose(2, 1, 0)
+    compare_perf(perf, ref["perf"])
+    assert np.array_equal(t_status.cpu().numpy(), ref["status"])
+    assert st["n_launches"] >= 5 and st["ms_total"] > 0 and st["ms_h2d"] < st["ms_total"]
+    dev.close()
