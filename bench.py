@@ -1,0 +1,324 @@
+#!/usr/bin/env python
+"""bench.py — member-HRU-timesteps/s of the DECIPHeR Monte-Carlo rainfall-runoff path on B200.
+
+Contract (driver): `python bench.py --gpus N --steps K --warmup W [--impl reference]`, one JSON line
+from rank 0.  For N>1 it is launched under torchrun (one rank per GPU, NCCL).
+
+Workload = BASELINE.json configs[1] ("C2"): synthetic 500-HRU catchment (kW=8, 3 gauged reaches,
+4 rain grids), hourly forcing, parameter sets sampled by RANMAR from the shipped params.dat bounds.
+One "step" = one pass of the hot path (init_satzone + build_hist + the Topmod time loop + routing +
+NSE/log-NSE) over one batch of `--members` ensemble members for `--nstep` timesteps.  Members are
+independent and identically sized, so throughput per unit does not depend on how the 10^5-member,
+87 600-step job is cut into such batches; `--nstep 87600` runs full-length simulations.
+
+  value  : device-resident inputs (parameters already in HBM, outputs left in HBM)
+  e2e    : the same call through host buffers (pinned), H2D of the parameter sets and D2H of the
+           performance measures / status words inside the timed region
+  roofline: FP64-pipe roofline of the physics kernel (the path is FP64-pipe bound, not HBM
+           or tensor bound); the HBM view (80 B/unit streamed-state figure) is reported beside it.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "member-HRU-timesteps/sec (MC ensemble)"
+UNIT = "member-HRU-timesteps/s"
+
+
+def algorithmic_flops_per_unit(cat, hist_len):
+    """131 + 3*kW + 5*kR + 2*T*nnode/nac weighted FP64 flops per member-HRU-step."""
+    kW = float(cat.ntrans.sum()) / cat.nac
+    kR = float((cat.rivers != 0).sum()) / cat.nac
+    return 131.0 + 3.0 * kW + 5.0 * kR + 2.0 * hist_len * cat.nnode / cat.nac
+
+
+def build_workload(args):
+    from decipher_b200 import synth
+    cfg = dict(synth.CONFIGS["C2"])
+    cfg.pop("members")
+    raw = synth.make_raw(**cfg)
+    if args.nstep < raw["nstep"]:                     # time window of the same 10-year forcing
+        n = args.nstep
+        raw["rain"] = np.asfortranarray(raw["rain"][:, :n])
+        raw["pet"] = np.asfortranarray(raw["pet"][:, :n])
+        raw["qobs"] = np.asfortranarray(raw["qobs"][:, :n])
+        raw["nstep"] = n
+    return synth.assemble(raw)
+
+
+def workload_config(args, cat, extra=None):
+    cfg = {"workload": "C2: synthetic 500-HRU catchment, 3 gauged reaches, kW=8, hourly forcing (10-year series), "
+                       "MC ensemble sampled with RANMAR seeds 5/2000 from RRMODEL_EXAMPLE_FILES/params.dat bounds",
+           "nac": cat.nac, "nriv": cat.nriv, "nstep_per_step": cat.nstep, "nstep_full_series": 87600,
+           "members_per_step_per_gpu": args.members, "ensemble_of_config": 100000,
+           "units_per_step_per_gpu": int(args.members) * cat.nac * cat.nstep}
+    if extra:
+        cfg.update(extra)
+    return cfg
+
+
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(gpu_index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, smax, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.f.read().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[1])); smax.append(float(parts[2])); pw.append(float(parts[3]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[4:8]):
+                if v.lower() == "active":
+                    reasons.add(n)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(pw)))
+        return out
+
+
+def cpu_baseline(cat, cores, flags=0):
+    """Times the oracle port on the host cores over a bounded member sample of the same workload."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from oracle_binding import oracle_run
+    from decipher_b200 import synth
+    per_thread = max(1, int(round(4.0e7 / (cat.nac * cat.nstep))))
+    n = cores * per_thread
+    mc = synth.sample_parameters(cat.npt, n)
+    t0 = time.perf_counter()
+    oracle_run(cat, mc, flags=flags, want_q=False, want_perf=True, want_totals=False, n_threads=cores)
+    dt = time.perf_counter() - t0
+    units = n * cat.nac * cat.nstep
+    return {"value": units / dt, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n} members x {cat.nac} HRUs x {cat.nstep} steps of the same catchment, "
+                      f"C++ oracle -O2 strict FP, {cores} threads over disjoint members, {dt:.1f} s"}, dt, units
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU path.  The Fortran sources cannot be compiled in this image
+    (no gfortran/flang/ifort), so this times the line-faithful C++ port on all host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cat = build_workload(args)
+    cores = os.cpu_count() or 1
+    vals, secs = [], []
+    info = None
+    for i in range(args.warmup + args.steps):
+        info, dt, units = cpu_baseline(cat, cores)
+        if i >= args.warmup:
+            vals.append(units); secs.append(dt)
+    value = sum(vals) / sum(secs)
+    info["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, cat, {"note": "bounded member sample per step, see cpu_baseline.sample"}),
+            "cpu_baseline": info,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--members", type=int, default=0, help="ensemble members per step per GPU (0 = kernel default)")
+    ap.add_argument("--nstep", type=int, default=0, help="timesteps simulated per step (0 = kernel default, 87600 = full)")
+    ap.add_argument("--kernel", default="auto", choices=["auto", "streamed", "resident"])
+    ap.add_argument("--math", default="exact", choices=["exact", "fast"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3 if args.impl == "ours" else 0)
+
+    if args.members <= 0:
+        args.members = 100000
+    if args.nstep <= 0:
+        args.nstep = 2190
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from decipher_b200 import synth
+    from decipher_b200 import capi
+    from decipher_b200.distributed import gather_to_rank0, shard_range
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the DECIPHeR B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    cat = build_workload(args)
+    dev = capi.DeviceCatchment(cat, device=local_rank)
+    M = args.members
+    # whole-job parameter table from ONE sequential RANMAR stream; this rank's contiguous slice
+    lo, hi = shard_range(M * world, rank, world)
+    table = synth.sample_parameters(cat.npt, M * world)
+    mine = np.ascontiguousarray(table[:, :, lo:hi].transpose(2, 1, 0))            # (M, 7, npt) == ABI layout
+    host_mc = torch.empty(mine.shape, dtype=torch.float64).pin_memory()
+    host_mc.copy_(torch.from_numpy(mine))
+    d_mc = host_mc.cuda()
+    d_work = torch.empty_like(d_mc)
+    d_perf = torch.empty((M, cat.nriv, capi.NMEASURE), dtype=torch.float64, device="cuda")
+    d_status = torch.empty(M, dtype=torch.int32, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")               # > 126 MB L2
+    kernel = {"auto": capi.KERNEL_AUTO, "streamed": capi.KERNEL_STREAMED, "resident": capi.KERNEL_RESIDENT}[args.kernel]
+    flags = capi.OPT_FAST_MATH if args.math == "fast" else 0
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device():
+        flush.zero_()                                  # L2 flush between timed iterations
+        d_work.copy_(d_mc)                             # srinit clip is in/out: fresh parameter sets each step
+        torch.cuda.synchronize()
+        st = dev.run_device(d_work.data_ptr(), M, perf_ptr=d_perf.data_ptr(), status_ptr=d_status.data_ptr(),
+                            flags=flags, kernel=kernel)
+        g_ms = 0.0
+        if world > 1:                                  # the only collective: gather of the measures to rank 0
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            gather_to_rank0(d_perf, M * world)
+            e1.record(); e1.synchronize()
+            g_ms = e0.elapsed_time(e1)
+        return st, g_ms
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    clocks = ClockSampler(local_rank)
+    wall0 = time.perf_counter()
+    ms_dev, ms_phys, n_phys, launches, ms_gather = 0.0, 0.0, 0, 0, 0.0
+    st = None
+    for _ in range(args.steps):
+        st, g_ms = step_device()
+        ms_dev += st["ms_total"] + g_ms
+        ms_gather += g_ms
+        ms_phys += st["ms_physics"]; n_phys += st["n_physics_launches"]; launches += st["n_launches"]
+    barrier()
+    wall_ms = (time.perf_counter() - wall0) * 1e3
+    clk = clocks.stop()
+
+    # e2e through the public host-buffer API (pinned parameter sets in, measures/status/diagnostics out)
+    h_np = host_mc.numpy().transpose(2, 1, 0)          # (npt, 7, M) Fortran-ordered view of the pinned buffer
+    work = torch.empty_like(host_mc).pin_memory()
+    w_np = work.numpy().transpose(2, 1, 0)
+    ms_e2e = 0.0
+    barrier()
+    for _ in range(args.steps):
+        flush.zero_()
+        work.copy_(host_mc)
+        torch.cuda.synchronize()
+        out = dev.run(w_np, flags=flags, kernel=kernel, want_q=False, want_perf=True, want_totals=False)
+        ms_e2e += out["stats"]["ms_total"]
+        if world > 1:
+            t_perf = torch.from_numpy(np.ascontiguousarray(out["perf"].transpose(2, 1, 0))).cuda()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(); gather_to_rank0(t_perf, M * world); e1.record(); e1.synchronize()
+            ms_e2e += e0.elapsed_time(e1)
+    barrier()
+    h2d = int(h_np.nbytes)
+    d2h = int(h_np.nbytes + out["perf"].nbytes + out["status"].nbytes + out["init_diag"].nbytes)
+
+    # max over ranks (device times)
+    t = torch.tensor([ms_dev, ms_e2e, wall_ms], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_dev_max, ms_e2e_max, wall_max = [float(x) for x in t.tolist()]
+    units_step_gpu = M * cat.nac * cat.nstep
+    units_total = units_step_gpu * world * args.steps
+    value = units_total / (ms_dev_max * 1e-3)
+    e2e_value = units_total / (ms_e2e_max * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        fp64_peak, _ = capi.measure_fp64_peak()        # dependency-free DFMA chains, TFLOP/s (measured live)
+        fpu = algorithmic_flops_per_unit(cat, st["hist_len"])
+        launch_ms = ms_phys / max(n_phys, 1)
+        units_per_launch = units_step_gpu * args.steps / max(n_phys, 1)
+        ach_tf = fpu * units_per_launch / (launch_ms * 1e-3) / 1e12
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        ach_gbs = 80.0 * units_per_launch / (launch_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, cat, {
+                "kernel": {1: "streamed", 2: "resident"}.get(st["kernel_used"], "?"), "math": args.math,
+                "l2": "256 MiB buffer written between timed steps (L2 flush)", "parallelism": f"members sharded over {world} GPU(s), no data-path collective; NCCL gather of NSE/log-NSE only"}),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+            "gpu_launches": int(launches),
+            "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
+                       "power_w_max": clk.get("power_w_max"), "samples": clk["samples"]},
+            "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach_tf / fp64_peak, "traffic": None,
+                         "kernel": "k_physics_" + {1: "streamed", 2: "resident"}.get(st["kernel_used"], "?"),
+                         "flops_per_unit": fpu, "units_per_launch": units_per_launch, "launch_ms": launch_ms,
+                         "peak_source": "dcp_measure_fp64_peak (DFMA chains, measured in this run; MEASURED_PEAKS.json has no FP64 figure)",
+                         "physics_share_of_step": ms_phys / max(ms_dev_max - ms_gather, 1e-9)},
+            "roofline_hbm": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                             "bytes_per_unit": 80.0, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650"},
+            "wall_ms_per_step": wall_max / args.steps, "gather_ms_per_step": ms_gather / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            info, _, _ = cpu_baseline(cat, os.cpu_count() or 1)
+            line["cpu_baseline"] = info
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
