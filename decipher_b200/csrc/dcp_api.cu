@@ -76,6 +76,10 @@ struct dcp_catchment {
     // host copies needed at run time
     std::vector<double> node_reach_dist, node_down_dist;
     bool has_qobs = false;
+    ResPlan plan{};                     // resident-kernel plan (plan.feasible == 0: streamed kernel only)
+    int n_sm = 148;
+    size_t smem_optin = 0;
+    std::string plan_why;               // why the resident kernel is not available
     dcp_run_stats stats{};
 };
 
@@ -272,11 +276,15 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
     DevCatchment &C = c->C;
     C.nac = nac; C.nriv = nriv; C.npt = npt; C.nstep = d->nstep; C.ngp = d->ngp; C.nge = d->nge; C.ntt = d->ntt;
     C.nnode = nnode; C.ncell = ncell;
-    C.dt = d->dt; C.dtt = d->dt / (double)d->ntt; C.log_dt = std::log(d->dt);
+    C.dt = d->dt; C.dtt = d->dt / (double)d->ntt; C.log_dt = std::log(d->dt); C.inv_dtt = 1.0 / C.dtt;
     C.nstep_obs = has_qobs ? d->nstep_obs : 0; C.t_warm = d->t_warm; C.flow_err = d->flow_err;
     c->has_qobs = has_qobs;
     c->node_reach_dist = reach_dist; c->node_down_dist = down_dist;
-    std::vector<double> rain(d->rain, d->rain + (size_t)d->ngp * d->nstep), pet(d->pet, d->pet + (size_t)d->nge * d->nstep);
+    // forcing zero-padded to whole TMA tiles (the resident kernel bulk-copies DCP_RES_TT steps at a time)
+    const size_t nstep_pad = ((size_t)d->nstep + DCP_FORCING_PAD - 1) / DCP_FORCING_PAD * DCP_FORCING_PAD + DCP_FORCING_PAD;
+    std::vector<double> rain((size_t)d->ngp * nstep_pad, 0.0), pet((size_t)d->nge * nstep_pad, 0.0);
+    std::copy(d->rain, d->rain + (size_t)d->ngp * d->nstep, rain.begin());
+    std::copy(d->pet, d->pet + (size_t)d->nge * d->nstep, pet.begin());
     std::vector<double> sum_ac_riv(d->sum_ac_riv, d->sum_ac_riv + nriv), qobs_start(d->qobs_start, d->qobs_start + nriv);
     cudaError_t e = cudaSuccess;
     auto up = [&](auto &vec, auto **dst) { if (e == cudaSuccess) e = upload(vec, dst, c->owned); };
@@ -287,6 +295,71 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
     up(node_input, &C.node_input); up(up_beg, &C.up_beg); up(up_idx, &C.up_idx); up(frac, &C.frac_sub_area);
     up(obs, &C.obs); up(tot_ppt, &C.tot_ppt); up(tot_pet, &C.tot_pet); up(tot_frac, &C.tot_frac);
     if (has_qobs) up(qobs, &C.qobs); else C.qobs = nullptr;
+    // ---------------- resident-kernel plan ----------------
+    {
+        cudaDeviceProp prop{};
+        cudaGetDeviceProperties(&prop, c->device);
+        c->n_sm = prop.multiProcessorCount;
+        c->smem_optin = prop.sharedMemPerBlockOptin;
+        ResPlan &P = c->plan;
+        P = ResPlan{};
+        int nac_pad = 32;
+        while (nac_pad < nac) nac_pad <<= 1;
+        const int S = DCP_RES_S;
+        if (nac_pad > DCP_RES_COMPUTE) c->plan_why = "nac > 512 HRUs";
+        else if (nac > 65535) c->plan_why = "nac > 65535";
+        else {
+            P.nac_pad = nac_pad; P.G = DCP_RES_COMPUTE / nac_pad; P.Mc = P.G * S; P.Tt = DCP_RES_TT; P.nnz = (int)w.size();
+            if (P.Mc * nriv > DCP_RES_MAXCHAIN) {           // fewer member sub-groups so the river warp can carry the chains
+                while (P.G > 1 && P.G * S * nriv > DCP_RES_MAXCHAIN) P.G >>= 1;
+                P.Mc = P.G * S;
+            }
+            if (P.Mc * nriv > DCP_RES_MAXCHAIN) c->plan_why = "too many rivers for the river warp";
+            else {
+                size_t off = 0;
+                auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
+                P.off_qbf = take((size_t)2 * P.G * nac_pad * S * 8);
+                P.off_ex = take((size_t)2 * P.Mc * nac_pad * 8);
+                P.off_cst = take((size_t)5 * P.G * nac_pad * S * 8);
+                P.off_par = take((size_t)P.Mc * npt * 6 * 8);
+                P.off_w = take((size_t)P.nnz * 8);
+                P.off_src = take((size_t)P.nnz * 2);
+                P.off_ac = take((size_t)nac_pad * 8);
+                P.off_forc = take((size_t)2 * P.Tt * (d->ngp + d->nge) * 8);
+                P.off_bar = take(16);
+                P.smem_bytes = (int)((off + 127) & ~(size_t)127);
+                if ((size_t)P.smem_bytes > c->smem_optin) {
+                    char buf[128];
+                    snprintf(buf, sizeof(buf), "needs %d B of shared memory per CTA (W has %d entries), device allows %zu",
+                             P.smem_bytes, P.nnz, c->smem_optin);
+                    c->plan_why = buf;
+                } else {
+                    // thread positions sorted by W row length (descending) so that the lanes of a warp walk rows of similar length
+                    std::vector<int32_t> order(nac), thread_hru(nac_pad, -1);
+                    for (int i = 0; i < nac; ++i) order[i] = i;
+                    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                        return (hru[a].row_end - hru[a].row_beg) > (hru[b].row_end - hru[b].row_beg); });
+                    for (int i = 0; i < nac; ++i) thread_hru[i] = order[i];
+                    std::vector<RivChain> rivq;
+                    std::vector<int32_t> rivq_beg(nriv + 1, 0), rivo, rivo_beg(nriv + 1, 0);
+                    for (int r = 0; r < nriv; ++r) {
+                        for (int ia = 0; ia < nac; ++ia) {
+                            const double sh = d->rivers[(size_t)r * nac + ia];
+                            if (sh != 0.0) { RivChain rc{}; rc.w_riv = hru[ia].w_riv; rc.share = sh; rc.ac = hru[ia].ac; rc.ia = ia; rivq.push_back(rc); }
+                            if (hru[ia].ipriv == r) rivo.push_back(ia);
+                        }
+                        rivq_beg[r + 1] = (int)rivq.size();
+                        rivo_beg[r + 1] = (int)rivo.size();
+                    }
+                    up(thread_hru, &P.thread_hru); up(rivq, &P.rivq); up(rivq_beg, &P.rivq_beg);
+                    up(rivo, &P.rivo); up(rivo_beg, &P.rivo_beg);
+                    P.feasible = 1;
+                    P.lean_ok = d->ntt == 1;
+                    for (int i = 0; i < nac; ++i) if (hru[i].ims_rz != 1 || hru[i].ims_uz != 1) P.lean_ok = 0;
+                }
+            }
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         const int code = fail(e == cudaErrorMemoryAllocation ? DCP_ERR_NOMEM : DCP_ERR_CUDA, "catchment upload failed: %s",
@@ -387,7 +460,6 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         if (opts->struct_size != (int)sizeof(dcp_run_opts)) return fail(DCP_ERR_INVALID, "dcp_run_opts.struct_size mismatch");
         o = *opts;
     }
-    if (o.kernel == DCP_KERNEL_RESIDENT) return fail(DCP_ERR_UNSUPPORTED, "resident kernel not built yet");
     CUDA_TRY(cudaSetDevice(c->device));
     const DevCatchment &C = c->C;
     const bool dev_io = (o.flags & DCP_OPT_DEVICE_BUFFERS) != 0;
@@ -395,59 +467,72 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     const bool fast = (o.flags & DCP_OPT_FAST_MATH) != 0;
     const bool aet = reach_totals != nullptr;
     const bool want_perf = perf_out != nullptr;
+    // kernel choice: the resident kernel whenever the catchment fits on chip; the balance checks
+    // (results_ts / root_zone1 STOP conditions) exist in the streamed kernel only
+    bool use_res = false;
+    if (o.kernel == DCP_KERNEL_RESIDENT) {
+        if (!c->plan.feasible) return fail(DCP_ERR_UNSUPPORTED, "resident kernel unavailable: %s", c->plan_why.c_str());
+        if (check) return fail(DCP_ERR_UNSUPPORTED, "DCP_OPT_CHECK_BALANCE needs the streamed kernel");
+        use_res = true;
+    } else if (o.kernel == DCP_KERNEL_AUTO) {
+        use_res = c->plan.feasible && !check;
+    } else if (o.kernel != DCP_KERNEL_STREAMED) {
+        return fail(DCP_ERR_INVALID, "unknown kernel selector %d", o.kernel);
+    }
     cudaStream_t s = c->stream;
     const size_t par_per_member = (size_t)C.npt * 7;
 
-    // ---- batch size from free memory ----
     size_t free_b = 0, total_b = 0;
     CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
     free_b += c->ws.cap + c->io.cap;            // our own slabs are reusable
-    int tile = o.steps_per_tile > 0 ? o.steps_per_tile : 1024;
+    const double mem_budget = 0.85 * (double)free_b;
+    // time tile: the resident kernel runs a member group through ALL steps in one launch
+    int tile = use_res ? C.nstep : (o.steps_per_tile > 0 ? o.steps_per_tile : 1024);
     tile = std::min(tile, C.nstep);
-    int64_t Bmax = o.members_per_batch > 0 ? o.members_per_batch : 131072;
+    const int wave = use_res ? c->n_sm * c->plan.Mc : 32;       // members that fill the GPU once
+    int64_t Bmax = o.members_per_batch > 0 ? o.members_per_batch : (use_res ? (int64_t)wave * 64 : 131072);
     Bmax = std::min<int64_t>(Bmax, n_member);
 
     c->stats = dcp_run_stats{};
-    c->stats.kernel_used = DCP_KERNEL_STREAMED;
+    c->stats.kernel_used = use_res ? DCP_KERNEL_RESIDENT : DCP_KERNEL_STREAMED;
     EventTimer tm(s);
     int64_t n_launch = 0, n_phys = 0;
     int hist_len_max = 0;
     DevBuf vmin_buf;
     CUDA_TRY(vmin_buf.reserve(sizeof(double)));
 
+    auto io_size = [&](int64_t B) {
+        size_t b = 256;
+        if (!dev_io) {
+            b += par_per_member * B * 8 + 256;
+            if (q_out) b += (size_t)C.nriv * C.nstep * B * 8 + 256;
+            if (want_perf) b += (size_t)DCP_NMEASURE * C.nriv * B * 8 + 256;
+            if (reach_totals) b += (size_t)3 * C.nriv * B * 8 + 256;
+            if (init_diag) b += (size_t)3 * B * 8 + 256;
+            if (status) b += (size_t)B * 4 + 256;
+        }
+        return b;
+    };
+    auto shrink = [&](int64_t B) {              // next smaller batch, whole waves when possible
+        int64_t nb = B / 2;
+        if (nb > wave) nb = nb / wave * wave;
+        return std::max<int64_t>(1, nb);
+    };
+
     for (int64_t m0 = 0; m0 < n_member;) {
         int64_t Bn = std::min<int64_t>(Bmax, n_member - m0);
-        // ---- stage parameters ----
-        tm.mark(T_H2D);
-        double *d_mcpar = nullptr;
-        size_t io_bytes = 0;
-        auto io_size = [&](int64_t B) {
-            size_t b = 256;
-            if (!dev_io) {
-                b += par_per_member * B * 8 + 256;
-                if (q_out) b += (size_t)C.nriv * C.nstep * B * 8 + 256;
-                if (want_perf) b += (size_t)DCP_NMEASURE * C.nriv * B * 8 + 256;
-                if (reach_totals) b += (size_t)3 * C.nriv * B * 8 + 256;
-                if (init_diag) b += (size_t)3 * B * 8 + 256;
-                if (status) b += (size_t)B * 4 + 256;
-            }
-            return b;
-        };
-        // v_min needs the parameters on the device: size io for the current guess of Bn first
-        {
-            // shrink Bn until the (io + workspace) estimate with a pessimistic ring fits; exact sizes follow
-            const double mem_budget = 0.85 * (double)free_b;
-            for (;;) {
-                DevBatch Wq{}; Wq.B = (int)Bn; Wq.Lcap = 1; Wq.R = 1;
-                const size_t fixed = carve_batch(nullptr, C, Wq, check, aet) + io_size(Bn);
-                if ((double)fixed < 0.6 * mem_budget || Bn <= 32) break;
-                Bn = std::max<int64_t>(32, Bn / 2);
-            }
+        // ---- first guess of the batch size: everything except the (still unknown) histogram length ----
+        for (;;) {
+            DevBatch Wq{}; Wq.B = (int)Bn; Wq.Lcap = 1; Wq.R = use_res ? C.nstep : tile + 64;
+            const size_t fixed = carve_batch(nullptr, C, Wq, check, aet) + io_size(Bn);
+            if ((double)fixed < 0.9 * mem_budget || Bn <= 1) break;
+            Bn = shrink(Bn);
         }
-        io_bytes = io_size(Bn);
+        const size_t io_bytes = io_size(Bn);
         CUDA_TRY(c->io.reserve(io_bytes));
+        tm.mark(T_H2D);
         Carver iocv(c->io.p);
-        double *d_q = nullptr, *d_perf = nullptr, *d_tot = nullptr, *d_diag = nullptr;
+        double *d_mcpar = nullptr, *d_q = nullptr, *d_perf = nullptr, *d_tot = nullptr, *d_diag = nullptr;
         int32_t *d_status = nullptr;
         if (dev_io) {
             d_mcpar = mcpar + m0 * par_per_member;
@@ -488,14 +573,18 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         W.Lcap = (int)std::ceil(max_reach) + 3;
         const int Tcap = (int)std::ceil(max_full) + 3;
         hist_len_max = std::max(hist_len_max, Tcap - 2);
-        int R = 1;
-        while (R < tile + Tcap + 1) R <<= 1;
-        W.R = R;
+        if (use_res || tile >= C.nstep) {        // whole series resident in the flow buffers: no ring
+            W.R = C.nstep; W.Rmask = 0x7fffffff;
+        } else {
+            int R = 1;
+            while (R < tile + Tcap + 1) R <<= 1;
+            W.R = R; W.Rmask = R - 1;
+        }
         const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet);
-        if ((double)(ws_bytes + io_bytes) > 0.92 * (double)free_b) {
-            if (Bn <= 32) return fail(DCP_ERR_NOMEM, "batch of 32 members needs %zu MB, device has %zu MB free",
-                                      (ws_bytes + io_bytes) >> 20, free_b >> 20);
-            Bmax = std::max<int64_t>(32, Bn / 2);   // retry this batch smaller
+        if ((double)(ws_bytes + io_bytes) > mem_budget) {
+            if (Bn <= 1) return fail(DCP_ERR_NOMEM, "one member needs %zu MB, device has %zu MB free",
+                                     (ws_bytes + io_bytes) >> 20, free_b >> 20);
+            Bmax = shrink(Bn);                  // retry this batch smaller
             continue;
         }
         CUDA_TRY(c->ws.reserve(ws_bytes));
@@ -503,12 +592,22 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
 
         tm.mark(T_INIT);
         dcp_launch_init(C, W, d_mcpar, check, s); ++n_launch;
-        for (int t0 = 0; t0 < C.nstep; t0 += tile) {
-            const int t1 = std::min(C.nstep, t0 + tile);
+        if (use_res) {
+            ResPlan P = c->plan;
+            P.n_groups = (int)((Bn + P.Mc - 1) / P.Mc);
             tm.mark(T_PHYS);
-            dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s); ++n_launch; ++n_phys;
+            CUDA_TRY(dcp_launch_physics_resident(C, W, P, fast, aet, std::min(c->n_sm, P.n_groups), s));
+            ++n_launch; ++n_phys;
             tm.mark(T_ROUTE);
-            dcp_launch_route(C, W, t0, t1, d_q, s); n_launch += 2;
+            dcp_launch_route(C, W, 0, C.nstep, d_q, s); n_launch += 2;
+        } else {
+            for (int t0 = 0; t0 < C.nstep; t0 += tile) {
+                const int t1 = std::min(C.nstep, t0 + tile);
+                tm.mark(T_PHYS);
+                dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s); ++n_launch; ++n_phys;
+                tm.mark(T_ROUTE);
+                dcp_launch_route(C, W, t0, t1, d_q, s); n_launch += 2;
+            }
         }
         tm.mark(T_FIN);
         dcp_launch_finalize(C, W, d_perf, d_tot, d_diag, d_status, s); ++n_launch;

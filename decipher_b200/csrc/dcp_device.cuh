@@ -54,7 +54,7 @@ struct ObsStat {                    // per gauge, host-computed once (member ind
 // Everything a kernel needs; passed by value (fits in the 4 KB parameter space).
 struct DevCatchment {
     int32_t nac, nriv, npt, nstep, ngp, nge, ntt, nnode, ncell;
-    double dt, dtt, log_dt;
+    double dt, dtt, log_dt, inv_dtt;
     const HruStatic *hru;           // [nac]
     const WEntry *w;                // gather CSR
     const RivEntry *riv;            // river CSR
@@ -83,7 +83,8 @@ struct DevCatchment {
 struct DevBatch {
     int32_t B;                      // members in this batch
     int32_t Lcap;                   // bins reserved per node histogram
-    int32_t R;                      // ring length (power of two) of qout / y in time
+    int32_t R;                      // length in time of the qout / y buffers
+    int32_t Rmask;                  // R-1 when R is a power of two used as a ring; 0x7fffffff when R >= nstep (no wrap)
     double *par;                    // [7][npt][B]  szm,lnto,srmax,srinit,chv,td,smax
     double *t0dt;                   // [npt][B]
     // state [nac][B]
@@ -103,4 +104,29 @@ struct DevBatch {
     // per member
     int32_t *status;                // [B]
     double *diag;                   // [3][B]
+};
+
+// ---- resident (persistent, on-chip state) kernel ------------------------------------------------
+struct __align__(8) RivChain {      // one term of qb(r): (((dtt*qbf(ia))*w_riv)*share)*ac   (dyna_dynamic_dist.f90:59-61)
+    double w_riv, share, ac;
+    int32_t ia;
+    int32_t pad;
+};
+
+struct ResPlan {
+    int32_t feasible;
+    int32_t lean_ok;                // every HRU has ims_rz == ims_uz == 1 and ntt == 1: the branch-free step applies
+    int32_t nac_pad;                // HRUs per member, padded to a power of two <= 512
+    int32_t G;                      // member sub-groups side by side in one CTA (512 / nac_pad)
+    int32_t Mc;                     // members per CTA = G * S
+    int32_t n_groups;               // ceil(B / Mc), set per launch
+    int32_t Tt;                     // forcing tile (timesteps) per TMA bulk copy
+    int32_t nnz;                    // W entries
+    int32_t smem_bytes;
+    int32_t off_qbf, off_ex, off_cst, off_par, off_w, off_src, off_ac, off_forc, off_bar;
+    const int32_t *thread_hru;      // [nac_pad] HRU handled at each thread position (-1 = idle), sorted by W row length
+    const RivChain *rivq;           // river CSR for qb, per river ascending HRU
+    const int32_t *rivq_beg;        // [nriv+1]
+    const int32_t *rivo;            // HRUs by ipriv, ascending
+    const int32_t *rivo_beg;        // [nriv+1]
 };

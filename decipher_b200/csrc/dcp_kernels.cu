@@ -260,7 +260,7 @@ k_physics_streamed(DevCatchment C, DevBatch W, int t0, int t1) {
     double *s_qof = s_acc + (size_t)nriv * nthr + threadIdx.x;
 
     StepConst g;
-    g.dt = C.dt; g.dtt = C.dtt; g.inv_dtt = 1.0 / C.dtt; g.ntt = C.ntt;
+    g.dt = C.dt; g.dtt = C.dtt; g.inv_dtt = C.inv_dtt; g.ntt = C.ntt;
 
     // parameters of layer 0 hoisted when there is a single layer
     double p_szm = 0, p_srmax = 0, p_td = 0, p_smax = 0;
@@ -356,7 +356,7 @@ k_physics_streamed(DevCatchment C, DevBatch W, int t0, int t1) {
             }
         }
         // river (dyna_river.f90:42-49): qout = qb + qof
-        double *qo = W.qout + ((size_t)(t & (W.R - 1)) * nriv) * B + m;
+        double *qo = W.qout + ((size_t)(t & W.Rmask) * nriv) * B + m;
         double k_qb = 0, k_qof = 0, k_out = 0;
         for (int r = 0; r < nriv; ++r) {
             const double qb = s_qb[r * nthr], qof = s_qof[r * nthr];
@@ -400,7 +400,7 @@ k_route_conv(DevCatchment C, DevBatch W, int t0, int t1) {
     const int riv = C.node_input[n];
     const int bins = W.hbins[n * (size_t)B + m];
     const double *dh = W.dh + (size_t)n * W.Lcap * B + m;
-    const int Rm = W.R - 1;
+    const int Rm = W.Rmask;
     for (int t = t0; t < t1; ++t) {
         double y = 0.0;
         if (riv >= 0) {
@@ -424,7 +424,7 @@ k_route_conv(DevCatchment C, DevBatch W, int t0, int t1) {
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ double node_at_column(const DevCatchment &C, const DevBatch &W, int m, int u,
                                                  int col, int t) {
-    const int B = W.B, Rm = W.R - 1;
+    const int B = W.B, Rm = W.Rmask;
     const int hs = W.hstart[u * (size_t)B + m];
     const int bins = W.hbins[u * (size_t)B + m];
     if (bins <= 0) return 0.0;

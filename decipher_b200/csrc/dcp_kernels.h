@@ -3,6 +3,12 @@
 #include "dcp_device.cuh"
 
 #define DCP_STREAM_THREADS 128
+#define DCP_RES_S 4                  // member slots per compute thread of the resident kernel
+#define DCP_RES_LG 1                 // member slots interleaved per basic block in the lean step
+#define DCP_RES_COMPUTE 512
+#define DCP_RES_MAXCHAIN 128         // (members per CTA) x nriv chains the river warp can carry
+#define DCP_RES_TT 64                // forcing tile length (timesteps)
+#define DCP_FORCING_PAD 64           // forcing arrays are zero-padded to a multiple of this many steps
 
 void dcp_launch_min_chv(const double *mcpar, int npt, int64_t n_member, double *out, cudaStream_t s);
 void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bool check, cudaStream_t s);
@@ -12,3 +18,5 @@ void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, 
 void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,
                          int32_t *status, cudaStream_t s);
 void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s);
+cudaError_t dcp_launch_physics_resident(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast,
+                                        bool aet, int grid, cudaStream_t s);

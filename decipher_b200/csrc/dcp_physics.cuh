@@ -10,6 +10,7 @@
 //          drift on flows stays far inside the 1e-9 contract (tests/test_gpu_parity.py).
 #pragma once
 #include "dcp_device.cuh"
+#include "dcp_fastmath.cuh"
 
 struct HruConst {            // per (HRU, member) constants for one step
     double ac, inv_ac;       // area, 1/area (FAST only)
@@ -152,4 +153,131 @@ __device__ __forceinline__ void hru_step(const HruConst &c, const StepConst &g, 
     f.exs1 = exs1;
     f.exs2 = exs2;
     f.exus = exus;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Generic saturated-zone step alone (slow path of the lean step below): the sat-zone statements of
+// hru_step<true, false>, kept out of line and fed by value so the hot loop holds no addressable structs.
+// ------------------------------------------------------------------------------------------------
+struct SatOut { double sd, qbf, exs; };
+
+static __device__ __noinline__ SatOut sat_zone_slow(double inv_ac, double q0, double q1, double q2, double m2, double inv_m2,
+                                             double smax, double dtt, double inv_dtt, int ntt, double qin, double uz,
+                                             double qint1, double sd) {
+    const double storeini = sd;
+    double qbf = 0.0;
+    const double qin_ac = qin * inv_ac;
+    for (int itt = 1; itt <= ntt; ++itt) {
+        const double qin2 = (ntt == 1) ? (qint1 + (qin - qint1)) * inv_ac
+                                       : (qint1 + (double)itt * (qin - qint1) / (double)ntt) * inv_ac;
+        const double u = qin2 + uz;
+        const double u2 = q2 + u;
+        if (sd <= smax) {
+            if (u2 > 0.0) {
+                const double a = (u2 * dtt) * inv_m2;
+                const double e1 = exp(sd * inv_m2);
+                if (a < DCP_F32_1EM10) {
+                    const double b = (q1 * dtt) * inv_m2;
+                    sd = m2 * log((e1 + b) - a * (e1 - 0.5 * b));
+                } else {
+                    const double r = q1 / u2;
+                    sd = m2 * log(r + (e1 - r) * exp(-a));
+                }
+            } else {
+                sd = m2 * log(exp(sd * inv_m2) + (q1 * dtt) * inv_m2);
+            }
+        } else {
+            const double tc = (sd - smax) / u;
+            if (tc > dtt) {
+                sd = sd - u * dtt;
+            } else {
+                const double r = q1 / u2;
+                sd = m2 * log(r + (exp(smax * inv_m2) - r) * exp(-((u2 * (dtt - tc)) * inv_m2)));
+            }
+        }
+        qbf = (sd - storeini) * inv_dtt + uz + qin_ac;
+    }
+    double exs = 0.0;
+    if (sd < 0.0) { exs = 0.0 - sd; sd = 0.0; }
+    if (qbf > q0) { exs = exs + (qbf - q0) * dtt; qbf = q0; }
+    SatOut o; o.sd = sd; o.qbf = qbf; o.exs = exs;
+    return o;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LEAN path of the FAST policy: the same model equations written branch-free (selects instead of
+// branches, fm_exp / fm_log / fm_rcp instead of the library calls) so that several member slots
+// interleave in one basic block and the FP64 pipe stays busy.  Preconditions (checked by the caller,
+// who otherwise uses hru_step<true,...>): ims_rz == ims_uz == 1, ntt == 1, epp = max(ep, 0).
+// The regular and the small-u2 branch of the solver (dyna_satzone_analyticalsolver.f90:72-84) are both
+// evaluated and selected; everything else (sd > smax, arguments outside the fast exp range) raises
+// `slow`, and the caller re-runs the saturated zone of that lane with sat_zone_generic.
+// Outputs uz and exus are returned so that the slow path can be completed.
+// ------------------------------------------------------------------------------------------------
+struct LeanOut {
+    double qbf, exac, ea, uz, exus, sd0;
+    bool slow;
+};
+
+__device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst &g, double p, double epp,
+                                              double qin, HruState &s, LeanOut &o) {
+    // root_zone1 (dyna_root_zone1.f90:39-66)
+    double srz = s.srz + p;
+    const double pex = fmax(srz - c.srmax, 0.0);
+    srz = fmin(srz, c.srmax);
+    double ea = epp * (srz * c.inv_srmax);
+    ea = fmin(fmin(ea, epp), srz);
+    srz = srz - ea;
+    // unsat_zone1 (dyna_unsat_zone1.f90:49-78)
+    const double sd0 = s.sd;
+    double suz = s.suz + pex;
+    const double lim = fmax(sd0, 0.0);
+    const double exus = fmax(suz - lim, 0.0);
+    suz = fmin(suz, lim);
+    const double den = sd0 * c.td;
+    double uz2 = g.dt * (suz * fm_rcp(den));
+    uz2 = (den > 1e-290) ? fmin(uz2, suz) : suz;         // tiny sd*td: suz/(sd*td) overflows, clipped to suz
+    uz2 = (sd0 > 0.0 && suz > 0.0) ? uz2 : 0.0;
+    suz = suz - uz2;
+    const bool flush = suz < 0.0000001;
+    uz2 = flush ? uz2 + suz : uz2;
+    suz = flush ? 0.0 : suz;
+    const double uz = uz2 * g.inv_dtt;
+    // satzone_analyticalsolver (dyna_satzone_analyticalsolver.f90:60-119), ntt == 1
+    const double qin_ac = qin * c.inv_ac;
+    const double qin2 = (s.qint1 + (qin - s.qint1)) * c.inv_ac;
+    const double u = qin2 + uz;
+    const double u2 = c.q2 + u;
+    const double a = (u2 * g.dtt) * c.inv_m2;
+    const double x1 = sd0 * c.inv_m2;
+    const double e1 = fm_exp(x1);
+    const double r = c.q1 * fm_rcp(u2);
+    const double e2 = fm_exp(-a);
+    const double b = (c.q1 * g.dtt) * c.inv_m2;
+    const double arg_small = (e1 + b) - a * (e1 - 0.5 * b);      // :76-77 (and :84 when u2 == 0)
+    const double arg_reg = fma(e1 - r, e2, r);                    // :80
+    const double arg = (a < DCP_F32_1EM10) ? arg_small : arg_reg;
+    double sd = c.m2 * fm_log(arg);
+    o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !(arg > 1e-290 && arg < 1e290);
+    double qbf = (sd - sd0) * g.inv_dtt + uz + qin_ac;            // :98
+    double exs = fmax(-sd, 0.0);                                  // :107-112
+    sd = fmax(sd, 0.0);
+    const double over = fmax(qbf - c.q0, 0.0);                    // :115-119
+    exs = fma(over, g.dtt, exs);
+    qbf = fmin(qbf, c.q0);
+    s.sd = sd; s.suz = suz; s.srz = srz; s.qint1 = qin;
+    o.qbf = qbf;
+    o.exac = (exs + exus) * c.ac;
+    o.ea = ea; o.uz = uz; o.exus = exus; o.sd0 = sd0;
+}
+
+// completes a lane whose lean step raised `slow`: redo the saturated zone from the saved inputs
+__device__ __forceinline__ void hru_step_lean_fixup(const HruConst &c, const StepConst &g, double qin,
+                                                    double qint1_old, double &sd_state, LeanOut &o) {
+    const SatOut r = sat_zone_slow(c.inv_ac, c.q0, c.q1, c.q2, c.m2, c.inv_m2, c.smax, g.dtt, g.inv_dtt, g.ntt, qin,
+                                   o.uz, qint1_old, o.sd0);
+    sd_state = r.sd;
+    o.qbf = r.qbf;
+    const double ex = r.exs + o.exus;
+    o.exac = (ex > 0.0) ? ex * c.ac : 0.0;
 }

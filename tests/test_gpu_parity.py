@@ -90,3 +90,47 @@ def test_device_buffers_and_stats():
     assert np.array_equal(t_status.cpu().numpy(), ref["status"])
     assert st["n_launches"] >= 5 and st["ms_total"] > 0 and st["ms_h2d"] < st["ms_total"]
     dev.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# resident (persistent, on-chip state) kernel
+# ---------------------------------------------------------------------------------------------
+from decipher_b200.capi import KERNEL_RESIDENT  # noqa: E402
+
+
+def test_resident_c1_exact_and_fast():
+    """nac=24 -> 16 member sub-groups per CTA, 3 parameter layers, ragged last group (M=70)."""
+    cat = synth.synth_catchment("C1", nstep=2500)
+    ref, out = _run_both(cat, 70, kernel=KERNEL_RESIDENT)
+    assert out["stats"]["kernel_used"] == KERNEL_RESIDENT
+    d = _check(ref, out)
+    print("resident C1 exact:", d)
+    assert d["max_rel"] < 1e-10
+    ref, out = _run_both(cat, 70, flags=OPT_FAST_MATH, kernel=KERNEL_RESIDENT)
+    print("resident C1 fast:", _check(ref, out))
+
+
+def test_resident_c2_subset():
+    """Config 2 catchment (500 HRUs -> one HRU per compute thread, 4 members per CTA), 1500 steps,
+    150 members = 38 member groups over the persistent grid (last group ragged)."""
+    cat = synth.synth_catchment("C2", nstep=1500)
+    ref, out = _run_both(cat, 150, kernel=KERNEL_RESIDENT)
+    assert out["stats"]["kernel_used"] == KERNEL_RESIDENT and out["stats"]["n_physics_launches"] == 1
+    d = _check(ref, out)
+    print("resident C2 exact:", d)
+    ref, out = _run_both(cat, 150, flags=OPT_FAST_MATH, kernel=KERNEL_RESIDENT)
+    print("resident C2 fast:", _check(ref, out))
+
+
+def test_resident_matches_streamed_bitwise_in_exact_mode():
+    """Both kernels evaluate the same operations in the same order: exact mode must agree to the bit."""
+    cat = synth.synth_catchment(nac=100, nriv=3, npt=2, ngp=2, nge=1, nstep=700, kW=6, seed=11, tree=True)
+    mc = synth.sample_parameters(cat.npt, 40)
+    dev = DeviceCatchment(cat)
+    a = dev.run(mc.copy(order="F"), kernel=KERNEL_STREAMED, want_q=True, want_totals=True)
+    b = dev.run(mc.copy(order="F"), kernel=KERNEL_RESIDENT, want_q=True, want_totals=True)
+    dev.close()
+    assert np.array_equal(a["q"], b["q"], equal_nan=True)
+    assert np.array_equal(a["perf"], b["perf"], equal_nan=True)
+    assert np.array_equal(a["reach_totals"], b["reach_totals"], equal_nan=True)
+    assert np.array_equal(a["status"], b["status"])
