@@ -12,6 +12,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <vector>
@@ -305,58 +306,61 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
         P = ResPlan{};
         int nac_pad = 32;
         while (nac_pad < nac) nac_pad <<= 1;
-        const int S = DCP_RES_S;
-        if (nac_pad > DCP_RES_COMPUTE) c->plan_why = "nac > 512 HRUs";
-        else if (nac > 65535) c->plan_why = "nac > 65535";
+        const int S = DCP_RES_S, CT = DCP_RES_COMPUTE;
+        if (nac_pad > CT) c->plan_why = "nac > 512 HRUs";
         else {
-            P.nac_pad = nac_pad; P.G = DCP_RES_COMPUTE / nac_pad; P.Mc = P.G * S; P.Tt = DCP_RES_TT; P.nnz = (int)w.size();
-            if (P.Mc * nriv > DCP_RES_MAXCHAIN) {           // fewer member sub-groups so the river warp can carry the chains
-                while (P.G > 1 && P.G * S * nriv > DCP_RES_MAXCHAIN) P.G >>= 1;
-                P.Mc = P.G * S;
-            }
-            if (P.Mc * nriv > DCP_RES_MAXCHAIN) c->plan_why = "too many rivers for the river warp";
-            else {
-                size_t off = 0;
-                auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
-                P.off_qbf = take((size_t)2 * P.G * nac_pad * S * 8);
-                P.off_ex = take((size_t)2 * P.Mc * nac_pad * 8);
-                P.off_cst = take((size_t)5 * P.G * nac_pad * S * 8);
-                P.off_par = take((size_t)P.Mc * npt * 6 * 8);
-                P.off_w = take((size_t)P.nnz * 8);
-                P.off_src = take((size_t)P.nnz * 2);
-                P.off_ac = take((size_t)nac_pad * 8);
-                P.off_forc = take((size_t)2 * P.Tt * (d->ngp + d->nge) * 8);
-                P.off_bar = take(16);
-                P.smem_bytes = (int)((off + 127) & ~(size_t)127);
-                if ((size_t)P.smem_bytes > c->smem_optin) {
-                    char buf[128];
-                    snprintf(buf, sizeof(buf), "needs %d B of shared memory per CTA (W has %d entries), device allows %zu",
-                             P.smem_bytes, P.nnz, c->smem_optin);
-                    c->plan_why = buf;
-                } else {
-                    // thread positions sorted by W row length (descending) so that the lanes of a warp walk rows of similar length
-                    std::vector<int32_t> order(nac), thread_hru(nac_pad, -1);
-                    for (int i = 0; i < nac; ++i) order[i] = i;
-                    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-                        return (hru[a].row_end - hru[a].row_beg) > (hru[b].row_end - hru[b].row_beg); });
-                    for (int i = 0; i < nac; ++i) thread_hru[i] = order[i];
-                    std::vector<RivChain> rivq;
-                    std::vector<int32_t> rivq_beg(nriv + 1, 0), rivo, rivo_beg(nriv + 1, 0);
-                    for (int r = 0; r < nriv; ++r) {
-                        for (int ia = 0; ia < nac; ++ia) {
-                            const double sh = d->rivers[(size_t)r * nac + ia];
-                            if (sh != 0.0) { RivChain rc{}; rc.w_riv = hru[ia].w_riv; rc.share = sh; rc.ac = hru[ia].ac; rc.ia = ia; rivq.push_back(rc); }
-                            if (hru[ia].ipriv == r) rivo.push_back(ia);
-                        }
-                        rivq_beg[r + 1] = (int)rivq.size();
-                        rivo_beg[r + 1] = (int)rivo.size();
-                    }
-                    up(thread_hru, &P.thread_hru); up(rivq, &P.rivq); up(rivq_beg, &P.rivq_beg);
-                    up(rivo, &P.rivo); up(rivo_beg, &P.rivo_beg);
-                    P.feasible = 1;
-                    P.lean_ok = d->ntt == 1;
-                    for (int i = 0; i < nac; ++i) if (hru[i].ims_rz != 1 || hru[i].ims_uz != 1) P.lean_ok = 0;
+            P.nac_pad = nac_pad; P.G = CT / nac_pad; P.Tt = DCP_RES_TT; P.nnz = (int)w.size();
+            while (P.G > 1 && P.G * S * nriv > DCP_RES_MAXPAIRS) P.G >>= 1;    // river lanes carry 2 chains per (member, river)
+            P.Mc = P.G * S;
+            std::vector<RivChain> rivq;
+            std::vector<int32_t> rivq_beg(nriv + 1, 0), rivo, rivo_beg(nriv + 1, 0);
+            for (int r = 0; r < nriv; ++r) {
+                for (int ia = 0; ia < nac; ++ia) {
+                    const double sh = d->rivers[(size_t)r * nac + ia];
+                    if (sh != 0.0) { RivChain rc{}; rc.w_riv = hru[ia].w_riv; rc.share = sh; rc.ac = hru[ia].ac; rc.ia = ia; rivq.push_back(rc); }
+                    if (hru[ia].ipriv == r) rivo.push_back(ia);
                 }
+                rivq_beg[r + 1] = (int)rivq.size();
+                rivo_beg[r + 1] = (int)rivo.size();
+            }
+            P.nq = (int)rivq.size();
+            const int n_chains = 2 * P.Mc * nriv;
+            P.n_threads = CT + 128;
+            P.river_team = 1;
+            while (P.river_team < 16 && 2 * P.river_team * n_chains <= 128) P.river_team <<= 1;
+            size_t off = 0;
+            auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
+            P.off_qbf = take((size_t)2 * P.G * nac_pad * S * 8);
+            P.off_ex = take((size_t)2 * S * CT * 8);
+            P.off_cst = take((size_t)5 * S * CT * 8);
+            P.off_par = take((size_t)P.Mc * npt * 6 * 8);
+            P.off_w = take((size_t)P.nnz * 8);
+            P.off_src = take((size_t)P.nnz * 2);
+            P.off_ac = take((size_t)nac_pad * 8);
+            P.off_forc = take((size_t)2 * P.Tt * (d->ngp + d->nge) * 8);
+            P.off_bar = take(16);
+            P.off_rqc = take((size_t)3 * (P.nq + 1) * 8);
+            P.off_rq = take((size_t)P.nq * 2);
+            P.off_ro = take((size_t)nac * 2);
+            P.smem_bytes = (int)((off + 127) & ~(size_t)127);
+            if (P.Mc * nriv > DCP_RES_MAXPAIRS) c->plan_why = "too many rivers for the river warps";
+            else if ((size_t)P.smem_bytes > c->smem_optin) {
+                char buf[160];
+                snprintf(buf, sizeof(buf), "needs %d B of shared memory per CTA (W has %d entries), device allows %zu",
+                         P.smem_bytes, P.nnz, c->smem_optin);
+                c->plan_why = buf;
+            } else {
+                // thread positions sorted by W row length (descending): the lanes of a warp walk rows of similar length
+                std::vector<int32_t> order(nac), thread_hru(nac_pad, -1), hru_pos(nac, 0);
+                for (int i = 0; i < nac; ++i) order[i] = i;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                    return (hru[a].row_end - hru[a].row_beg) > (hru[b].row_end - hru[b].row_beg); });
+                for (int i = 0; i < nac; ++i) { thread_hru[i] = order[i]; hru_pos[order[i]] = i; }
+                up(thread_hru, &P.thread_hru); up(hru_pos, &P.hru_pos); up(rivq, &P.rivq); up(rivq_beg, &P.rivq_beg);
+                up(rivo, &P.rivo); up(rivo_beg, &P.rivo_beg);
+                P.feasible = 1;
+                P.lean_ok = d->ntt == 1;
+                for (int i = 0; i < nac; ++i) if (hru[i].ims_rz != 1 || hru[i].ims_uz != 1) P.lean_ok = 0;
             }
         }
     }
@@ -595,9 +599,23 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         if (use_res) {
             ResPlan P = c->plan;
             P.n_groups = (int)((Bn + P.Mc - 1) / P.Mc);
+            const int grid = std::min(c->n_sm, P.n_groups);
+            DevBuf dbg;
+            if (getenv("DCP_RES_DEBUG")) { CUDA_TRY(dbg.reserve((size_t)grid * 20 * 8)); CUDA_TRY(cudaMemsetAsync(dbg.p, 0, (size_t)grid * 20 * 8, s)); P.dbg = (long long *)dbg.p; }
             tm.mark(T_PHYS);
-            CUDA_TRY(dcp_launch_physics_resident(C, W, P, fast, aet, std::min(c->n_sm, P.n_groups), s));
+            CUDA_TRY(dcp_launch_physics_resident(C, W, P, fast, aet, grid, s));
             ++n_launch; ++n_phys;
+            if (P.dbg) {           // per-warp busy cycles of the persistent kernel (tuning aid)
+                std::vector<long long> hb((size_t)grid * 20);
+                CUDA_TRY(cudaMemcpyAsync(hb.data(), dbg.p, hb.size() * 8, cudaMemcpyDeviceToHost, s));
+                CUDA_TRY(cudaStreamSynchronize(s));
+                for (int b = 0; b < std::min(grid, 3); ++b) {
+                    fprintf(stderr, "[dcp resident dbg] cta %d busy Mcycles per warp:", b);
+                    for (int w2 = 0; w2 < 20; ++w2) fprintf(stderr, " %.2f", hb[(size_t)b * 20 + w2] * 1e-6);
+                    fprintf(stderr, "\n");
+                }
+                dbg.release();
+            }
             tm.mark(T_ROUTE);
             dcp_launch_route(C, W, 0, C.nstep, d_q, s); n_launch += 2;
         } else {
@@ -637,6 +655,19 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     c->stats.n_physics_launches = n_phys;
     c->stats.n_launches = n_launch;
     c->stats.hist_len = hist_len_max;
+    return DCP_OK;
+}
+
+int dcp_debug_fastmath(int op, int64_t n, const double *x, double *y) {
+    if (dcp_device_count() < 1) return fail(DCP_ERR_NO_DEVICE, "no CUDA device");
+    if (op < 0 || op > 2 || n < 1 || !x || !y) return fail(DCP_ERR_INVALID, "bad argument");
+    double *dx = nullptr, *dy = nullptr;
+    CUDA_TRY(cudaMalloc(&dx, n * 8));
+    CUDA_TRY(cudaMalloc(&dy, n * 8));
+    CUDA_TRY(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
+    dcp_launch_debug_fastmath(op, n, dx, dy, 0);
+    CUDA_TRY(cudaMemcpy(y, dy, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(dx); cudaFree(dy);
     return DCP_OK;
 }
 

@@ -120,13 +120,18 @@ struct ResPlan {
     int32_t G;                      // member sub-groups side by side in one CTA (512 / nac_pad)
     int32_t Mc;                     // members per CTA = G * S
     int32_t n_groups;               // ceil(B / Mc), set per launch
+    int32_t n_threads;              // 512 compute threads + 128 river threads
+    int32_t river_team;             // lanes per summation chain in FAST mode (power of two <= 16)
     int32_t Tt;                     // forcing tile (timesteps) per TMA bulk copy
     int32_t nnz;                    // W entries
+    int32_t nq;                     // non-zero entries of rivers(:, :)
     int32_t smem_bytes;
-    int32_t off_qbf, off_ex, off_cst, off_par, off_w, off_src, off_ac, off_forc, off_bar;
+    int32_t off_qbf, off_ex, off_cst, off_par, off_w, off_src, off_ac, off_forc, off_bar, off_rqc, off_rq, off_ro;
     const int32_t *thread_hru;      // [nac_pad] HRU handled at each thread position (-1 = idle), sorted by W row length
+    const int32_t *hru_pos;         // [nac] inverse of thread_hru
     const RivChain *rivq;           // river CSR for qb, per river ascending HRU
     const int32_t *rivq_beg;        // [nriv+1]
     const int32_t *rivo;            // HRUs by ipriv, ascending
     const int32_t *rivo_beg;        // [nriv+1]
+    long long *dbg;                 // optional [grid][20 warps] busy-cycle counters (env DCP_RES_DEBUG=1), else null
 };

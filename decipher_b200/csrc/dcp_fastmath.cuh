@@ -17,12 +17,15 @@
 #include <cstdint>
 #include <cstring>
 
+#include <cmath>
+#if defined(__CUDACC__)
+#define FM_HD __host__ __device__ __forceinline__
+#else
+#define FM_HD inline
+#endif
 #if defined(__CUDA_ARCH__)
-#define FM_HD __device__ __forceinline__
 #define FM_FMA(a, b, c) fma((a), (b), (c))
 #else
-#include <cmath>
-#define FM_HD inline
 #define FM_FMA(a, b, c) std::fma((a), (b), (c))
 #endif
 
@@ -48,7 +51,34 @@ FM_HD double fm_make(int32_t hi, int32_t lo) {
 #endif
 }
 
-// 1/y for normal y, ~1 ulp
+// Coefficient table: on the device it lives in constant memory so that every DFMA takes its
+// coefficient straight from the constant bank (c[3][..]) instead of two register moves per use.
+#define FM_NC 32
+#define FM_TABLE                                                                                                   \
+    /* 0  L2E    */ 1.4426950408889634074, /* 1  LN2_HI */ 6.93147180369123816490e-01,                              \
+    /* 2  LN2_LO */ 1.90821492927058770002e-10, /* 3  MAGIC  */ 6755399441055744.0,                                 \
+    /* 4..13 exp: (exp(r)-1-r)/r^2 ~ sum c[4+j] r^j, j = 0..9 */                                                    \
+    0.5000000000000001, 0.16666666666666669, 0.04166666666662348, 0.008333333333330011, 0.0013888888917538296,      \
+    0.00019841269863303223, 2.4801520792572694e-05, 2.75572680728901e-06, 2.762032742826824e-07,                    \
+    2.5100569275813683e-08, /* 14..20 log: fdlibm Lg1..Lg7 */                                                       \
+    6.666666666666735130e-01, 3.999999999940941908e-01, 2.857142874366239149e-01, 2.222219843214978396e-01,         \
+    1.818357216161805012e-01, 1.531383769920937332e-01, 1.479819860511658591e-01, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0
+static const double FM_CH[FM_NC] = {FM_TABLE};
+#if defined(__CUDACC__)
+static __constant__ double FM_CD[FM_NC] = {FM_TABLE};
+#endif
+#if defined(__CUDA_ARCH__)
+#define FMC(i) FM_CD[i]
+#else
+#define FMC(i) FM_CH[i]
+#endif
+
+// a > b ? a : b without the NaN bookkeeping of fmax()/fmin() (3 instructions instead of ~7);
+// callers only pass ordered finite operands or accept either operand on NaN
+FM_HD double fm_max(double a, double b) { return a > b ? a : b; }
+FM_HD double fm_min(double a, double b) { return a < b ? a : b; }
+
+// 1/y for normal y, <= 1 ulp: ~20-bit seed r0, e = 1 - y r0, r = r0 + r0 (e + e^2)  [error e^3 ~ 2^-60]
 FM_HD double fm_rcp(double y) {
     double r;
 #if defined(__CUDA_ARCH__)
@@ -56,45 +86,36 @@ FM_HD double fm_rcp(double y) {
 #else
     r = fm_make(fm_hi(1.0 / y), 0);                   // host stand-in for the ~20-bit hardware seed (MUFU.RCP64H)
 #endif
-    double e = FM_FMA(-y, r, 1.0);
-    r = FM_FMA(r, e, r);
-    e = FM_FMA(-y, r, 1.0);
-    r = FM_FMA(r, e, r);
-    return r;
+    const double e = FM_FMA(-y, r, 1.0);
+    const double t = FM_FMA(e, e, e);
+    return FM_FMA(r, t, r);
 }
 
-// exp(x), |x| <= 700
+// exp(x), |x| <= 700.  Estrin evaluation of the degree-9 polynomial: depth 4 instead of 9 dependent DFMAs.
 FM_HD double fm_exp(double x) {
-    const double L2E = 1.4426950408889634074;         // 1/ln2
-    const double LN2_HI = 6.93147180369123816490e-01; // fdlibm split of ln2
-    const double LN2_LO = 1.90821492927058770002e-10;
-    const double MAGIC = 6755399441055744.0;          // 1.5 * 2^52: adding it rounds to nearest integer
-    const double t = FM_FMA(x, L2E, MAGIC);
+    const double t = FM_FMA(x, FMC(0), FMC(3));
     const int32_t k = fm_lo(t);
-    const double kf = t - MAGIC;
-    double r = FM_FMA(kf, -LN2_HI, x);
-    r = FM_FMA(kf, -LN2_LO, r);
-    double p = 2.5100569275813683e-08;
-    p = FM_FMA(p, r, 2.762032742826824e-07);
-    p = FM_FMA(p, r, 2.75572680728901e-06);
-    p = FM_FMA(p, r, 2.4801520792572694e-05);
-    p = FM_FMA(p, r, 0.00019841269863303223);
-    p = FM_FMA(p, r, 0.0013888888917538296);
-    p = FM_FMA(p, r, 0.008333333333330011);
-    p = FM_FMA(p, r, 0.04166666666662348);
-    p = FM_FMA(p, r, 0.16666666666666669);
-    p = FM_FMA(p, r, 0.5000000000000001);
+    const double kf = t - FMC(3);
+    double r = FM_FMA(kf, -FMC(1), x);
+    r = FM_FMA(kf, -FMC(2), r);
     const double r2 = r * r;
+    const double p01 = FM_FMA(FMC(5), r, FMC(4));
+    const double p23 = FM_FMA(FMC(7), r, FMC(6));
+    const double p45 = FM_FMA(FMC(9), r, FMC(8));
+    const double p67 = FM_FMA(FMC(11), r, FMC(10));
+    const double p89 = FM_FMA(FMC(13), r, FMC(12));
+    const double r4 = r2 * r2;
+    const double q0 = FM_FMA(p23, r2, p01);
+    const double q1 = FM_FMA(p67, r2, p45);
+    const double r8 = r4 * r4;
+    const double s0 = FM_FMA(q1, r4, q0);
+    const double p = FM_FMA(p89, r8, s0);
     const double y = 1.0 + FM_FMA(r2, p, r);          // in (0.70, 1.42)
     return fm_make(fm_hi(y) + (k << 20), fm_lo(y));   // * 2^k, result stays normal for |x| <= 700
 }
 
 // log(x), x finite, normal, > 0
 FM_HD double fm_log(double x) {
-    const double LN2_HI = 6.93147180369123816490e-01, LN2_LO = 1.90821492927058770002e-10;
-    const double Lg1 = 6.666666666666735130e-01, Lg2 = 3.999999999940941908e-01, Lg3 = 2.857142874366239149e-01,
-                 Lg4 = 2.222219843214978396e-01, Lg5 = 1.818357216161805012e-01, Lg6 = 1.531383769920937332e-01,
-                 Lg7 = 1.479819860511658591e-01;
     int32_t hi = fm_hi(x);
     int32_t k = (hi >> 20) - 1023;
     hi &= 0x000fffff;
@@ -105,11 +126,11 @@ FM_HD double fm_log(double x) {
     const double s = f * fm_rcp(2.0 + f);
     const double z = s * s;
     const double w = z * z;
-    const double t1 = w * FM_FMA(w, FM_FMA(w, Lg6, Lg4), Lg2);
-    const double t2 = z * FM_FMA(w, FM_FMA(w, FM_FMA(w, Lg7, Lg5), Lg3), Lg1);
+    const double t1 = w * FM_FMA(w, FM_FMA(w, FMC(19), FMC(17)), FMC(15));
+    const double t2 = z * FM_FMA(w, FM_FMA(w, FM_FMA(w, FMC(20), FMC(18)), FMC(16)), FMC(14));
     const double R = t2 + t1;
     const double hfsq = 0.5 * f * f;
     const double dk = (double)k;
     // log(x) = k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f)
-    return FM_FMA(dk, LN2_HI, -((hfsq - FM_FMA(s, hfsq + R, dk * LN2_LO)) - f));
+    return FM_FMA(dk, FMC(1), -((hfsq - FM_FMA(s, hfsq + R, dk * FMC(2))) - f));
 }

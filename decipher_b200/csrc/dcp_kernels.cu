@@ -538,6 +538,18 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// device evaluation of the fast-math primitives (accuracy tests): op 0 exp, 1 log, 2 rcp
+__global__ void k_debug_fastmath(int op, int64_t n, const double *__restrict__ x, double *__restrict__ y) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = x[i];
+        y[i] = op == 0 ? fm_exp(v) : (op == 1 ? fm_log(v) : fm_rcp(v));
+    }
+}
+
+void dcp_launch_debug_fastmath(int op, int64_t n, const double *x, double *y, cudaStream_t s) {
+    k_debug_fastmath<<<592, 256, 0, s>>>(op, n, x, y);
+}
+
 // ------------------------------------------------------------------------------------------------
 // launch wrappers (called from dcp_api.cu)
 // ------------------------------------------------------------------------------------------------

@@ -6,7 +6,7 @@
 #define DCP_RES_S 4                  // member slots per compute thread of the resident kernel
 #define DCP_RES_LG 1                 // member slots interleaved per basic block in the lean step
 #define DCP_RES_COMPUTE 512
-#define DCP_RES_MAXCHAIN 128         // (members per CTA) x nriv chains the river warp can carry
+#define DCP_RES_MAXPAIRS 256         // (members per CTA) x nriv the river warps can carry (4 warps x 4 passes x 16 pairs)
 #define DCP_RES_TT 64                // forcing tile length (timesteps)
 #define DCP_FORCING_PAD 64           // forcing arrays are zero-padded to a multiple of this many steps
 
@@ -20,3 +20,4 @@ void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf,
 void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s);
 cudaError_t dcp_launch_physics_resident(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast,
                                         bool aet, int grid, cudaStream_t s);
+void dcp_launch_debug_fastmath(int op, int64_t n, const double *x, double *y, cudaStream_t s);

@@ -223,30 +223,29 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
                                               double qin, HruState &s, LeanOut &o) {
     // root_zone1 (dyna_root_zone1.f90:39-66)
     double srz = s.srz + p;
-    const double pex = fmax(srz - c.srmax, 0.0);
-    srz = fmin(srz, c.srmax);
+    const double pex = fm_max(srz - c.srmax, 0.0);
+    srz = fm_min(srz, c.srmax);
     double ea = epp * (srz * c.inv_srmax);
-    ea = fmin(fmin(ea, epp), srz);
+    ea = fm_min(fm_min(ea, epp), srz);
     srz = srz - ea;
     // unsat_zone1 (dyna_unsat_zone1.f90:49-78)
     const double sd0 = s.sd;
     double suz = s.suz + pex;
-    const double lim = fmax(sd0, 0.0);
-    const double exus = fmax(suz - lim, 0.0);
-    suz = fmin(suz, lim);
+    const double lim = fm_max(sd0, 0.0);
+    const double exus = fm_max(suz - lim, 0.0);
+    suz = fm_min(suz, lim);
     const double den = sd0 * c.td;
     double uz2 = g.dt * (suz * fm_rcp(den));
-    uz2 = (den > 1e-290) ? fmin(uz2, suz) : suz;         // tiny sd*td: suz/(sd*td) overflows, clipped to suz
+    uz2 = (den > 1e-290) ? fm_min(uz2, suz) : suz;       // tiny sd*td: suz/(sd*td) overflows, clipped to suz
     uz2 = (sd0 > 0.0 && suz > 0.0) ? uz2 : 0.0;
     suz = suz - uz2;
     const bool flush = suz < 0.0000001;
     uz2 = flush ? uz2 + suz : uz2;
     suz = flush ? 0.0 : suz;
     const double uz = uz2 * g.inv_dtt;
-    // satzone_analyticalsolver (dyna_satzone_analyticalsolver.f90:60-119), ntt == 1
+    // satzone_analyticalsolver (dyna_satzone_analyticalsolver.f90:60-119), ntt == 1 so qin2 == qin/ac
     const double qin_ac = qin * c.inv_ac;
-    const double qin2 = (s.qint1 + (qin - s.qint1)) * c.inv_ac;
-    const double u = qin2 + uz;
+    const double u = qin_ac + uz;
     const double u2 = c.q2 + u;
     const double a = (u2 * g.dtt) * c.inv_m2;
     const double x1 = sd0 * c.inv_m2;
@@ -260,11 +259,11 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     double sd = c.m2 * fm_log(arg);
     o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !(arg > 1e-290 && arg < 1e290);
     double qbf = (sd - sd0) * g.inv_dtt + uz + qin_ac;            // :98
-    double exs = fmax(-sd, 0.0);                                  // :107-112
-    sd = fmax(sd, 0.0);
-    const double over = fmax(qbf - c.q0, 0.0);                    // :115-119
+    double exs = fm_max(-sd, 0.0);                                // :107-112
+    sd = fm_max(sd, 0.0);
+    const double over = fm_max(qbf - c.q0, 0.0);                  // :115-119
     exs = fma(over, g.dtt, exs);
-    qbf = fmin(qbf, c.q0);
+    qbf = fm_min(qbf, c.q0);
     s.sd = sd; s.suz = suz; s.srz = srz; s.qint1 = qin;
     o.qbf = qbf;
     o.exac = (exs + exus) * c.ac;

@@ -4,21 +4,22 @@
 // their ENTIRE simulation (all nstep timesteps) before it fetches the next member group:
 //
 //   * 512 compute threads: thread = one HRU (x G member sub-groups side by side when nac <= 256),
-//     S member slots per thread.  The HRU store state (sd, suz, srz, qint1[, aet]) and the per
-//     (HRU, member) constants (q0, q2, m2) live in REGISTERS for the whole simulation; the static
-//     HRU record (area, slope cosine, forcing columns, W row bounds) is loaded into registers once.
-//   * last step's baseflow qbf of every (member, HRU) lives in SHARED memory, double buffered in
-//     time; the dynamic_dist gather  qin(dest) = sum_src (qbf(src)*w)*ac(src)  walks a CSR copy of the
-//     weighting matrix held in shared memory, sources ascending (== the reference's scatter order),
-//     each W entry loaded once and applied to the thread's S member slots (SpMM with members as the
-//     dense dimension, 32-byte vector loads of the S-member qbf tuple).
+//     S member slots per thread.  The time-varying stores (sd, suz, srz, qint1[, aet]) live in
+//     REGISTERS for the whole simulation; the per (HRU, member) constants (q0, q1, q2, m2, 1/m2) live
+//     in shared memory in a [slot][thread] layout (each thread reads only its own column: no bank
+//     conflicts, immediate offsets); the static HRU record is loaded into registers once.
+//   * last step's baseflow qbf of every (member, HRU) lives in SHARED memory as S-tuples, double
+//     buffered in time.  The dynamic_dist gather  qin(dest) = sum_src (qbf(src)*w)*ac(src)  walks a CSR
+//     copy of the weighting matrix in shared memory, sources ascending (== the reference's scatter
+//     order), each W entry loaded once and applied to the thread's S member slots: an SpMM with the
+//     members as the dense dimension, fed by 32-byte vector loads of the qbf tuple.
 //   * rain / PET tiles of Tt timesteps are staged into shared memory with TMA bulk copies
 //     (cp.async.bulk + mbarrier, double buffered) by one elected thread and read by every member.
-//   * one extra "river" warp does the per-river sums off the critical path: lane = (member, river)
-//     chain, summing qb (from the qbf tuple in shared memory) and qof (from the ex*ac terms the
-//     compute threads publish) over the HRUs in ascending order — bit-for-bit the reference's
-//     summation order — one step behind the compute warps, and streams qout(t) to global memory for
-//     the routing kernels.  One __syncthreads per timestep is the only CTA-wide synchronisation.
+//   * "river" warps do the per-river sums off the critical path: lane = one summation chain
+//     (member, river, qb | qof) walking the river's HRU list (kept in shared memory) in ascending HRU
+//     order — bit-for-bit the reference's summation order — one step behind the compute warps; the
+//     qb/qof lanes of a pair meet through one warp shuffle and stream qout(t) to global memory for the
+//     routing kernels.  One __syncthreads per timestep is the only CTA-wide synchronisation.
 //
 // Hot path citations: RRMODEL/dyna_topmod.f90:92-233, dyna_dynamic_dist.f90:47-67, dyna_river.f90:42-49.
 #include "dcp_device.cuh"
@@ -27,9 +28,11 @@
 
 #include <cstdint>
 
-#define RES_COMPUTE 512
-#define RES_THREADS (RES_COMPUTE + 32)
-#define RES_MAXPASS 4                 // river chains per lane of the river warp
+#define RES_CT DCP_RES_COMPUTE        // compute threads (4 warpgroups)
+#define RES_THREADS (RES_CT + 128)    // + one warpgroup of river warps: 5 warps per SM sub-partition
+#define RES_REGS_COMPUTE 104          // after setmaxnreg: launch allocation is 96/thread; the river warpgroup gives up (96-56)x128 registers, the compute warpgroups take (104-96)x512 of them
+#define RES_REGS_RIVER 56
+#define RES_MAXPASS 4                 // chains per river lane
 #define RES_PARW 6                    // srmax, td, smax, szm, 1/srmax, 1/szm
 
 // ---------------------------------------------------------------------------------------------
@@ -62,302 +65,378 @@ __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.
 __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory views and per-launch constants common to both warp roles
+// ---------------------------------------------------------------------------------------------
+struct ResSmem {
+    double *qbf_s, *ex_s, *cst_s, *par_s, *w_s, *ac_s, *forc_s, *rqc_s;
+    uint16_t *src_s, *rq_s, *ro_s;
+    uint64_t *bars;
+};
+
+// CTA-wide barrier used inside the role-specialised code (both roles execute the same sequence)
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RES_THREADS) : "memory"); }
+
+#define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})     /* straight from the constant bank, no registers */
+
+// ---------------------------------------------------------------------------------------------
+// compute role: 16 warps, thread = HRU x S member slots
 // MODE 0: EXACT arithmetic (reference order, IEEE division, library exp/log)
 // MODE 1: FAST arithmetic, generic branchy step (any ims flags / ntt)
-// MODE 2: FAST arithmetic, LEAN branch-free step, two member slots interleaved per basic block
+// MODE 2: FAST arithmetic, LEAN branch-free step (dcp_physics.cuh: hru_step_lean)
+// ---------------------------------------------------------------------------------------------
 template <int S, int MODE, bool AET>
-__global__ void __launch_bounds__(RES_THREADS, 1)
-k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
+__device__ __forceinline__ void res_compute_role(const DevCatchment &C, const DevBatch &W, const ResPlan &P,
+                                                 const ResSmem &M) {
     constexpr bool FAST = MODE != 0;
     constexpr bool LEAN = MODE == 2;
-    extern __shared__ __align__(128) unsigned char smem[];
-    double *qbf_s = (double *)(smem + P.off_qbf);          // [2][G*nac_pad*S]
-    double *ex_s = (double *)(smem + P.off_ex);            // [2][Mc*nac_pad]
-    double *cst_s = (double *)(smem + P.off_cst);          // [5][G*nac_pad*S]  q0, q2, m2, q1, 1/m2 per (HRU, member)
-    double *par_s = (double *)(smem + P.off_par);          // [Mc][npt][RES_PARW]
-    double *w_s = (double *)(smem + P.off_w);              // [nnz]   w (EXACT) or w*ac_src (FAST)
-    uint16_t *src_s = (uint16_t *)(smem + P.off_src);      // [nnz]
-    double *ac_s = (double *)(smem + P.off_ac);            // [nac_pad]
-    double *forc_s = (double *)(smem + P.off_forc);        // [2][Tt*(ngp+nge)]
-    uint64_t *bars = (uint64_t *)(smem + P.off_bar);       // [2]
-
     const int tid = threadIdx.x;
-    const bool is_compute = tid < RES_COMPUTE;
-    const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, nriv = C.nriv, npt = C.npt;
-    const int qbf_stride = P.G * nac_pad * S;              // doubles per time buffer
-    const int ex_stride = Mc * nac_pad;
+    const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, npt = C.npt;
+    const int qbf_stride = P.G * nac_pad * S;              // doubles per qbf time buffer
     const int forc_stride = P.Tt * (C.ngp + C.nge);
-    const int Rm = W.Rmask;
 
-    // ---- one-time CTA setup: W copy to shared memory, barriers ----
-    for (int e = tid; e < P.nnz; e += RES_THREADS) {
-        const WEntry we = C.w[e];
-        w_s[e] = FAST ? we.w * we.ac_src : we.w;
-        src_s[e] = (uint16_t)we.src;
-    }
-    for (int i = tid; i < nac_pad; i += RES_THREADS) ac_s[i] = i < C.nac ? C.hru[i].ac : 0.0;
-    if (tid == RES_COMPUTE) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
-        fence_mbar_init();
-    }
-
-    // ---- per-thread static HRU record (registers for the whole launch) ----
-    const int g = is_compute ? tid / nac_pad : 0;
-    const int ia = is_compute ? P.thread_hru[tid % nac_pad] : -1;      // permuted so warps see similar W row lengths
+    // per-thread static HRU record (registers for the whole launch)
+    const int pos = tid % nac_pad;                          // position inside the member sub-group
+    const int g = tid / nac_pad;
+    const int ia = P.thread_hru[pos];                       // positions are sorted by W row length
     HruStatic h;
     if (ia >= 0) h = C.hru[ia];
     else { h = HruStatic{}; h.ac = 1.0; h.cosm = 1.0; }
     const double inv_ac = 1.0 / h.ac;
-    const int gbase = g * nac_pad;
-
-#define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})     /* straight from the constant bank, no registers */
+    const int my_tuple = (g * nac_pad + pos) * S;           // offset of this thread's qbf tuple
+    const int g_tuple = g * nac_pad * S;
+    const double *my_par = M.par_s + ((size_t)g * S * npt + h.ipar) * RES_PARW;
+    const int par_kstride = npt * RES_PARW;
     const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
-    const uint32_t rain_bytes = (uint32_t)(P.Tt * C.ngp * sizeof(double));
-    const uint32_t pet_bytes = (uint32_t)(P.Tt * C.nge * sizeof(double));
-    uint32_t tiles_done = 0;                               // forcing tiles consumed so far (barrier phase tracking)
+    uint32_t tiles_done = 0;                                // forcing tiles consumed so far (mbarrier phase tracking)
+    long long busy = 0;
 
     for (int gi = blockIdx.x; gi < P.n_groups; gi += gridDim.x) {
         const int m_base = gi * Mc;
-        __syncthreads();                                   // previous group fully done with shared memory
+        cta_sync();                                         // previous group fully done with shared memory
 
         // ---- load the group's initial state (written by k_init_members) ----
-        // time-varying stores stay in registers; the per (HRU, member) constants q0, q2, m2 go to shared
-        // memory as S-tuples.  Slots beyond the batch (m >= B) run on benign dummy values: no predicates.
         double sd[S], suz[S], srz[S], qint1[S], aet[S];
-        if (is_compute) {
 #pragma unroll
-            for (int k = 0; k < S; ++k) {
-                const int m = m_base + g * S + k;
-                sd[k] = 1.0; suz[k] = 0.0; srz[k] = 0.0; qint1[k] = 0.0; aet[k] = 0.0;
-                double qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_m2 = 1.0, c_q1 = 1.0, c_im2 = 1.0;
-                if (ia >= 0 && m < B) {
-                    const size_t o = (size_t)ia * B + m;
-                    sd[k] = W.sd[o]; suz[k] = W.suz[o]; srz[k] = W.srz[o]; qint1[k] = W.qint1[o];
-                    c_q0 = W.q0[o]; c_q2 = W.q2[o];
-                    const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
-                    c_m2 = szm / h.cosm;                   // dyna_satzone_analyticalsolver.f90:52
-                    c_q1 = c_q0 * h.cosm;                  // :49
-                    c_im2 = h.cosm / szm;
-                    qb0 = W.qbf0[o];
-                }
-                if (ia >= 0) {
-                    qbf_s[(gbase + ia) * S + k] = qb0;     // time buffer 0 = step 0's "old" qbf
-                    cst_s[0 * qbf_stride + (gbase + ia) * S + k] = c_q0;
-                    cst_s[1 * qbf_stride + (gbase + ia) * S + k] = c_q2;
-                    cst_s[2 * qbf_stride + (gbase + ia) * S + k] = c_m2;
-                    cst_s[3 * qbf_stride + (gbase + ia) * S + k] = c_q1;
-                    cst_s[4 * qbf_stride + (gbase + ia) * S + k] = c_im2;
-                }
+        for (int k = 0; k < S; ++k) {
+            const int m = m_base + g * S + k;
+            sd[k] = 1.0; suz[k] = 0.0; srz[k] = 0.0; qint1[k] = 0.0; aet[k] = 0.0;
+            double qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_m2 = 1.0, c_q1 = 1.0, c_im2 = 1.0;
+            if (ia >= 0 && m < B) {
+                const size_t o = (size_t)ia * B + m;
+                sd[k] = W.sd[o]; suz[k] = W.suz[o]; srz[k] = W.srz[o]; qint1[k] = W.qint1[o];
+                c_q0 = W.q0[o]; c_q2 = W.q2[o];
+                const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
+                c_m2 = szm / h.cosm;                        // dyna_satzone_analyticalsolver.f90:52
+                c_q1 = c_q0 * h.cosm;                       // :49
+                c_im2 = h.cosm / szm;
+                qb0 = W.qbf0[o];
             }
-            if (ia < 0) {                                   // idle thread: zero its padding rows in both buffers
-                const int ip = tid % nac_pad;
-                if (ip >= C.nac)
-                    for (int k = 0; k < S; ++k) {
-                        qbf_s[(gbase + ip) * S + k] = 0.0;
-                        qbf_s[qbf_stride + (gbase + ip) * S + k] = 0.0;
-                    }
-            }
-            // member parameters -> shared (one thread per (member, layer))
-            for (int i = tid; i < Mc * npt; i += RES_COMPUTE) {
-                const int jm = i / npt, l = i % npt;
-                const int m = m_base + jm;
-                double *pp = par_s + (size_t)i * RES_PARW;
-                if (m < B) {
-                    const double srmax = W.par[(2 * npt + l) * (size_t)B + m];
-                    const double szm = W.par[(0 * npt + l) * (size_t)B + m];
-                    pp[0] = srmax;
-                    pp[1] = W.par[(5 * npt + l) * (size_t)B + m];
-                    pp[2] = W.par[(6 * npt + l) * (size_t)B + m];
-                    pp[3] = szm;
-                    pp[4] = 1.0 / srmax;
-                    pp[5] = 1.0 / szm;
-                } else {
-                    pp[0] = pp[1] = pp[2] = pp[3] = pp[4] = pp[5] = 1.0;
-                }
-            }
-        } else if (tid == RES_COMPUTE) {
-            // forcing tile 0 of this group
-            const uint32_t b = tiles_done & 1;
-            fence_proxy_async();
-            mbar_expect_tx(&bars[b], rain_bytes + pet_bytes);
-            tma_load_1d(forc_s + b * forc_stride, C.rain, rain_bytes, &bars[b]);
-            tma_load_1d(forc_s + b * forc_stride + P.Tt * C.ngp, C.pet, pet_bytes, &bars[b]);
+            M.qbf_s[my_tuple + k] = qb0;                    // time buffer 0 = step 0's "old" qbf
+            M.qbf_s[qbf_stride + my_tuple + k] = 0.0;
+            M.cst_s[(0 * S + k) * RES_CT + tid] = c_q0;
+            M.cst_s[(1 * S + k) * RES_CT + tid] = c_q2;
+            M.cst_s[(2 * S + k) * RES_CT + tid] = c_m2;
+            M.cst_s[(3 * S + k) * RES_CT + tid] = c_q1;
+            M.cst_s[(4 * S + k) * RES_CT + tid] = c_im2;
+            M.ex_s[(0 * S + k) * RES_CT + tid] = 0.0;
+            M.ex_s[(1 * S + k) * RES_CT + tid] = 0.0;
         }
-        __syncthreads();
-
-        // river warp: chains (member jm, river r)
-        double qb_prev[RES_MAXPASS];
-#pragma unroll
-        for (int q = 0; q < RES_MAXPASS; ++q) qb_prev[q] = 0.0;
+        // member parameters -> shared (one thread per (member, layer))
+        for (int i = tid; i < Mc * npt; i += RES_CT) {
+            const int jm = i / npt, l = i % npt;
+            const int m = m_base + jm;
+            double *pp = M.par_s + (size_t)i * RES_PARW;
+            if (m < B) {
+                const double srmax = W.par[(2 * npt + l) * (size_t)B + m];
+                const double szm = W.par[(0 * npt + l) * (size_t)B + m];
+                pp[0] = srmax;
+                pp[1] = W.par[(5 * npt + l) * (size_t)B + m];
+                pp[2] = W.par[(6 * npt + l) * (size_t)B + m];
+                pp[3] = szm;
+                pp[4] = 1.0 / srmax;
+                pp[5] = 1.0 / szm;
+            } else {
+                pp[0] = pp[1] = pp[2] = pp[3] = pp[4] = pp[5] = 1.0;
+            }
+        }
+        cta_sync();
 
         int t = 0;
         for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
             const uint32_t b = tiles_done & 1;
-            if (tid == RES_COMPUTE && tile + 1 < ntiles) {
-                // prefetch the next tile into the other buffer (everyone left it at the last __syncthreads)
-                const uint32_t nb = b ^ 1;
-                const size_t t_next = (size_t)(tile + 1) * P.Tt;
-                fence_proxy_async();
-                mbar_expect_tx(&bars[nb], rain_bytes + pet_bytes);
-                tma_load_1d(forc_s + nb * forc_stride, C.rain + t_next * C.ngp, rain_bytes, &bars[nb]);
-                tma_load_1d(forc_s + nb * forc_stride + P.Tt * C.ngp, C.pet + t_next * C.nge, pet_bytes, &bars[nb]);
-            }
-            if (is_compute) mbar_wait(&bars[b], (tiles_done >> 1) & 1);
-            const double *rain_t = forc_s + b * forc_stride;
-            const double *pet_t = rain_t + P.Tt * C.ngp;
+            mbar_wait(&M.bars[b], (tiles_done >> 1) & 1);   // forcing tile landed (TMA, issued by the river role)
+            const double *rain_t = M.forc_s + b * forc_stride + h.ippt;
+            const double *pet_t = M.forc_s + b * forc_stride + P.Tt * C.ngp + h.ipet;
             const int t_end = min(C.nstep, t + P.Tt);
-            for (int tt = 0; t < t_end; ++t, ++tt) {
-                const double *qbf_cur = qbf_s + (t & 1) * qbf_stride;
-                double *qbf_nxt = qbf_s + ((t & 1) ^ 1) * qbf_stride;
-                if (is_compute) {
-                    if (ia >= 0) {
-                        const double p = rain_t[tt * C.ngp + h.ippt], ep = pet_t[tt * C.nge + h.ipet];
-                        // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52) ----
-                        double qin[S];
+            for (; t < t_end; ++t, rain_t += C.ngp, pet_t += C.nge) {
+                const long long c0 = P.dbg ? clock64() : 0;
+                if (ia >= 0) {
+                    const double *qbf_cur = M.qbf_s + (t & 1) * qbf_stride;
+                    double *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * qbf_stride;
+                    const double p = *rain_t, ep = *pet_t;
+                    // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52) ----
+                    double qin[S];
 #pragma unroll
-                        for (int k = 0; k < S; ++k) qin[k] = 0.0;
-                        for (int e = h.row_beg; e < h.row_end; ++e) {
-                            const int src = src_s[e];
-                            const double w = w_s[e];
-                            const double2 *qv = reinterpret_cast<const double2 *>(qbf_cur + (gbase + src) * S);
-                            double qs[S];
+                    for (int k = 0; k < S; ++k) qin[k] = 0.0;
+                    const double *qg = qbf_cur + g_tuple;
+                    for (int e = h.row_beg; e < h.row_end; ++e) {
+                        const int sp = M.src_s[e];
+                        const double w = M.w_s[e];
+                        const double2 *qv = reinterpret_cast<const double2 *>(qg + sp * S);
+                        double qs[S];
 #pragma unroll
-                            for (int k2 = 0; k2 < S / 2; ++k2) { const double2 v = qv[k2]; qs[2 * k2] = v.x; qs[2 * k2 + 1] = v.y; }
-                            if (FAST) {
+                        for (int k2 = 0; k2 < S / 2; ++k2) { const double2 v = qv[k2]; qs[2 * k2] = v.x; qs[2 * k2 + 1] = v.y; }
+                        if (FAST) {
 #pragma unroll
-                                for (int k = 0; k < S; ++k) qin[k] = qin[k] + qs[k] * w;
-                            } else {
-                                const double acs = ac_s[src];
-#pragma unroll
-                                for (int k = 0; k < S; ++k) qin[k] = qin[k] + qs[k] * w * acs;
-                            }
-                        }
-                        // ---- root zone, unsaturated zone, saturated zone per member slot ----
-                        double *qo = qbf_nxt + (gbase + ia) * S;
-                        double *exo = ex_s + (t & 1) * ex_stride + (g * S) * nac_pad + ia;
-                        const double *cst = cst_s + (gbase + ia) * S;
-                        if (LEAN) {
-                            const double epp = fmax(ep, 0.0);
-#pragma unroll
-                            for (int k0 = 0; k0 < S; k0 += DCP_RES_LG) {
-                                LeanOut lo[DCP_RES_LG];
-                                double qi_old[DCP_RES_LG];
-#pragma unroll
-                                for (int j = 0; j < DCP_RES_LG; ++j) {
-                                    const int k = k0 + j;
-                                    const double *pp = par_s + ((size_t)(g * S + k) * npt + h.ipar) * RES_PARW;
-                                    HruConst c;
-                                    c.ac = h.ac; c.inv_ac = inv_ac;
-                                    c.q0 = cst[k]; c.q2 = cst[qbf_stride + k]; c.m2 = cst[2 * qbf_stride + k];
-                                    c.q1 = cst[3 * qbf_stride + k]; c.inv_m2 = cst[4 * qbf_stride + k];
-                                    c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
-                                    c.ims_rz = 1; c.ims_uz = 1;
-                                    qi_old[j] = qint1[k];
-                                    HruState st;
-                                    st.sd = sd[k]; st.suz = suz[k]; st.srz = srz[k]; st.qint1 = qint1[k];
-                                    hru_step_lean(c, gc, p, epp, qin[k], st, lo[j]);
-                                    sd[k] = st.sd; suz[k] = st.suz; srz[k] = st.srz; qint1[k] = st.qint1;
-                                }
-                                bool any_slow = false;
-#pragma unroll
-                                for (int j = 0; j < DCP_RES_LG; ++j) any_slow |= lo[j].slow;
-                                if (any_slow) {
-#pragma unroll
-                                    for (int j = 0; j < DCP_RES_LG; ++j)
-                                        if (lo[j].slow) {           // rare: constants are re-read instead of kept live
-                                            const int k = k0 + j;
-                                            const double *pp = par_s + ((size_t)(g * S + k) * npt + h.ipar) * RES_PARW;
-                                            HruConst c;
-                                            c.ac = h.ac; c.inv_ac = inv_ac;
-                                            c.q0 = cst[k]; c.q2 = cst[qbf_stride + k]; c.m2 = cst[2 * qbf_stride + k];
-                                            c.q1 = cst[3 * qbf_stride + k]; c.inv_m2 = cst[4 * qbf_stride + k];
-                                            c.smax = pp[2];
-                                            hru_step_lean_fixup(c, gc, qin[k], qi_old[j], sd[k], lo[j]);
-                                        }
-                                }
-#pragma unroll
-                                for (int j = 0; j < DCP_RES_LG; ++j) {
-                                    qo[k0 + j] = lo[j].qbf;
-                                    exo[(k0 + j) * nac_pad] = lo[j].exac;
-                                    if (AET) aet[k0 + j] = aet[k0 + j] + lo[j].ea;
-                                }
-                            }
+                            for (int k = 0; k < S; ++k) qin[k] = fma(qs[k], w, qin[k]);
                         } else {
+                            const double acs = M.ac_s[sp];
 #pragma unroll
-                            for (int k = 0; k < S; ++k) {
-                                const double *pp = par_s + ((size_t)(g * S + k) * npt + h.ipar) * RES_PARW;
-                                HruConst c;
-                                c.ac = h.ac; c.inv_ac = inv_ac;
-                                c.q0 = cst[k]; c.q1 = cst[3 * qbf_stride + k]; c.q2 = cst[qbf_stride + k];
-                                c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2];
-                                c.inv_srmax = pp[4];
-                                c.m2 = cst[2 * qbf_stride + k];
-                                c.inv_m2 = cst[4 * qbf_stride + k];
-                                c.ims_rz = h.ims_rz; c.ims_uz = h.ims_uz;
-                                HruState s;
-                                s.sd = sd[k]; s.suz = suz[k]; s.srz = srz[k]; s.qint1 = qint1[k];
-                                HruFlux f;
-                                hru_step<FAST, false>(c, gc, p, ep, qin[k], s, f);
-                                sd[k] = s.sd; suz[k] = s.suz; srz[k] = s.srz; qint1[k] = s.qint1;
-                                qo[k] = f.qbf;
-                                exo[k * nac_pad] = (f.ex > 0.0) ? f.ex * h.ac : 0.0;   // dyna_results_ac.f90:35-38
-                                if (AET) { if (h.ims_rz == 1 && ep > 0.0) aet[k] = aet[k] + f.ea; }
-                            }
+                            for (int k = 0; k < S; ++k) qin[k] = qin[k] + qs[k] * w * acs;
                         }
                     }
-                } else {
-                    // ---- river warp: qb(t) from qbf_cur, qof(t-1) from last step's ex terms ----
-                    const int lane = tid - RES_COMPUTE;
-                    const double *ex_prev = ex_s + ((t & 1) ^ 1) * ex_stride;
+                    // ---- root zone, unsaturated zone, saturated zone per member slot ----
+                    double *qo = qbf_nxt + my_tuple;
+                    double *exo = M.ex_s + (t & 1) * (S * RES_CT) + tid;
+                    const double *cst = M.cst_s + tid;
+                    if (LEAN) {
+                        const double epp = fm_max(ep, 0.0);
 #pragma unroll
-                    for (int q = 0; q < RES_MAXPASS; ++q) {
-                        const int cidx = lane + 32 * q;
-                        if (cidx < Mc * nriv) {
-                            const int jm = cidx / nriv, r = cidx - jm * nriv;
-                            const int gg = jm / S, kk = jm - gg * S;
-                            const int m = m_base + jm;
-                            double qb = 0.0;
-                            for (int i = P.rivq_beg[r]; i < P.rivq_beg[r + 1]; ++i) {
-                                const RivChain rc = P.rivq[i];
-                                const double qv = qbf_cur[(gg * nac_pad + rc.ia) * S + kk];
-                                qb = qb + C.dtt * qv * rc.w_riv * rc.share * rc.ac;    // dyna_dynamic_dist.f90:59-61
-                            }
-                            if (t > 0) {
-                                double qof = 0.0;
-                                for (int i = P.rivo_beg[r]; i < P.rivo_beg[r + 1]; ++i)
-                                    qof = qof + ex_prev[jm * nac_pad + P.rivo[i]];
-                                if (m < B) W.qout[((size_t)((t - 1) & Rm) * nriv + r) * B + m] = qb_prev[q] + qof;   // dyna_river.f90:43
-                            }
-                            qb_prev[q] = qb;
+                        for (int k = 0; k < S; ++k) {
+                            const double *pp = my_par + k * par_kstride;
+                            HruConst c;
+                            c.ac = h.ac; c.inv_ac = inv_ac;
+                            c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
+                            c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
+                            c.inv_m2 = cst[(4 * S + k) * RES_CT];
+                            c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
+                            c.ims_rz = 1; c.ims_uz = 1;
+                            HruState st;
+                            st.sd = sd[k]; st.suz = suz[k]; st.srz = srz[k]; st.qint1 = 0.0;
+                            LeanOut lo;
+                            hru_step_lean(c, gc, p, epp, qin[k], st, lo);
+                            sd[k] = st.sd; suz[k] = st.suz; srz[k] = st.srz;                         // qint1 is not carried:
+                            if (lo.slow) hru_step_lean_fixup(c, gc, qin[k], qin[k], sd[k], lo);      // ntt == 1 => qin2 == qin/ac
+                            qo[k] = lo.qbf;
+                            exo[k * RES_CT] = lo.exac;
+                            if (AET) aet[k] = aet[k] + lo.ea;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < S; ++k) {
+                            const double *pp = my_par + k * par_kstride;
+                            HruConst c;
+                            c.ac = h.ac; c.inv_ac = inv_ac;
+                            c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
+                            c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
+                            c.inv_m2 = cst[(4 * S + k) * RES_CT];
+                            c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
+                            c.ims_rz = h.ims_rz; c.ims_uz = h.ims_uz;
+                            HruState s;
+                            s.sd = sd[k]; s.suz = suz[k]; s.srz = srz[k]; s.qint1 = qint1[k];
+                            HruFlux f;
+                            hru_step<FAST, false>(c, gc, p, ep, qin[k], s, f);
+                            sd[k] = s.sd; suz[k] = s.suz; srz[k] = s.srz; qint1[k] = s.qint1;
+                            qo[k] = f.qbf;
+                            exo[k * RES_CT] = (f.ex > 0.0) ? f.ex * h.ac : 0.0;   // dyna_results_ac.f90:35-38
+                            if (AET) { if (h.ims_rz == 1 && ep > 0.0) aet[k] = aet[k] + f.ea; }
                         }
                     }
                 }
-                __syncthreads();
+                if (P.dbg) busy += clock64() - c0;
+                cta_sync();
             }
         }
-        // ---- drain: qof of the last step ----
-        if (!is_compute) {
-            const int lane = tid - RES_COMPUTE;
-            const double *ex_prev = ex_s + ((t & 1) ^ 1) * ex_stride;
-#pragma unroll
-            for (int q = 0; q < RES_MAXPASS; ++q) {
-                const int cidx = lane + 32 * q;
-                if (cidx < Mc * nriv) {
-                    const int jm = cidx / nriv, r = cidx - jm * nriv;
-                    const int m = m_base + jm;
-                    double qof = 0.0;
-                    for (int i = P.rivo_beg[r]; i < P.rivo_beg[r + 1]; ++i) qof = qof + ex_prev[jm * nac_pad + P.rivo[i]];
-                    if (m < B) W.qout[((size_t)((t - 1) & Rm) * nriv + r) * B + m] = qb_prev[q] + qof;
-                }
-            }
-        } else if (AET) {
+        if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 20 + (tid >> 5)] = busy;
+        if (AET) {
 #pragma unroll
             for (int k = 0; k < S; ++k)
                 if (ia >= 0 && m_base + g * S + k < B) W.aet[(size_t)ia * B + (m_base + g * S + k)] = aet[k];
         }
     }
 }
+
+// ---------------------------------------------------------------------------------------------
+// river role: 4 warps.  Lane = summation chain; thread RES_CT also drives the forcing TMA.
+// ---------------------------------------------------------------------------------------------
+template <int S, bool FAST>
+__device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevBatch &W, const ResPlan &P,
+                                               const ResSmem &M) {
+    const int tid = threadIdx.x;
+    const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, nriv = C.nriv;
+    const int qbf_stride = P.G * nac_pad * S;
+    const int forc_stride = P.Tt * (C.ngp + C.nge);
+    const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
+    const uint32_t rain_bytes = (uint32_t)(P.Tt * C.ngp * sizeof(double));
+    const uint32_t pet_bytes = (uint32_t)(P.Tt * C.nge * sizeof(double));
+    uint32_t tiles_done = 0;
+    const int rlane = tid - RES_CT;
+    constexpr int n_rlanes = RES_THREADS - RES_CT;
+    const int n_chains = 2 * Mc * nriv;                     // chain id = (pair << 1) | type, pair = member * nriv + river
+    // EXACT: one lane per chain, terms added in ascending HRU order (the reference's order).
+    // FAST : a team of T lanes per chain (strided partial sums + shuffle tree) -- order is free there.
+    const int T = FAST ? P.river_team : 1;
+    const int sub = rlane & (T - 1);
+    const int chains_per_pass = n_rlanes / T;
+    long long busy = 0;
+
+    for (int gi = blockIdx.x; gi < P.n_groups; gi += gridDim.x) {
+        const int m_base = gi * Mc;
+        cta_sync();
+        if (tid == RES_CT) {                                // forcing tile 0 of this group
+            const uint32_t b = tiles_done & 1;
+            fence_proxy_async();
+            mbar_expect_tx(&M.bars[b], rain_bytes + pet_bytes);
+            tma_load_1d(M.forc_s + b * forc_stride, C.rain, rain_bytes, &M.bars[b]);
+            tma_load_1d(M.forc_s + b * forc_stride + P.Tt * C.ngp, C.pet, pet_bytes, &M.bars[b]);
+        }
+        cta_sync();
+
+        double qb_prev[RES_MAXPASS];
+#pragma unroll
+        for (int q = 0; q < RES_MAXPASS; ++q) qb_prev[q] = 0.0;
+
+        int t = 0;
+        for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
+            if (tid == RES_CT && tile + 1 < ntiles) {
+                // prefetch the next tile into the other buffer (everyone left it at the last barrier)
+                const uint32_t nb = (tiles_done & 1) ^ 1;
+                const size_t t_next = (size_t)(tile + 1) * P.Tt;
+                fence_proxy_async();
+                mbar_expect_tx(&M.bars[nb], rain_bytes + pet_bytes);
+                tma_load_1d(M.forc_s + nb * forc_stride, C.rain + t_next * C.ngp, rain_bytes, &M.bars[nb]);
+                tma_load_1d(M.forc_s + nb * forc_stride + P.Tt * C.ngp, C.pet + t_next * C.nge, pet_bytes, &M.bars[nb]);
+            }
+            const int t_end = min(C.nstep, t + P.Tt);
+            for (; t <= t_end; ++t) {
+                // step t: qb(t) chains from qbf_cur, qof(t-1) chains from last step's ex terms.
+                // t == nstep (only after the last tile) drains qof(nstep-1).
+                if (t == t_end && t < C.nstep) break;
+                const bool drain = (t == C.nstep);
+                const long long c0 = P.dbg ? clock64() : 0;
+                const double *qbf_cur = M.qbf_s + (t & 1) * qbf_stride;
+                const double *ex_prev = M.ex_s + ((t & 1) ^ 1) * (S * RES_CT);
+#pragma unroll
+                for (int q = 0; q < RES_MAXPASS; ++q) {
+                    if (q * chains_per_pass < n_chains) {                 // uniform over the river warps
+                        const int cid = rlane / T + q * chains_per_pass;
+                        const bool live = cid < n_chains;
+                        const int type = cid & 1, pair = cid >> 1;
+                        const int jm = live ? pair / nriv : 0, r = live ? pair - jm * nriv : 0;
+                        const int gg = jm / S, kk = jm - gg * S;
+                        // both chain kinds run the same loop:  acc += (((f0*v)*c0)*c1)*c2  with unit factors for qof
+                        const uint16_t *lst; const double *val; int vstride, cstride, beg, end; double f0;
+                        if (type == 0) {
+                            lst = M.rq_s; beg = P.rivq_beg[r]; end = P.rivq_beg[r + 1];
+                            val = qbf_cur + gg * nac_pad * S + kk; vstride = S; cstride = 1; f0 = FAST ? 1.0 : C.dtt;
+                            if (drain) end = beg;
+                        } else {
+                            lst = M.ro_s; beg = P.rivo_beg[r]; end = P.rivo_beg[r + 1];
+                            val = ex_prev + kk * RES_CT + gg * nac_pad; vstride = 1; cstride = 0; f0 = 1.0;
+                        }
+                        if (!live) end = beg;
+                        const double *cf = M.rqc_s + (cstride ? 0 : P.nq);
+                        double acc = 0.0;
+                        int i = beg + sub;
+                        for (; i + 3 * T < end; i += 4 * T) {
+                            double v[4], a0[4], a1[4], a2[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const int iu = i + u * T;
+                                v[u] = val[lst[iu] * vstride];
+                                a0[u] = cf[iu * cstride];
+                                if (!FAST) { a1[u] = cf[(P.nq + 1) + iu * cstride]; a2[u] = cf[2 * (P.nq + 1) + iu * cstride]; }
+                            }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                acc = FAST ? fma(v[u], a0[u], acc) : acc + f0 * v[u] * a0[u] * a1[u] * a2[u];   // dyna_dynamic_dist.f90:59-61
+                        }
+                        for (; i < end; i += T) {
+                            const double vv = val[lst[i] * vstride];
+                            const double b0 = cf[i * cstride];
+                            if (FAST) acc = fma(vv, b0, acc);
+                            else acc = acc + f0 * vv * b0 * cf[(P.nq + 1) + i * cstride] * cf[2 * (P.nq + 1) + i * cstride];
+                        }
+                        if (FAST)
+                            for (int o = T >> 1; o > 0; o >>= 1) acc = acc + __shfl_xor_sync(0xffffffffu, acc, o);
+                        const double qof = __shfl_down_sync(0xffffffffu, acc, T);           // the pair's qof(t-1) team
+                        if (type == 0 && live && sub == 0) {
+                            const int m = m_base + jm;
+                            if (t > 0 && m < B)
+                                W.qout[((size_t)((t - 1) & W.Rmask) * nriv + r) * B + m] = qb_prev[q] + qof;   // dyna_river.f90:43
+                        }
+                        if (type == 0) qb_prev[q] = acc;
+                    }
+                }
+                if (P.dbg) busy += clock64() - c0;
+                if (drain) { ++t; break; }
+                cta_sync();
+            }
+        }
+        if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 20 + (tid >> 5)] = busy;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int S, int MODE, bool AET>
+__global__ void __launch_bounds__(RES_THREADS, 1)
+k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
+    constexpr bool FAST = MODE != 0;
+    extern __shared__ __align__(128) unsigned char smem[];
+    ResSmem M;
+    M.qbf_s = (double *)(smem + P.off_qbf);          // [2][G*nac_pad][S]   qbf tuples, time double buffer
+    M.ex_s = (double *)(smem + P.off_ex);            // [2][S][CT]          ex*ac terms
+    M.cst_s = (double *)(smem + P.off_cst);          // [5][S][CT]          q0, q2, m2, q1, 1/m2
+    M.par_s = (double *)(smem + P.off_par);          // [Mc][npt][RES_PARW]
+    M.w_s = (double *)(smem + P.off_w);              // [nnz]    w (EXACT) or w*ac_src (FAST)
+    M.src_s = (uint16_t *)(smem + P.off_src);        // [nnz]    thread position of the source HRU
+    M.ac_s = (double *)(smem + P.off_ac);            // [nac_pad] ac by thread position
+    M.forc_s = (double *)(smem + P.off_forc);        // [2][Tt*(ngp+nge)]
+    M.bars = (uint64_t *)(smem + P.off_bar);         // [2]
+    M.rqc_s = (double *)(smem + P.off_rqc);          // [3][nq+1] river-term coefficients; [.][nq] = 1.0
+    M.rq_s = (uint16_t *)(smem + P.off_rq);          // [nq]  thread positions, per river ascending HRU (share != 0)
+    M.ro_s = (uint16_t *)(smem + P.off_ro);          // [nac] thread positions, per river ascending HRU (ipriv == r)
+
+    const int tid = threadIdx.x;
+    // ---- one-time CTA setup ----
+    for (int e = tid; e < P.nnz; e += RES_THREADS) {
+        const WEntry we = C.w[e];
+        M.w_s[e] = FAST ? we.w * we.ac_src : we.w;
+        M.src_s[e] = (uint16_t)P.hru_pos[we.src];
+    }
+    for (int i = tid; i < P.nac_pad; i += RES_THREADS) {
+        const int hh = P.thread_hru[i];
+        M.ac_s[i] = hh >= 0 ? C.hru[hh].ac : 0.0;
+    }
+    for (int i = tid; i < P.nq; i += RES_THREADS) {
+        const RivChain rc = P.rivq[i];
+        M.rq_s[i] = (uint16_t)P.hru_pos[rc.ia];
+        if (FAST) {
+            M.rqc_s[i] = C.dtt * rc.w_riv * rc.share * rc.ac;
+        } else {
+            M.rqc_s[i] = rc.w_riv; M.rqc_s[(P.nq + 1) + i] = rc.share; M.rqc_s[2 * (P.nq + 1) + i] = rc.ac;
+        }
+    }
+    if (tid < 3) M.rqc_s[tid * (P.nq + 1) + P.nq] = 1.0;
+    for (int i = tid; i < C.nac; i += RES_THREADS) M.ro_s[i] = (uint16_t)P.hru_pos[P.rivo[i]];
+    if (tid == RES_CT) {
+        mbar_init(&M.bars[0], 1);
+        mbar_init(&M.bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    // ---- warp-role split with register reallocation (setmaxnreg): per SM sub-partition
+    //      4 compute warps x 112 + 1 river warp x 64 = 512 x 32 registers ----
+    if (tid < RES_CT) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RES_REGS_COMPUTE));
+        res_compute_role<S, MODE, AET>(C, W, P, M);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RES_REGS_RIVER));
+        res_river_role<S, FAST>(C, W, P, M);
+    }
+}
+#undef gc
 
 // ---------------------------------------------------------------------------------------------
 template <int S>

@@ -197,6 +197,10 @@ int  dcp_get_run_stats(const dcp_catchment *c, dcp_run_stats *out);
    denominator; returns TFLOP/s (2 flops per DFMA) in *tflops. */
 int  dcp_measure_fp64_peak(double *tflops, double *ms);
 
+/* Test hook: evaluates the FAST policy's branch-free primitives on the device
+   (op 0: exp, 1: log, 2: reciprocal) for host arrays x -> y; used by the accuracy tests. */
+int  dcp_debug_fastmath(int op, int64_t n, const double *x, double *y);
+
 #ifdef __cplusplus
 }
 #endif
