@@ -419,6 +419,8 @@ size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, b
     W.hbins = cv.take<int32_t>(C.nnode * B);
     W.qout = cv.take<double>((size_t)W.R * C.nriv * B);
     W.y = cv.take<double>((size_t)W.R * C.nnode * B);
+    if (C.qobs) { W.d2 = cv.take<double>((size_t)W.R * C.nriv * B); W.dl2 = cv.take<double>((size_t)W.R * C.nriv * B); }
+    else { W.d2 = W.dl2 = nullptr; }
     W.sse = cv.take<double>(C.nriv * B); W.lsse = cv.take<double>(C.nriv * B);
     W.bad = cv.take<int32_t>(C.nriv * B);
     W.status = cv.take<int32_t>(B);
@@ -617,14 +619,14 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
                 dbg.release();
             }
             tm.mark(T_ROUTE);
-            dcp_launch_route(C, W, 0, C.nstep, d_q, s); n_launch += 2;
+            dcp_launch_route(C, W, 0, C.nstep, d_q, s); n_launch += C.qobs ? 3 : 2;
         } else {
             for (int t0 = 0; t0 < C.nstep; t0 += tile) {
                 const int t1 = std::min(C.nstep, t0 + tile);
                 tm.mark(T_PHYS);
                 dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s); ++n_launch; ++n_phys;
                 tm.mark(T_ROUTE);
-                dcp_launch_route(C, W, t0, t1, d_q, s); n_launch += 2;
+                dcp_launch_route(C, W, t0, t1, d_q, s); n_launch += C.qobs ? 3 : 2;
             }
         }
         tm.mark(T_FIN);

@@ -93,11 +93,12 @@ struct DevBatch {
     double *sum_pptin, *sum_pein, *sumexs, *sumexus, *sdini, *srzini, *qbfini;
     double *riv_sums;               // [3][nriv][B]  sumqb, sumqof, sumqout (checked mode)
     // routing
-    double *dh;                     // [nnode][Lcap][B] normalised delay histograms
+    double *dh;                     // [B][nnode][Lcap] normalised delay histograms (bins contiguous)
     int32_t *hstart;                // [nnode][B]  node_hist_indexes(:,1)
     int32_t *hbins;                 // [nnode][B]  bin count
-    double *qout;                   // [R][nriv][B]
-    double *y;                      // [R][nnode][B]
+    double *qout;                   // [B][nriv][R]   river inflow series, time fastest
+    double *y;                      // [B][nnode][R]  routed own-reach series
+    double *d2, *dl2;               // [B][nriv][R]   per-step objective terms (null without observed flow)
     // objective accumulators [nriv][B]
     double *sse, *lsse;
     int32_t *bad;                   // [nriv][B] non-finite flow seen

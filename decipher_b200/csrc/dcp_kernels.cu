@@ -107,8 +107,8 @@ k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7
                 status |= DCP_ST_HIST_DROPPED;
                 bins = bins < 1 ? 0 : W.Lcap;
             }
-            double *dh = W.dh + (size_t)n * W.Lcap * B + m;
-            for (int k = 0; k < bins; ++k) dh[(size_t)k * B] = 0.0;
+            double *dh = W.dh + ((size_t)m * C.nnode + n) * W.Lcap;      // [member][node][bin], bins contiguous
+            for (int k = 0; k < bins; ++k) dh[k] = 0.0;
             for (int j = cb; j < ce; ++j) {
                 const double cur_a = C.cell_a[j] / chvdt1;                    // :337
                 const double cur_b = C.cell_b[j] / chvdt1;                    // :339
@@ -121,19 +121,19 @@ k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7
                 }
                 if (hist_a == hist_b) {
                     const double fr = cur_b - cur_a;
-                    dh[(size_t)(hist_a - 1) * B] = dh[(size_t)(hist_a - 1) * B] + value * fr;
+                    dh[hist_a - 1] = dh[hist_a - 1] + value * fr;
                 } else {
                     for (int k = hist_a + 1; k <= hist_b - 1; ++k)
-                        dh[(size_t)(k - 1) * B] = dh[(size_t)(k - 1) * B] + value;
+                        dh[k - 1] = dh[k - 1] + value;
                     double fr = (1.0 - (cur_a - (double)hist_a + 1.0));       // :410
-                    dh[(size_t)(hist_a - 1) * B] = dh[(size_t)(hist_a - 1) * B] + (value * fr);
+                    dh[hist_a - 1] = dh[hist_a - 1] + (value * fr);
                     fr = (cur_b - (double)hist_b + 1.0);                      // :413
-                    dh[(size_t)(hist_b - 1) * B] = dh[(size_t)(hist_b - 1) * B] + (value * fr);
+                    dh[hist_b - 1] = dh[hist_b - 1] + (value * fr);
                 }
             }
             double s = 0.0;                                                   // :347
-            for (int k = 0; k < bins; ++k) s += dh[(size_t)k * B];
-            for (int k = 0; k < bins; ++k) dh[(size_t)k * B] = dh[(size_t)k * B] / s;
+            for (int k = 0; k < bins; ++k) s += dh[k];
+            for (int k = 0; k < bins; ++k) dh[k] = dh[k] / s;
         }
         W.hstart[n * (size_t)B + m] = hstart;
         W.hbins[n * (size_t)B + m] = bins;
@@ -356,12 +356,12 @@ k_physics_streamed(DevCatchment C, DevBatch W, int t0, int t1) {
             }
         }
         // river (dyna_river.f90:42-49): qout = qb + qof
-        double *qo = W.qout + ((size_t)(t & W.Rmask) * nriv) * B + m;
+        double *qo = W.qout + (size_t)m * nriv * W.R + (t & W.Rmask);      // [member][river][time]
         double k_qb = 0, k_qof = 0, k_out = 0;
         for (int r = 0; r < nriv; ++r) {
             const double qb = s_qb[r * nthr], qof = s_qof[r * nthr];
             const double qout = qb + qof;
-            qo[(size_t)r * B] = qout;
+            qo[(size_t)r * W.R] = qout;
             if (CHECK) {
                 double *rs = W.riv_sums + m;
                 const double a = rs[(0 * nriv + r) * (size_t)B] + qb;     // sumqb (dyna_dynamic_dist.f90:63-65)
@@ -386,52 +386,71 @@ k_physics_streamed(DevCatchment C, DevBatch W, int t0, int t1) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// K3a: y_n(t) = flow_matrix(n, node_hist_indexes(n,1)) at step t
-//      = sum_k delay_hist_n(k) * qout_n(t-k), accumulated oldest first exactly like the reference's
-//        add-then-shift matrix (DTA/dta_route_processing.f90:671-681, 723-727).
-// Thread = (member, node); sequential over the tile's steps.
+// Routing.  The reference keeps a flow matrix per node that is incremented by histogram*inflow and
+// shifted one column per step (DTA/dta_route_processing.f90:671-681, 723-727).  Column
+// node_hist_indexes(n,1) of row n therefore carries the FIR
+//     y_n(t) = sum_k delay_hist_n(k) * qout_n(t-k),   accumulated oldest term first,
+// and a column further downstream is the same series delayed.  Both facts make the routing
+// time-parallel: one thread per (member, node, timestep), lanes along time so that the inflow window
+// and the y series are read as coalesced, sliding lines ([member][node][time] layouts) and the
+// histogram taps are broadcast.  The accumulation order per output equals the reference's.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-k_route_conv(DevCatchment C, DevBatch W, int t0, int t1) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    const int n = blockIdx.y;
+#define ROUTE_CH 256        // timesteps per block
+
+// K3a: y_n(t) for t in [t0, t1)
+__global__ void __launch_bounds__(ROUTE_CH)
+k_route_conv(DevCatchment C, DevBatch W, int t0, int t1, int use_smem) {
+    extern __shared__ double s_route[];              // taps[Lcap] | window[Lcap + ROUTE_CH]
+    const int m = blockIdx.x, n = blockIdx.y;
+    const int tb = t0 + blockIdx.z * ROUTE_CH;        // first step of this block
+    const int t = tb + threadIdx.x;
     const int B = W.B;
-    if (m >= B) return;
     const int riv = C.node_input[n];
     const int bins = W.hbins[n * (size_t)B + m];
-    const double *dh = W.dh + (size_t)n * W.Lcap * B + m;
-    const int Rm = W.Rmask;
-    for (int t = t0; t < t1; ++t) {
-        double y = 0.0;
-        if (riv >= 0) {
-            int k = bins - 1;
-            if (k > t) k = t;
-            for (; k >= 0; --k) {
-                const double q = W.qout[((size_t)((t - k) & Rm) * C.nriv + riv) * B + m];
-                y = y + dh[(size_t)k * B] * q;
-            }
-        }
-        W.y[((size_t)(t & Rm) * C.nnode + n) * B + m] = y;
+    const size_t R = W.R;
+    double *yo = W.y + ((size_t)m * C.nnode + n) * R;
+    if (riv < 0 || bins <= 0) {
+        if (t < t1) yo[t & W.Rmask] = 0.0;
+        return;
     }
+    const double *dh = W.dh + ((size_t)m * C.nnode + n) * W.Lcap;
+    const double *qi = W.qout + ((size_t)m * C.nriv + riv) * R;
+    double y = 0.0;
+    if (use_smem) {
+        double *taps = s_route, *win = s_route + W.Lcap;
+        for (int k = threadIdx.x; k < bins; k += ROUTE_CH) taps[k] = dh[k];
+        // window element j holds qout(tb - (bins-1) + j)
+        const int wlen = bins - 1 + ROUTE_CH;
+        for (int j = threadIdx.x; j < wlen; j += ROUTE_CH) {
+            const int tt = tb - (bins - 1) + j;
+            win[j] = (tt >= 0 && tt < t1) ? qi[tt & W.Rmask] : 0.0;
+        }
+        __syncthreads();
+        if (t < t1) {
+            int k = bins - 1;
+            if (k > t) k = t;                        // terms before the first timestep do not exist
+            const double *wp = win + (bins - 1) + threadIdx.x;
+            for (; k >= 0; --k) y = y + taps[k] * wp[-k];
+        }
+    } else if (t < t1) {
+        int k = bins - 1;
+        if (k > t) k = t;
+        for (; k >= 0; --k) y = y + dh[k] * qi[(t - k) & W.Rmask];
+    }
+    if (t < t1) yo[t & W.Rmask] = y;
 }
 
-// ------------------------------------------------------------------------------------------------
-// K3b: q(iriv, t) = sum over {node, upstream tree} of flow_matrix(node', c_i), / frac_sub_area
-//      (DTA/dta_route_processing.f90:685-714, RRMODEL/dyna_river.f90:57-59), then the objective sums.
-// For an upstream row u, column c_i lies before u's own histogram, so flow_matrix(u, c_i)(t) is
-// y_u delayed by (hstart_u - c_i) steps; the general case (c_i inside u's histogram) is summed directly.
-// Thread = (member, gauge).
-// ------------------------------------------------------------------------------------------------
+// flow_matrix(u, col) at step t (col = the gauge's sum_index)
 __device__ __forceinline__ double node_at_column(const DevCatchment &C, const DevBatch &W, int m, int u,
                                                  int col, int t) {
-    const int B = W.B, Rm = W.Rmask;
+    const int B = W.B;
     const int hs = W.hstart[u * (size_t)B + m];
     const int bins = W.hbins[u * (size_t)B + m];
     if (bins <= 0) return 0.0;
     const int d = hs - col;
-    if (d >= 0) {
+    if (d >= 0) {                                    // column upstream of u's histogram: pure delay
         if (t - d < 0) return 0.0;
-        return W.y[((size_t)((t - d) & Rm) * C.nnode + u) * B + m];
+        return W.y[((size_t)m * C.nnode + u) * W.R + ((t - d) & W.Rmask)];
     }
     // column inside (or past) the histogram of u: partial sum, oldest first
     const int riv = C.node_input[u];
@@ -440,46 +459,61 @@ __device__ __forceinline__ double node_at_column(const DevCatchment &C, const De
     double y = 0.0;
     int k = bins - 1 - o;
     if (k > t) k = t;
-    const double *dh = W.dh + (size_t)u * W.Lcap * B + m;
-    for (; k >= 0; --k)
-        y = y + dh[(size_t)(k + o) * B] * W.qout[((size_t)((t - k) & Rm) * C.nriv + riv) * B + m];
+    const double *dh = W.dh + ((size_t)m * C.nnode + u) * W.Lcap;
+    const double *qi = W.qout + ((size_t)m * C.nriv + riv) * W.R;
+    for (; k >= 0; --k) y = y + dh[k + o] * qi[(t - k) & W.Rmask];
     return y;
 }
 
-__global__ void __launch_bounds__(128)
+// K3b: q(iriv, t) = (own node + upstream tree at the gauge's column) / frac_sub_area
+//      (DTA/dta_route_processing.f90:685-714, RRMODEL/dyna_river.f90:57-59) and the per-step objective terms.
+__global__ void __launch_bounds__(ROUTE_CH)
 k_route_gauge(DevCatchment C, DevBatch W, int t0, int t1, double *__restrict__ q_out /*[nriv x nstep x B] or null*/) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;                      // river / output index; flow_output_indexes(i) = i
+    const int m = blockIdx.x, i = blockIdx.y;        // river / output index; flow_output_indexes(i) = i
+    const int t = t0 + blockIdx.z * ROUTE_CH + threadIdx.x;
+    if (t >= t1) return;
     const int B = W.B;
-    if (m >= B) return;
-    const int col = W.hstart[i * (size_t)B + m];   // sum_index
-    const double frac = C.frac_sub_area[i];
-    double sse = W.sse[i * (size_t)B + m], lsse = W.lsse[i * (size_t)B + m];
-    int bad = W.bad[i * (size_t)B + m];
-    const bool obj = (C.qobs != nullptr);
-    ObsStat os;
-    if (obj) os = C.obs[i];
-    const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
-    for (int t = t0; t < t1; ++t) {
-        double q_sum = 0.0;
-        q_sum = q_sum + node_at_column(C, W, m, i, col, t);
-        for (int e = C.up_beg[i]; e < C.up_beg[i + 1]; ++e)
-            q_sum = q_sum + node_at_column(C, W, m, C.up_idx[e], col, t);
-        const double q = q_sum / frac;
-        if (q_out) q_out[((size_t)m * C.nstep + t) * C.nriv + i] = q;
-        if (!isfinite(q)) bad = 1;
-        if (obj && t >= C.t_warm && t < n_t) {
+    const int col = W.hstart[i * (size_t)B + m];     // sum_index
+    double q_sum = 0.0;
+    q_sum = q_sum + node_at_column(C, W, m, i, col, t);
+    for (int e = C.up_beg[i]; e < C.up_beg[i + 1]; ++e) q_sum = q_sum + node_at_column(C, W, m, C.up_idx[e], col, t);
+    const double q = q_sum / C.frac_sub_area[i];
+    if (q_out) q_out[((size_t)m * C.nstep + t) * C.nriv + i] = q;
+    if (!isfinite(q)) W.bad[i * (size_t)B + m] = 1;
+    if (C.qobs != nullptr) {
+        double d2 = 0.0, dl2 = 0.0;
+        const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
+        if (t >= C.t_warm && t < n_t) {
             const double o = C.qobs[(size_t)t * C.nriv + i];
             if (o != C.flow_err) {
-                sse = sse + (q - o) * (q - o);
-                const double dl = log(q > os.eps ? q : os.eps) - log(o > os.eps ? o : os.eps);
-                lsse = lsse + dl * dl;
+                const double eps = C.obs[i].eps;
+                d2 = (q - o) * (q - o);
+                const double dl = log(q > eps ? q : eps) - log(o > eps ? o : eps);
+                dl2 = dl * dl;
             }
         }
+        const size_t o2 = ((size_t)m * C.nriv + i) * W.R + (t & W.Rmask);
+        W.d2[o2] = d2;
+        W.dl2[o2] = dl2;
     }
-    W.sse[i * (size_t)B + m] = sse;
-    W.lsse[i * (size_t)B + m] = lsse;
-    W.bad[i * (size_t)B + m] = bad;
+}
+
+// K3c: sums of the objective terms in ascending time order (one thread per member x gauge; adding the
+// zero of a masked step leaves the sum unchanged, so the result equals a sum over the valid steps only)
+__global__ void __launch_bounds__(128)
+k_objective_sum(DevCatchment C, DevBatch W, int t0, int t1) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.y;
+    if (m >= W.B) return;
+    const double *d2 = W.d2 + ((size_t)m * C.nriv + i) * W.R;
+    const double *dl2 = W.dl2 + ((size_t)m * C.nriv + i) * W.R;
+    double sse = W.sse[i * (size_t)W.B + m], lsse = W.lsse[i * (size_t)W.B + m];
+    for (int t = t0; t < t1; ++t) {
+        sse = sse + d2[t & W.Rmask];
+        lsse = lsse + dl2[t & W.Rmask];
+    }
+    W.sse[i * (size_t)W.B + m] = sse;
+    W.lsse[i * (size_t)W.B + m] = lsse;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -596,9 +630,17 @@ void dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t
 }
 
 void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s) {
-    dim3 g1(cdiv(W.B, 128), C.nnode), g2(cdiv(W.B, 128), C.nriv);
-    k_route_conv<<<g1, 128, 0, s>>>(C, W, t0, t1);
-    k_route_gauge<<<g2, 128, 0, s>>>(C, W, t0, t1, q_out);
+    const int nchunk = cdiv(t1 - t0, ROUTE_CH);
+    const size_t smem = ((size_t)2 * W.Lcap + ROUTE_CH) * sizeof(double);
+    const int use_smem = smem <= 96 * 1024;
+    if (use_smem && smem > 48 * 1024) cudaFuncSetAttribute(k_route_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    dim3 g1(W.B, C.nnode, nchunk), g2(W.B, C.nriv, nchunk);      // members on grid.x (no 65535 limit)
+    k_route_conv<<<g1, ROUTE_CH, use_smem ? smem : 0, s>>>(C, W, t0, t1, use_smem);
+    k_route_gauge<<<g2, ROUTE_CH, 0, s>>>(C, W, t0, t1, q_out);
+    if (C.qobs != nullptr) {
+        dim3 g3(cdiv(W.B, 128), C.nriv);
+        k_objective_sum<<<g3, 128, 0, s>>>(C, W, t0, t1);
+    }
 }
 
 void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,

@@ -219,6 +219,23 @@ struct LeanOut {
     bool slow;
 };
 
+// accuracy experiments (tools/err_probe.py): swap single primitives of the lean step for the library ones
+#ifdef DCP_LEAN_LIBM_EXP
+#define LEAN_EXP(x) exp(x)
+#else
+#define LEAN_EXP(x) fm_exp(x)
+#endif
+#ifdef DCP_LEAN_LIBM_LOG
+#define LEAN_LOG(x) log(x)
+#else
+#define LEAN_LOG(x) fm_log(x)
+#endif
+#ifdef DCP_LEAN_TRUE_DIV
+#define LEAN_DIV(a, b) ((a) / (b))
+#else
+#define LEAN_DIV(a, b) ((a) * fm_rcp(b))
+#endif
+
 __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst &g, double p, double epp,
                                               double qin, HruState &s, LeanOut &o) {
     // root_zone1 (dyna_root_zone1.f90:39-66)
@@ -235,7 +252,7 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     const double exus = fm_max(suz - lim, 0.0);
     suz = fm_min(suz, lim);
     const double den = sd0 * c.td;
-    double uz2 = g.dt * (suz * fm_rcp(den));
+    double uz2 = g.dt * LEAN_DIV(suz, den);
     uz2 = (den > 1e-290) ? fm_min(uz2, suz) : suz;       // tiny sd*td: suz/(sd*td) overflows, clipped to suz
     uz2 = (sd0 > 0.0 && suz > 0.0) ? uz2 : 0.0;
     suz = suz - uz2;
@@ -248,15 +265,18 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     const double u = qin_ac + uz;
     const double u2 = c.q2 + u;
     const double a = (u2 * g.dtt) * c.inv_m2;
-    const double x1 = sd0 * c.inv_m2;
-    const double e1 = fm_exp(x1);
-    const double r = c.q1 * fm_rcp(u2);
-    const double e2 = fm_exp(-a);
+    // sd/m2 enters an exponential, so its rounding error is amplified by |sd/m2| (up to a few hundred):
+    // one Newton correction makes the quotient faithful to the reference's sd/m2
+    double x1 = sd0 * c.inv_m2;
+    x1 = fma(fma(-x1, c.m2, sd0), c.inv_m2, x1);
+    const double e1 = LEAN_EXP(x1);
+    const double r = LEAN_DIV(c.q1, u2);
+    const double e2 = LEAN_EXP(-a);
     const double b = (c.q1 * g.dtt) * c.inv_m2;
     const double arg_small = (e1 + b) - a * (e1 - 0.5 * b);      // :76-77 (and :84 when u2 == 0)
     const double arg_reg = fma(e1 - r, e2, r);                    // :80
     const double arg = (a < DCP_F32_1EM10) ? arg_small : arg_reg;
-    double sd = c.m2 * fm_log(arg);
+    double sd = c.m2 * LEAN_LOG(arg);
     o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !(arg > 1e-290 && arg < 1e290);
     double qbf = (sd - sd0) * g.inv_dtt + uz + qin_ac;            // :98
     double exs = fm_max(-sd, 0.0);                                // :107-112

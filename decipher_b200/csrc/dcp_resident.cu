@@ -30,8 +30,8 @@
 
 #define RES_CT DCP_RES_COMPUTE        // compute threads (4 warpgroups)
 #define RES_THREADS (RES_CT + 128)    // + one warpgroup of river warps: 5 warps per SM sub-partition
-#define RES_REGS_COMPUTE 104          // after setmaxnreg: launch allocation is 96/thread; the river warpgroup gives up (96-56)x128 registers, the compute warpgroups take (104-96)x512 of them
-#define RES_REGS_RIVER 56
+#define RES_REGS_COMPUTE 112          // after setmaxnreg: launch allocation is 96/thread; the river warpgroup gives up (96-32)x128 registers, the compute warpgroups take exactly those: (112-96)x512
+#define RES_REGS_RIVER 32
 #define RES_MAXPASS 4                 // chains per river lane
 #define RES_PARW 6                    // srmax, td, smax, szm, 1/srmax, 1/szm
 
@@ -201,25 +201,48 @@ __device__ __forceinline__ void res_compute_role(const DevCatchment &C, const De
                     const double *cst = M.cst_s + tid;
                     if (LEAN) {
                         const double epp = fm_max(ep, 0.0);
+                        // DCP_RES_LG member slots per basic block: their dependency chains interleave (ILP)
 #pragma unroll
-                        for (int k = 0; k < S; ++k) {
-                            const double *pp = my_par + k * par_kstride;
-                            HruConst c;
-                            c.ac = h.ac; c.inv_ac = inv_ac;
-                            c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
-                            c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
-                            c.inv_m2 = cst[(4 * S + k) * RES_CT];
-                            c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
-                            c.ims_rz = 1; c.ims_uz = 1;
-                            HruState st;
-                            st.sd = sd[k]; st.suz = suz[k]; st.srz = srz[k]; st.qint1 = 0.0;
-                            LeanOut lo;
-                            hru_step_lean(c, gc, p, epp, qin[k], st, lo);
-                            sd[k] = st.sd; suz[k] = st.suz; srz[k] = st.srz;                         // qint1 is not carried:
-                            if (lo.slow) hru_step_lean_fixup(c, gc, qin[k], qin[k], sd[k], lo);      // ntt == 1 => qin2 == qin/ac
-                            qo[k] = lo.qbf;
-                            exo[k * RES_CT] = lo.exac;
-                            if (AET) aet[k] = aet[k] + lo.ea;
+                        for (int k0 = 0; k0 < S; k0 += DCP_RES_LG) {
+                            LeanOut lo[DCP_RES_LG];
+                            bool any_slow = false;
+#pragma unroll
+                            for (int j = 0; j < DCP_RES_LG; ++j) {
+                                const int k = k0 + j;
+                                const double *pp = my_par + k * par_kstride;
+                                HruConst c;
+                                c.ac = h.ac; c.inv_ac = inv_ac;
+                                c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
+                                c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
+                                c.inv_m2 = cst[(4 * S + k) * RES_CT];
+                                c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
+                                c.ims_rz = 1; c.ims_uz = 1;
+                                HruState st;
+                                st.sd = sd[k]; st.suz = suz[k]; st.srz = srz[k]; st.qint1 = 0.0;
+                                hru_step_lean(c, gc, p, epp, qin[k], st, lo[j]);
+                                sd[k] = st.sd; suz[k] = st.suz; srz[k] = st.srz;      // qint1 is not carried: ntt == 1 => qin2 == qin/ac
+                                any_slow |= lo[j].slow;
+                            }
+                            if (any_slow) {                                            // rare: constants are re-read, not kept live
+#pragma unroll
+                                for (int j = 0; j < DCP_RES_LG; ++j)
+                                    if (lo[j].slow) {
+                                        const int k = k0 + j;
+                                        HruConst c;
+                                        c.ac = h.ac; c.inv_ac = inv_ac;
+                                        c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
+                                        c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
+                                        c.inv_m2 = cst[(4 * S + k) * RES_CT];
+                                        c.smax = (my_par + k * par_kstride)[2];
+                                        hru_step_lean_fixup(c, gc, qin[k], qin[k], sd[k], lo[j]);
+                                    }
+                            }
+#pragma unroll
+                            for (int j = 0; j < DCP_RES_LG; ++j) {
+                                qo[k0 + j] = lo[j].qbf;
+                                exo[(k0 + j) * RES_CT] = lo[j].exac;
+                                if (AET) aet[k0 + j] = aet[k0 + j] + lo[j].ea;
+                            }
                         }
                     } else {
 #pragma unroll
@@ -363,7 +386,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
                         if (type == 0 && live && sub == 0) {
                             const int m = m_base + jm;
                             if (t > 0 && m < B)
-                                W.qout[((size_t)((t - 1) & W.Rmask) * nriv + r) * B + m] = qb_prev[q] + qof;   // dyna_river.f90:43
+                                W.qout[((size_t)m * nriv + r) * W.R + ((t - 1) & W.Rmask)] = qb_prev[q] + qof;   // dyna_river.f90:43
                         }
                         if (type == 0) qb_prev[q] = acc;
                     }
