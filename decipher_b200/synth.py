@@ -116,13 +116,13 @@ def make_raw(nac=24, nriv=2, npt=3, ngp=2, nge=1, nstep=8760, kW=4, seed=BASE_SE
             dist = ds_dist + cell_m
             rows.append((gauge_id[n], area[j], dist, j * cell_m, elev0 + 0.002 * (j + 1) * cell_m, 0.002,
                          ds_dist, elev0 + 0.002 * j * cell_m))
-    raw["river_data"] = np.asfortranarray(np.array(rows, dtype=np.float64))
-    raw["flow_point"] = np.array([(gauge_id[n], 1000.0 + n, 2000.0 + n, 2, outlet_dist[n], 10.0 + 0.002 * outlet_dist[n])
-                                  for n in range(nriv)], dtype=np.float64)
-    raw["flow_conn"] = np.array([(gauge_id[n], 1000.0 + n, 2000.0 + n, 2,
+    raw["river_data"] = np.asfortranarray(quant(np.array(rows, dtype=np.float64), 3))     # written with 3 decimals
+    raw["flow_point"] = quant(np.array([(gauge_id[n], 1000.0 + n, 2000.0 + n, 2, outlet_dist[n], 10.0 + 0.002 * outlet_dist[n])
+                                  for n in range(nriv)], dtype=np.float64), 3)
+    raw["flow_conn"] = quant(np.array([(gauge_id[n], 1000.0 + n, 2000.0 + n, 2,
                                   gauge_id[down[n] - 1] if down[n] > 0 else 0,
                                   0.0, 0.0, length[down[n] - 1] if down[n] > 0 else 0.0, 1.0, 0.002)
-                                 for n in range(nriv)], dtype=np.float64)
+                                 for n in range(nriv)], dtype=np.float64), 3)
 
     # ---- forcing: hourly rain (m/ts), PET, synthetic "observed" flow
     wet = rng.uniform(size=(ngp, nstep)) < 0.10
