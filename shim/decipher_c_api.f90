@@ -1,0 +1,74 @@
+! decipher_c_api.f90 -- ISO_C_BINDING interface to libdecipher_b200.so (include/decipher_b200.h).
+!
+! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (gfortran, flang,
+! nvfortran and ifort are all absent), so this module is shipped as source, written 1:1 against the C
+! header.  Every derived-type component below has the same order, kind and meaning as the field of
+! the same name in `dcp_catchment_desc` / `dcp_run_opts`.
+!
+! Use: add this file and shim/dyna_main_gpu.f90 to RRMODEL's makefile sources, drop dyna_main.f90,
+! link with -ldecipher_b200 -lcudart.  All the reference's setup routines (project, Tread_dyna,
+! Inputs, mc_setup, modelstruct_setup, read_routingdata, genpar, write_output's formats) stay Fortran.
+module decipher_c_api
+    use, intrinsic :: iso_c_binding
+    implicit none
+
+    integer(c_int), parameter :: DCP_OK = 0
+    integer(c_int32_t), parameter :: DCP_OPT_CHECK_BALANCE = 1, DCP_OPT_DEVICE_BUFFERS = 2, DCP_OPT_FAST_MATH = 4
+    integer(c_int32_t), parameter :: DCP_ST_SOLFLAG_MASK = 3, DCP_ST_RZ_BALANCE = 4, DCP_ST_TS_OUTSUM = 8, &
+                                     DCP_ST_TS_WBAL = 16, DCP_ST_NONFINITE = 32, DCP_ST_INIT_ITERCAP = 64, &
+                                     DCP_ST_HIST_DROPPED = 128
+    integer(c_int), parameter :: DCP_NMEASURE = 2
+
+    type, bind(C) :: dcp_catchment_desc
+        integer(c_int32_t) :: struct_size, nac, nriv, npt, nstep, ngp, nge, ntt
+        real(c_double)     :: dt
+        type(c_ptr) :: ac, st, mslp                          ! real(c_double) (nac)
+        type(c_ptr) :: ippt, ipet, ipar, ipriv, ims_rz, ims_uz   ! integer(c_int32_t) (nac), 1-based values
+        type(c_ptr) :: ntrans, itrans, wtrans                ! (nac), (sum ntrans), (sum ntrans+1)
+        type(c_ptr) :: rivers, sum_ac_riv, qobs_start        ! (nac,nriv), (nriv), (nriv)
+        integer(c_int32_t) :: nnode, ncell
+        type(c_ptr) :: node_gauge_id, node_type, uptree_count, uptree_index
+        type(c_ptr) :: frac_sub_area, river_data, node_to_flow_mapping
+        type(c_ptr) :: rain, pet                             ! r_gau_step(ngp,nstep), pe_step(nge,nstep)
+        type(c_ptr) :: qobs                                  ! qobs_riv_step(nriv,nstep_obs) or c_null_ptr
+        integer(c_int32_t) :: nstep_obs, t_warm
+        real(c_double)     :: flow_err
+    end type
+
+    type, bind(C) :: dcp_run_opts
+        integer(c_int32_t) :: struct_size, flags, kernel, members_per_batch, steps_per_tile, reserved
+    end type
+
+    interface
+        integer(c_int) function dcp_device_count() bind(C, name="dcp_device_count")
+            import :: c_int
+        end function
+        integer(c_int) function dcp_set_device(device) bind(C, name="dcp_set_device")
+            import :: c_int
+            integer(c_int), value :: device
+        end function
+        type(c_ptr) function dcp_last_error() bind(C, name="dcp_last_error")
+            import :: c_ptr
+        end function
+        integer(c_int) function dcp_catchment_create(desc, handle) bind(C, name="dcp_catchment_create")
+            import :: c_int, c_ptr, dcp_catchment_desc
+            type(dcp_catchment_desc), intent(in) :: desc
+            type(c_ptr), intent(out) :: handle
+        end function
+        integer(c_int) function dcp_catchment_destroy(handle) bind(C, name="dcp_catchment_destroy")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: handle
+        end function
+        ! mcpar(npt,7,n_member) in/out; q_out(nriv,nstep,n_member); perf_out(2,nriv,n_member);
+        ! reach_totals(3,nriv,n_member); init_diag(3,n_member); status(n_member).  Pass c_null_ptr to skip an output.
+        integer(c_int) function dcp_run_ensemble(handle, first_member, n_member, mcpar, opts, q_out, perf_out, &
+                                                 reach_totals, init_diag, status) bind(C, name="dcp_run_ensemble")
+            import :: c_int, c_int64_t, c_ptr, dcp_run_opts
+            type(c_ptr), value :: handle
+            integer(c_int64_t), value :: first_member, n_member
+            type(c_ptr), value :: mcpar
+            type(dcp_run_opts), intent(in) :: opts
+            type(c_ptr), value :: q_out, perf_out, reach_totals, init_diag, status
+        end function
+    end interface
+end module decipher_c_api
