@@ -39,15 +39,29 @@ __global__ void k_min_chv(const double *__restrict__ mcpar, int npt, int64_t n_m
 }
 
 // ------------------------------------------------------------------------------------------------
-// K1: per-member initialisation
+// K1: per-member initialisation — one WARP per member
 // ------------------------------------------------------------------------------------------------
-// calculate_qb (RRMODEL/dyna_init_satzone.f90:266-294) without storing: returns qb_tmp
+// The init search (dyna_init_satzone.f90:134-174) has a data-dependent trip count (a handful to
+// thousands of iterations, each O(nac) with an exp per HRU), so a thread-per-member kernel is bound by
+// its slowest thread.  Here the lanes of a warp share the HRUs of ONE member: calculate_qb runs 32 HRUs
+// at a time and its river sum is a strided partial sum + shuffle tree (the only place where the
+// summation order differs from the reference's ascending-HRU order; the search compares that sum with
+// a 1e-5 tolerance, so a last-bit difference cannot change the path except at measure-zero ties).
+// Everything order-sensitive that is cheap — the area-weighted means, the routing histogram — stays
+// sequential on lane 0 in the reference's order.
+
+__device__ __forceinline__ double warp_sum(double v) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// calculate_qb (RRMODEL/dyna_init_satzone.f90:266-294): lanes stride over the HRUs
 template <bool STORE>
-__device__ __forceinline__ double calc_qb(const DevCatchment &C, const DevBatch &W, int m, double D,
+__device__ __forceinline__ double calc_qb(const DevCatchment &C, const DevBatch &W, int m, int lane, double D,
                                           double meanatb, double meanT0DT) {
     const int B = W.B, npt = C.npt;
-    double qb_tmp = 0.0;
-    for (int ia = 0; ia < C.nac; ++ia) {
+    double part = 0.0;
+    for (int ia = lane; ia < C.nac; ia += 32) {
         const HruStatic h = C.hru[ia];
         const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
         const double smax = W.par[(6 * npt + h.ipar) * (size_t)B + m];
@@ -69,112 +83,127 @@ __device__ __forceinline__ double calc_qb(const DevCatchment &C, const DevBatch 
         const double base = C.dt * qbf * h.w_riv;                             // :289  (dt*qbf)*w
         for (int e = h.riv_beg; e < h.riv_end; ++e) {
             const RivEntry r = C.riv[e];
-            qb_tmp = qb_tmp + (base * r.share * h.ac);
+            part = part + (base * r.share * h.ac);
         }
     }
-    return qb_tmp;
+    return warp_sum(part);
 }
 
 template <bool CHECK>
 __global__ void __launch_bounds__(128)
 k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7 x B]*/) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    const int m = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
     const int B = W.B;
-    if (m >= B) return;
+    if (m >= B) return;                                                       // whole warp leaves together
     const int npt = C.npt, nac = C.nac;
     int status = 0;
 
     // ---- param_setup (RRMODEL/dyna_param_setup.f90:58-70) ----
     double *mp = mcpar + (size_t)m * npt * 7;
-    for (int i = 0; i < npt; ++i) {
+    for (int i = lane; i < npt; i += 32) {
         for (int p = 0; p < 7; ++p) W.par[(p * npt + i) * (size_t)B + m] = mp[p * npt + i];
         W.t0dt[i * (size_t)B + m] = mp[1 * npt + i] + C.log_dt;
     }
+    __syncwarp();
     const double chvdt1 = mp[4 * npt + 0] * C.dt;                             // dyna_init_satzone.f90:85
 
-    // ---- route_processing_build_hist (DTA/dta_route_processing.f90:154-354), v = chvdt(1) ----
-    for (int n = 0; n < C.nnode; ++n) {
-        const int cb = C.node_cell_beg[n], ce = C.node_cell_end[n];
-        int hstart = 0, bins = 0;
-        if (cb >= 0) {
-            const double reach_delay = C.node_reach_dist[n] / chvdt1;         // :231
-            const double tdd = C.node_down_dist[n] / chvdt1;                  // :241
-            const double full_delay = reach_delay + tdd;                      // :256
-            hstart = (int)floor(tdd) + 1;                                     // :259
-            const int hend = (int)ceil(full_delay) + 1;                       // :260
-            bins = (hend - hstart) + 1;                                       // :312
-            if (bins > W.Lcap || bins < 1) {                                  // sized from the slowest member
-                status |= DCP_ST_HIST_DROPPED;
-                bins = bins < 1 ? 0 : W.Lcap;
-            }
-            double *dh = W.dh + ((size_t)m * C.nnode + n) * W.Lcap;      // [member][node][bin], bins contiguous
-            for (int k = 0; k < bins; ++k) dh[k] = 0.0;
-            for (int j = cb; j < ce; ++j) {
-                const double cur_a = C.cell_a[j] / chvdt1;                    // :337
-                const double cur_b = C.cell_b[j] / chvdt1;                    // :339
-                const double value = C.cell_area[j];
-                const int hist_a = (int)floor(cur_a) + 1;                     // hist_add_value :369-370
-                const int hist_b = (int)floor(cur_b) + 1;
-                if (hist_b > bins || hist_a < 1) {                            // :378-382 drops the cell
+    // ---- route_processing_build_hist (DTA/dta_route_processing.f90:154-354), v = chvdt(1); lane 0, reference order ----
+    if (lane == 0) {
+        for (int n = 0; n < C.nnode; ++n) {
+            const int cb = C.node_cell_beg[n], ce = C.node_cell_end[n];
+            int hstart = 0, bins = 0;
+            if (cb >= 0) {
+                const double reach_delay = C.node_reach_dist[n] / chvdt1;     // :231
+                const double tdd = C.node_down_dist[n] / chvdt1;              // :241
+                const double full_delay = reach_delay + tdd;                  // :256
+                hstart = (int)floor(tdd) + 1;                                 // :259
+                const int hend = (int)ceil(full_delay) + 1;                   // :260
+                bins = (hend - hstart) + 1;                                   // :312
+                if (bins > W.Lcap || bins < 1) {                              // sized from the slowest member
                     status |= DCP_ST_HIST_DROPPED;
-                    continue;
+                    bins = bins < 1 ? 0 : W.Lcap;
                 }
-                if (hist_a == hist_b) {
-                    const double fr = cur_b - cur_a;
-                    dh[hist_a - 1] = dh[hist_a - 1] + value * fr;
-                } else {
-                    for (int k = hist_a + 1; k <= hist_b - 1; ++k)
-                        dh[k - 1] = dh[k - 1] + value;
-                    double fr = (1.0 - (cur_a - (double)hist_a + 1.0));       // :410
-                    dh[hist_a - 1] = dh[hist_a - 1] + (value * fr);
-                    fr = (cur_b - (double)hist_b + 1.0);                      // :413
-                    dh[hist_b - 1] = dh[hist_b - 1] + (value * fr);
+                double *dh = W.dh + ((size_t)m * C.nnode + n) * W.Lcap;       // [member][node][bin], bins contiguous
+                for (int k = 0; k < bins; ++k) dh[k] = 0.0;
+                for (int j = cb; j < ce; ++j) {
+                    const double cur_a = C.cell_a[j] / chvdt1;                // :337
+                    const double cur_b = C.cell_b[j] / chvdt1;                // :339
+                    const double value = C.cell_area[j];
+                    const int hist_a = (int)floor(cur_a) + 1;                 // hist_add_value :369-370
+                    const int hist_b = (int)floor(cur_b) + 1;
+                    if (hist_b > bins || hist_a < 1) {                        // :378-382 drops the cell
+                        status |= DCP_ST_HIST_DROPPED;
+                        continue;
+                    }
+                    if (hist_a == hist_b) {
+                        const double fr = cur_b - cur_a;
+                        dh[hist_a - 1] = dh[hist_a - 1] + value * fr;
+                    } else {
+                        for (int k = hist_a + 1; k <= hist_b - 1; ++k) dh[k - 1] = dh[k - 1] + value;
+                        double fr = (1.0 - (cur_a - (double)hist_a + 1.0));   // :410
+                        dh[hist_a - 1] = dh[hist_a - 1] + (value * fr);
+                        fr = (cur_b - (double)hist_b + 1.0);                  // :413
+                        dh[hist_b - 1] = dh[hist_b - 1] + (value * fr);
+                    }
                 }
+                double s = 0.0;                                               // :347
+                for (int k = 0; k < bins; ++k) s += dh[k];
+                for (int k = 0; k < bins; ++k) dh[k] = dh[k] / s;
             }
-            double s = 0.0;                                                   // :347
-            for (int k = 0; k < bins; ++k) s += dh[k];
-            for (int k = 0; k < bins; ++k) dh[k] = dh[k] / s;
+            W.hstart[n * (size_t)B + m] = hstart;
+            W.hbins[n * (size_t)B + m] = bins;
         }
-        W.hstart[n * (size_t)B + m] = hstart;
-        W.hbins[n * (size_t)B + m] = bins;
     }
 
     // ---- init_satzone (RRMODEL/dyna_init_satzone.f90:92-213) ----
-    double mean_q = 0.0;
-    for (int r = 0; r < C.nriv; ++r) mean_q = mean_q + C.qobs_start[r] * C.sum_ac_riv[r];
-    double meanatb = 0.0, meanT0DT = 0.0, meanSZM = 0.0;
-    for (int ia = 0; ia < nac; ++ia) {
+    // q0 (:108) and the hoisted q2 of dyna_satzone_analyticalsolver.f90:50-51 per HRU: independent, all lanes
+    for (int ia = lane; ia < nac; ia += 32) {
         const HruStatic h = C.hru[ia];
         const double t0 = W.t0dt[h.ipar * (size_t)B + m];
         const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
         const double smax = W.par[(6 * npt + h.ipar) * (size_t)B + m];
-        meanatb = meanatb + (h.st * h.ac);
-        meanT0DT = meanT0DT + (t0 * h.ac);
-        meanSZM = meanSZM + (szm * h.ac);
-        const double q0 = exp(t0 - h.st);                                     // :108
+        const double q0 = exp(t0 - h.st);
         W.q0[ia * (size_t)B + m] = q0;
-        // q2 of dyna_satzone_analyticalsolver.f90:50-51 is time invariant: hoisted here
         W.q2[ia * (size_t)B + m] = q0 * h.cosm * exp(-1.0 * h.cosm * smax / szm);
     }
+    // the area-weighted means in ascending HRU order (:92-105) on lane 0, broadcast
+    double mean_q = 0.0, meanatb = 0.0, meanT0DT = 0.0, meanSZM = 0.0;
+    if (lane == 0) {
+        for (int r = 0; r < C.nriv; ++r) mean_q = mean_q + C.qobs_start[r] * C.sum_ac_riv[r];
+        for (int ia = 0; ia < nac; ++ia) {
+            const HruStatic h = C.hru[ia];
+            meanatb = meanatb + (h.st * h.ac);
+            meanT0DT = meanT0DT + (W.t0dt[h.ipar * (size_t)B + m] * h.ac);
+            meanSZM = meanSZM + (W.par[(0 * npt + h.ipar) * (size_t)B + m] * h.ac);
+        }
+    }
+    mean_q = __shfl_sync(0xffffffffu, mean_q, 0);
+    meanatb = __shfl_sync(0xffffffffu, meanatb, 0);
+    meanT0DT = __shfl_sync(0xffffffffu, meanT0DT, 0);
+    meanSZM = __shfl_sync(0xffffffffu, meanSZM, 0);
+    __syncwarp();                                                             // q0 stores visible to every lane
     const double q0bar = exp(meanT0DT - meanatb);                             // :112
     double D = -meanSZM * log(mean_q / q0bar);                                // :113
     double guess = mean_q, ndiff = DCP_F32_1EM4, qb_diff = 1.0, qb_diff_prev;
     int sol_flag = 1;
 
     // calculate_qbmax (:324-345): sd = 0, qbf = q0
-    double qb_tmp = 0.0;
-    for (int ia = 0; ia < nac; ++ia) {
+    double part = 0.0;
+    for (int ia = lane; ia < nac; ia += 32) {
         const HruStatic h = C.hru[ia];
         const double base = C.dt * W.q0[ia * (size_t)B + m] * h.w_riv;
-        for (int e = h.riv_beg; e < h.riv_end; ++e) qb_tmp = qb_tmp + (base * C.riv[e].share * h.ac);
+        for (int e = h.riv_beg; e < h.riv_end; ++e) part = part + (base * C.riv[e].share * h.ac);
     }
+    double qb_tmp = warp_sum(part);
     bool use_max = true;          // state currently defined by calculate_qbmax
     double D_last = 0.0;
     if (qb_tmp <= mean_q) { qb_diff = 0.0; sol_flag = 2; }                    // :126-131
     int iter = 0;
+    // every lane carries identical copies of the scalars (warp_sum returns the same bits to all lanes)
     while (fabs(qb_diff) > DCP_F32_1EM2) {                                    // :134
         if (++iter > DCP_INIT_MAX_ITER) { status |= DCP_ST_INIT_ITERCAP; break; }
-        qb_tmp = calc_qb<false>(C, W, m, D, meanatb, meanT0DT);
+        qb_tmp = calc_qb<false>(C, W, m, lane, D, meanatb, meanT0DT);
         use_max = false; D_last = D;
         qb_diff_prev = qb_diff;
         qb_diff = (qb_tmp - mean_q) * 1000.0;                                 // :140
@@ -187,28 +216,25 @@ k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7
             } else {
                 sol_flag = 0;
                 if (fabs(qb_diff) < fabs(qb_diff_prev)) break;
-                qb_tmp = calc_qb<false>(C, W, m, D, meanatb, meanT0DT);
+                qb_tmp = calc_qb<false>(C, W, m, lane, D, meanatb, meanT0DT);
                 D_last = D;
                 break;
             }
         }
     }
     status |= (sol_flag & DCP_ST_SOLFLAG_MASK);
-    W.diag[0 * (size_t)B + m] = mean_q;
-    W.diag[1 * (size_t)B + m] = qb_tmp;
-    W.diag[2 * (size_t)B + m] = guess;
 
     // final state = that of the last calculate_qb / calculate_qbmax call
     if (use_max) {
-        for (int ia = 0; ia < nac; ++ia) {
+        for (int ia = lane; ia < nac; ia += 32) {
             W.sd[ia * (size_t)B + m] = 0.0;
             W.qbf0[ia * (size_t)B + m] = W.q0[ia * (size_t)B + m];
         }
     } else {
-        (void)calc_qb<true>(C, W, m, D_last, meanatb, meanT0DT);
+        (void)calc_qb<true>(C, W, m, lane, D_last, meanatb, meanT0DT);
     }
     // srinit clip (:203-206): only layers some HRU references are touched
-    for (int i = 0; i < npt; ++i) {
+    for (int i = lane; i < npt; i += 32) {
         if (!C.layer_used[i]) continue;
         const double srmax = W.par[(2 * npt + i) * (size_t)B + m];
         if (W.par[(3 * npt + i) * (size_t)B + m] > srmax) {
@@ -216,7 +242,8 @@ k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7
             mp[3 * npt + i] = srmax;
         }
     }
-    for (int ia = 0; ia < nac; ++ia) {                                        // :194-213
+    __syncwarp();
+    for (int ia = lane; ia < nac; ia += 32) {                                 // :194-213
         const HruStatic h = C.hru[ia];
         const size_t o = ia * (size_t)B + m;
         const double qbf = W.qbf0[o];
@@ -231,13 +258,18 @@ k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7
         }
     }
     if (CHECK)
-        for (int r = 0; r < 3 * C.nriv; ++r) W.riv_sums[r * (size_t)B + m] = 0.0;
-    for (int r = 0; r < C.nriv; ++r) {
+        for (int r = lane; r < 3 * C.nriv; r += 32) W.riv_sums[r * (size_t)B + m] = 0.0;
+    for (int r = lane; r < C.nriv; r += 32) {
         W.sse[r * (size_t)B + m] = 0.0;
         W.lsse[r * (size_t)B + m] = 0.0;
         W.bad[r * (size_t)B + m] = 0;
     }
-    W.status[m] = status;
+    if (lane == 0) {
+        W.diag[0 * (size_t)B + m] = mean_q;
+        W.diag[1 * (size_t)B + m] = qb_tmp;
+        W.diag[2 * (size_t)B + m] = guess;
+        W.status[m] = status;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -594,7 +626,7 @@ void dcp_launch_min_chv(const double *mcpar, int npt, int64_t n_member, double *
 }
 
 void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bool check, cudaStream_t s) {
-    const int grid = cdiv(W.B, 128);
+    const int grid = cdiv(W.B, 4);                       // one warp per member, 4 members per block
     if (check) k_init_members<true><<<grid, 128, 0, s>>>(C, W, mcpar);
     else k_init_members<false><<<grid, 128, 0, s>>>(C, W, mcpar);
 }
