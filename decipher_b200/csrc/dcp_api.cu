@@ -326,6 +326,7 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
             P.nq = (int)rivq.size();
             const int n_chains = 2 * P.Mc * nriv;
             P.n_threads = CT + 128;
+            P.variant = getenv("DCP_RES_VARIANT") ? atoi(getenv("DCP_RES_VARIANT")) : 0;   // 0 = chosen per arithmetic policy
             P.river_team = 1;
             while (P.river_team < 16 && 2 * P.river_team * n_chains <= 128) P.river_team <<= 1;
             size_t off = 0;

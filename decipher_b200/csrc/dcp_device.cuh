@@ -122,6 +122,7 @@ struct ResPlan {
     int32_t Mc;                     // members per CTA = G * S
     int32_t n_groups;               // ceil(B / Mc), set per launch
     int32_t n_threads;              // 512 compute threads + 128 river threads
+    int32_t variant;                // 1: one HRU column per compute thread (16 warps), 2: two columns (8 warps, 232 registers)
     int32_t river_team;             // lanes per summation chain in FAST mode (power of two <= 16)
     int32_t Tt;                     // forcing tile (timesteps) per TMA bulk copy
     int32_t nnz;                    // W entries

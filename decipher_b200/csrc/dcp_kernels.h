@@ -5,6 +5,7 @@
 #define DCP_STREAM_THREADS 128
 #define DCP_RES_S 4                  // member slots per compute thread of the resident kernel
 #define DCP_RES_LG 2                 // member slots interleaved per basic block in the lean step
+#define DCP_RES_LG2 2                // same for the two-columns-per-thread variant
 #define DCP_RES_COMPUTE 512
 #define DCP_RES_MAXPAIRS 256         // (members per CTA) x nriv the river warps can carry (4 warps x 4 passes x 16 pairs)
 #define DCP_RES_TT 64                // forcing tile length (timesteps)

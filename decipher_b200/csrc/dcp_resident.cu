@@ -28,10 +28,8 @@
 
 #include <cstdint>
 
-#define RES_CT DCP_RES_COMPUTE        // compute threads (4 warpgroups)
-#define RES_THREADS (RES_CT + 128)    // + one warpgroup of river warps: 5 warps per SM sub-partition
-#define RES_REGS_COMPUTE 112          // after setmaxnreg: launch allocation is 96/thread; the river warpgroup gives up (96-32)x128 registers, the compute warpgroups take exactly those: (112-96)x512
-#define RES_REGS_RIVER 32
+#define RES_COLS DCP_RES_COMPUTE      // unit columns per member slot (= HRU positions across the CTA)
+#define RES_RIVER 128                 // one warpgroup of river warps
 #define RES_MAXPASS 4                 // chains per river lane
 #define RES_PARW 6                    // srmax, td, smax, szm, 1/srmax, 1/szm
 
@@ -74,7 +72,8 @@ struct ResSmem {
 };
 
 // CTA-wide barrier used inside the role-specialised code (both roles execute the same sequence)
-__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(RES_THREADS) : "memory"); }
+template <int THREADS>
+__device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n"(THREADS) : "memory"); }
 
 #define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})     /* straight from the constant bank, no registers */
 
@@ -84,27 +83,37 @@ __device__ __forceinline__ void cta_sync() { asm volatile("bar.sync 1, %0;" ::"n
 // MODE 1: FAST arithmetic, generic branchy step (any ims flags / ntt)
 // MODE 2: FAST arithmetic, LEAN branch-free step (dcp_physics.cuh: hru_step_lean)
 // ---------------------------------------------------------------------------------------------
-template <int S, int MODE, bool AET>
+template <int S, int H, int LG, int MODE, bool AET>
 __device__ __forceinline__ void res_compute_role(const DevCatchment &C, const DevBatch &W, const ResPlan &P,
                                                  const ResSmem &M) {
     constexpr bool FAST = MODE != 0;
     constexpr bool LEAN = MODE == 2;
+    constexpr int CT = RES_COLS / H;                        // compute threads; each owns H HRU columns x S member slots
+    constexpr int THREADS = CT + RES_RIVER;
     const int tid = threadIdx.x;
     const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, npt = C.npt;
     const int qbf_stride = P.G * nac_pad * S;              // doubles per qbf time buffer
     const int forc_stride = P.Tt * (C.ngp + C.nge);
 
-    // per-thread static HRU record (registers for the whole launch)
-    const int pos = tid % nac_pad;                          // position inside the member sub-group
-    const int g = tid / nac_pad;
-    const int ia = P.thread_hru[pos];                       // positions are sorted by W row length
-    HruStatic h;
-    if (ia >= 0) h = C.hru[ia];
-    else { h = HruStatic{}; h.ac = 1.0; h.cosm = 1.0; }
-    const double inv_ac = 1.0 / h.ac;
-    const int my_tuple = (g * nac_pad + pos) * S;           // offset of this thread's qbf tuple
-    const int g_tuple = g * nac_pad * S;
-    const double *my_par = M.par_s + ((size_t)g * S * npt + h.ipar) * RES_PARW;
+    // per-thread static HRU records (registers for the whole launch)
+    int ia[H], gq[H], ippt[H], ipet[H], row_beg[H], row_end[H], my_tuple[H], g_tuple[H];
+    double ac[H], inv_ac[H];
+    const double *my_par[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+        const int col = tid + CT * j;                       // unit column 0..511
+        const int pos = col % nac_pad;                      // position inside the member sub-group
+        gq[j] = col / nac_pad;
+        ia[j] = P.thread_hru[pos];                          // positions are sorted by W row length
+        HruStatic h;
+        if (ia[j] >= 0) h = C.hru[ia[j]];
+        else { h = HruStatic{}; h.ac = 1.0; h.cosm = 1.0; }
+        ac[j] = h.ac; inv_ac[j] = 1.0 / h.ac;
+        ippt[j] = h.ippt; ipet[j] = h.ipet; row_beg[j] = h.row_beg; row_end[j] = h.row_end;
+        my_tuple[j] = (gq[j] * nac_pad + pos) * S;          // offset of this column's qbf tuple
+        g_tuple[j] = gq[j] * nac_pad * S;
+        my_par[j] = M.par_s + ((size_t)gq[j] * S * npt + h.ipar) * RES_PARW;
+    }
     const int par_kstride = npt * RES_PARW;
     const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
     uint32_t tiles_done = 0;                                // forcing tiles consumed so far (mbarrier phase tracking)
@@ -112,37 +121,46 @@ __device__ __forceinline__ void res_compute_role(const DevCatchment &C, const De
 
     for (int gi = blockIdx.x; gi < P.n_groups; gi += gridDim.x) {
         const int m_base = gi * Mc;
-        cta_sync();                                         // previous group fully done with shared memory
+        cta_sync<THREADS>();                                // previous group fully done with shared memory
 
         // ---- load the group's initial state (written by k_init_members) ----
-        double sd[S], suz[S], srz[S], qint1[S], aet[S];
+        double sd[H][S], suz[H][S], srz[H][S], qint1[H][S], aet[H][S];
+        // the fat-thread variant (H == 2, 232 registers) also keeps the per-unit constants in registers
+        constexpr bool CREG = false;   // tried: per-unit constants in registers for H == 2 -> 24 % slower (spills), kept in shared memory
+        double rq0[H][S], rq1[H][S], rq2[H][S], rm2[H][S], rim2[H][S];
 #pragma unroll
-        for (int k = 0; k < S; ++k) {
-            const int m = m_base + g * S + k;
-            sd[k] = 1.0; suz[k] = 0.0; srz[k] = 0.0; qint1[k] = 0.0; aet[k] = 0.0;
-            double qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_m2 = 1.0, c_q1 = 1.0, c_im2 = 1.0;
-            if (ia >= 0 && m < B) {
-                const size_t o = (size_t)ia * B + m;
-                sd[k] = W.sd[o]; suz[k] = W.suz[o]; srz[k] = W.srz[o]; qint1[k] = W.qint1[o];
-                c_q0 = W.q0[o]; c_q2 = W.q2[o];
-                const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
-                c_m2 = szm / h.cosm;                        // dyna_satzone_analyticalsolver.f90:52
-                c_q1 = c_q0 * h.cosm;                       // :49
-                c_im2 = h.cosm / szm;
-                qb0 = W.qbf0[o];
+        for (int j = 0; j < H; ++j) {
+            const int col = tid + CT * j;
+            const HruStatic h = ia[j] >= 0 ? C.hru[ia[j]] : HruStatic{};
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const int m = m_base + gq[j] * S + k;
+                sd[j][k] = 1.0; suz[j][k] = 0.0; srz[j][k] = 0.0; qint1[j][k] = 0.0; aet[j][k] = 0.0;
+                double qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_m2 = 1.0, c_q1 = 1.0, c_im2 = 1.0;
+                if (ia[j] >= 0 && m < B) {
+                    const size_t o = (size_t)ia[j] * B + m;
+                    sd[j][k] = W.sd[o]; suz[j][k] = W.suz[o]; srz[j][k] = W.srz[o]; qint1[j][k] = W.qint1[o];
+                    c_q0 = W.q0[o]; c_q2 = W.q2[o];
+                    const double szm = W.par[(0 * npt + h.ipar) * (size_t)B + m];
+                    c_m2 = szm / h.cosm;                    // dyna_satzone_analyticalsolver.f90:52
+                    c_q1 = c_q0 * h.cosm;                   // :49
+                    c_im2 = h.cosm / szm;
+                    qb0 = W.qbf0[o];
+                }
+                M.qbf_s[my_tuple[j] + k] = qb0;             // time buffer 0 = step 0's "old" qbf
+                M.qbf_s[qbf_stride + my_tuple[j] + k] = 0.0;
+                M.cst_s[(0 * S + k) * RES_COLS + col] = c_q0;
+                M.cst_s[(1 * S + k) * RES_COLS + col] = c_q2;
+                M.cst_s[(2 * S + k) * RES_COLS + col] = c_m2;
+                M.cst_s[(3 * S + k) * RES_COLS + col] = c_q1;
+                M.cst_s[(4 * S + k) * RES_COLS + col] = c_im2;
+                rq0[j][k] = c_q0; rq1[j][k] = c_q1; rq2[j][k] = c_q2; rm2[j][k] = c_m2; rim2[j][k] = c_im2;
+                M.ex_s[(0 * S + k) * RES_COLS + col] = 0.0;
+                M.ex_s[(1 * S + k) * RES_COLS + col] = 0.0;
             }
-            M.qbf_s[my_tuple + k] = qb0;                    // time buffer 0 = step 0's "old" qbf
-            M.qbf_s[qbf_stride + my_tuple + k] = 0.0;
-            M.cst_s[(0 * S + k) * RES_CT + tid] = c_q0;
-            M.cst_s[(1 * S + k) * RES_CT + tid] = c_q2;
-            M.cst_s[(2 * S + k) * RES_CT + tid] = c_m2;
-            M.cst_s[(3 * S + k) * RES_CT + tid] = c_q1;
-            M.cst_s[(4 * S + k) * RES_CT + tid] = c_im2;
-            M.ex_s[(0 * S + k) * RES_CT + tid] = 0.0;
-            M.ex_s[(1 * S + k) * RES_CT + tid] = 0.0;
         }
         // member parameters -> shared (one thread per (member, layer))
-        for (int i = tid; i < Mc * npt; i += RES_CT) {
+        for (int i = tid; i < Mc * npt; i += CT) {
             const int jm = i / npt, l = i % npt;
             const int m = m_base + jm;
             double *pp = M.par_s + (size_t)i * RES_PARW;
@@ -159,27 +177,26 @@ __device__ __forceinline__ void res_compute_role(const DevCatchment &C, const De
                 pp[0] = pp[1] = pp[2] = pp[3] = pp[4] = pp[5] = 1.0;
             }
         }
-        cta_sync();
+        cta_sync<THREADS>();
 
         int t = 0;
         for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
             const uint32_t b = tiles_done & 1;
             mbar_wait(&M.bars[b], (tiles_done >> 1) & 1);   // forcing tile landed (TMA, issued by the river role)
-            const double *rain_t = M.forc_s + b * forc_stride + h.ippt;
-            const double *pet_t = M.forc_s + b * forc_stride + P.Tt * C.ngp + h.ipet;
+            const double *forc_t = M.forc_s + b * forc_stride;
             const int t_end = min(C.nstep, t + P.Tt);
-            for (; t < t_end; ++t, rain_t += C.ngp, pet_t += C.nge) {
+            for (int tt = 0; t < t_end; ++t, ++tt) {
                 const long long c0 = P.dbg ? clock64() : 0;
-                if (ia >= 0) {
-                    const double *qbf_cur = M.qbf_s + (t & 1) * qbf_stride;
-                    double *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * qbf_stride;
-                    const double p = *rain_t, ep = *pet_t;
-                    // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52) ----
-                    double qin[S];
+                const double *qbf_cur = M.qbf_s + (t & 1) * qbf_stride;
+                double *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * qbf_stride;
+                // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52) for the thread's H rows ----
+                double qin[H][S];
 #pragma unroll
-                    for (int k = 0; k < S; ++k) qin[k] = 0.0;
-                    const double *qg = qbf_cur + g_tuple;
-                    for (int e = h.row_beg; e < h.row_end; ++e) {
+                for (int j = 0; j < H; ++j) {
+#pragma unroll
+                    for (int k = 0; k < S; ++k) qin[j][k] = 0.0;
+                    const double *qg = qbf_cur + g_tuple[j];
+                    for (int e = row_beg[j]; e < row_end[j]; ++e) {
                         const int sp = M.src_s[e];
                         const double w = M.w_s[e];
                         const double2 *qv = reinterpret_cast<const double2 *>(qg + sp * S);
@@ -188,93 +205,113 @@ __device__ __forceinline__ void res_compute_role(const DevCatchment &C, const De
                         for (int k2 = 0; k2 < S / 2; ++k2) { const double2 v = qv[k2]; qs[2 * k2] = v.x; qs[2 * k2 + 1] = v.y; }
                         if (FAST) {
 #pragma unroll
-                            for (int k = 0; k < S; ++k) qin[k] = fma(qs[k], w, qin[k]);
+                            for (int k = 0; k < S; ++k) qin[j][k] = fma(qs[k], w, qin[j][k]);
                         } else {
                             const double acs = M.ac_s[sp];
 #pragma unroll
-                            for (int k = 0; k < S; ++k) qin[k] = qin[k] + qs[k] * w * acs;
+                            for (int k = 0; k < S; ++k) qin[j][k] = qin[j][k] + qs[k] * w * acs;
                         }
                     }
-                    // ---- root zone, unsaturated zone, saturated zone per member slot ----
-                    double *qo = qbf_nxt + my_tuple;
-                    double *exo = M.ex_s + (t & 1) * (S * RES_CT) + tid;
-                    const double *cst = M.cst_s + tid;
-                    if (LEAN) {
-                        const double epp = fm_max(ep, 0.0);
-                        // DCP_RES_LG member slots per basic block: their dependency chains interleave (ILP)
+                }
+                // ---- root zone, unsaturated zone, saturated zone per (HRU, member slot) ----
+                if (LEAN) {
+                    // LG units per basic block: their dependency chains interleave (ILP)
 #pragma unroll
-                        for (int k0 = 0; k0 < S; k0 += DCP_RES_LG) {
-                            LeanOut lo[DCP_RES_LG];
-                            bool any_slow = false;
+                    for (int u0 = 0; u0 < H * S; u0 += LG) {
+                        LeanOut lo[LG];
+                        bool any_slow = false;
 #pragma unroll
-                            for (int j = 0; j < DCP_RES_LG; ++j) {
-                                const int k = k0 + j;
-                                const double *pp = my_par + k * par_kstride;
-                                HruConst c;
-                                c.ac = h.ac; c.inv_ac = inv_ac;
-                                c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
-                                c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
-                                c.inv_m2 = cst[(4 * S + k) * RES_CT];
-                                c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
-                                c.ims_rz = 1; c.ims_uz = 1;
-                                HruState st;
-                                st.sd = sd[k]; st.suz = suz[k]; st.srz = srz[k]; st.qint1 = 0.0;
-                                hru_step_lean(c, gc, p, epp, qin[k], st, lo[j]);
-                                sd[k] = st.sd; suz[k] = st.suz; srz[k] = st.srz;      // qint1 is not carried: ntt == 1 => qin2 == qin/ac
-                                any_slow |= lo[j].slow;
+                        for (int v = 0; v < LG; ++v) {
+                            const int j = (u0 + v) / S, k = (u0 + v) % S;
+                            const int col = tid + CT * j;
+                            const double *pp = my_par[j] + k * par_kstride;
+                            const double *cst = M.cst_s + col;
+                            HruConst c;
+                            c.ac = ac[j]; c.inv_ac = inv_ac[j];
+                            if (CREG) {
+                                c.q0 = rq0[j][k]; c.q2 = rq2[j][k]; c.m2 = rm2[j][k]; c.q1 = rq1[j][k]; c.inv_m2 = rim2[j][k];
+                            } else {
+                                c.q0 = cst[(0 * S + k) * RES_COLS]; c.q2 = cst[(1 * S + k) * RES_COLS];
+                                c.m2 = cst[(2 * S + k) * RES_COLS]; c.q1 = cst[(3 * S + k) * RES_COLS];
+                                c.inv_m2 = cst[(4 * S + k) * RES_COLS];
                             }
-                            if (any_slow) {                                            // rare: constants are re-read, not kept live
-#pragma unroll
-                                for (int j = 0; j < DCP_RES_LG; ++j)
-                                    if (lo[j].slow) {
-                                        const int k = k0 + j;
-                                        HruConst c;
-                                        c.ac = h.ac; c.inv_ac = inv_ac;
-                                        c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
-                                        c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
-                                        c.inv_m2 = cst[(4 * S + k) * RES_CT];
-                                        c.smax = (my_par + k * par_kstride)[2];
-                                        hru_step_lean_fixup(c, gc, qin[k], qin[k], sd[k], lo[j]);
-                                    }
-                            }
-#pragma unroll
-                            for (int j = 0; j < DCP_RES_LG; ++j) {
-                                qo[k0 + j] = lo[j].qbf;
-                                exo[(k0 + j) * RES_CT] = lo[j].exac;
-                                if (AET) aet[k0 + j] = aet[k0 + j] + lo[j].ea;
-                            }
+                            c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
+                            c.ims_rz = 1; c.ims_uz = 1;
+                            const double p = forc_t[tt * C.ngp + ippt[j]];
+                            const double epp = fm_max(forc_t[P.Tt * C.ngp + tt * C.nge + ipet[j]], 0.0);
+                            HruState st;
+                            st.sd = sd[j][k]; st.suz = suz[j][k]; st.srz = srz[j][k]; st.qint1 = 0.0;
+                            hru_step_lean(c, gc, p, epp, qin[j][k], st, lo[v]);
+                            sd[j][k] = st.sd; suz[j][k] = st.suz; srz[j][k] = st.srz;     // qint1 is not carried: ntt == 1 => qin2 == qin/ac
+                            any_slow |= lo[v].slow;
                         }
-                    } else {
+                        if (any_slow) {                                                    // rare: constants are re-read, not kept live
+#pragma unroll
+                            for (int v = 0; v < LG; ++v)
+                                if (lo[v].slow) {
+                                    const int j = (u0 + v) / S, k = (u0 + v) % S;
+                                    const double *cst = M.cst_s + tid + CT * j;
+                                    HruConst c;
+                                    c.ac = ac[j]; c.inv_ac = inv_ac[j];
+                                    c.q0 = cst[(0 * S + k) * RES_COLS]; c.q2 = cst[(1 * S + k) * RES_COLS];
+                                    c.m2 = cst[(2 * S + k) * RES_COLS]; c.q1 = cst[(3 * S + k) * RES_COLS];
+                                    c.inv_m2 = cst[(4 * S + k) * RES_COLS];
+                                    c.smax = (my_par[j] + k * par_kstride)[2];
+                                    hru_step_lean_fixup(c, gc, qin[j][k], qin[j][k], sd[j][k], lo[v]);
+                                }
+                        }
+#pragma unroll
+                        for (int v = 0; v < LG; ++v) {
+                            const int j = (u0 + v) / S, k = (u0 + v) % S;
+                            if (ia[j] >= 0) {
+                                qbf_nxt[my_tuple[j] + k] = lo[v].qbf;
+                                M.ex_s[((t & 1) * S + k) * RES_COLS + tid + CT * j] = lo[v].exac;
+                            }
+                            if (AET) aet[j][k] = aet[j][k] + lo[v].ea;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < H; ++j) {
+                        if (ia[j] < 0) continue;
+                        const int col = tid + CT * j;
+                        const HruStatic &hh = C.hru[ia[j]];
+                        const int ims_rz = hh.ims_rz, ims_uz = hh.ims_uz;
+                        const double p = forc_t[tt * C.ngp + ippt[j]];
+                        const double ep = forc_t[P.Tt * C.ngp + tt * C.nge + ipet[j]];
+                        const double *cst = M.cst_s + col;
 #pragma unroll
                         for (int k = 0; k < S; ++k) {
-                            const double *pp = my_par + k * par_kstride;
+                            const double *pp = my_par[j] + k * par_kstride;
                             HruConst c;
-                            c.ac = h.ac; c.inv_ac = inv_ac;
-                            c.q0 = cst[(0 * S + k) * RES_CT]; c.q2 = cst[(1 * S + k) * RES_CT];
-                            c.m2 = cst[(2 * S + k) * RES_CT]; c.q1 = cst[(3 * S + k) * RES_CT];
-                            c.inv_m2 = cst[(4 * S + k) * RES_CT];
+                            c.ac = ac[j]; c.inv_ac = inv_ac[j];
+                            c.q0 = cst[(0 * S + k) * RES_COLS]; c.q2 = cst[(1 * S + k) * RES_COLS];
+                            c.m2 = cst[(2 * S + k) * RES_COLS]; c.q1 = cst[(3 * S + k) * RES_COLS];
+                            c.inv_m2 = cst[(4 * S + k) * RES_COLS];
                             c.srmax = pp[0]; c.td = pp[1]; c.smax = pp[2]; c.inv_srmax = pp[4];
-                            c.ims_rz = h.ims_rz; c.ims_uz = h.ims_uz;
+                            c.ims_rz = ims_rz; c.ims_uz = ims_uz;
                             HruState s;
-                            s.sd = sd[k]; s.suz = suz[k]; s.srz = srz[k]; s.qint1 = qint1[k];
+                            s.sd = sd[j][k]; s.suz = suz[j][k]; s.srz = srz[j][k]; s.qint1 = qint1[j][k];
                             HruFlux f;
-                            hru_step<FAST, false>(c, gc, p, ep, qin[k], s, f);
-                            sd[k] = s.sd; suz[k] = s.suz; srz[k] = s.srz; qint1[k] = s.qint1;
-                            qo[k] = f.qbf;
-                            exo[k * RES_CT] = (f.ex > 0.0) ? f.ex * h.ac : 0.0;   // dyna_results_ac.f90:35-38
-                            if (AET) { if (h.ims_rz == 1 && ep > 0.0) aet[k] = aet[k] + f.ea; }
+                            hru_step<FAST, false>(c, gc, p, ep, qin[j][k], s, f);
+                            sd[j][k] = s.sd; suz[j][k] = s.suz; srz[j][k] = s.srz; qint1[j][k] = s.qint1;
+                            qbf_nxt[my_tuple[j] + k] = f.qbf;
+                            M.ex_s[((t & 1) * S + k) * RES_COLS + col] = (f.ex > 0.0) ? f.ex * ac[j] : 0.0;   // dyna_results_ac.f90:35-38
+                            if (AET) { if (ims_rz == 1 && ep > 0.0) aet[j][k] = aet[j][k] + f.ea; }
                         }
                     }
                 }
                 if (P.dbg) busy += clock64() - c0;
-                cta_sync();
+                cta_sync<THREADS>();
             }
         }
         if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 20 + (tid >> 5)] = busy;
         if (AET) {
 #pragma unroll
-            for (int k = 0; k < S; ++k)
-                if (ia >= 0 && m_base + g * S + k < B) W.aet[(size_t)ia * B + (m_base + g * S + k)] = aet[k];
+            for (int j = 0; j < H; ++j)
+#pragma unroll
+                for (int k = 0; k < S; ++k)
+                    if (ia[j] >= 0 && m_base + gq[j] * S + k < B) W.aet[(size_t)ia[j] * B + (m_base + gq[j] * S + k)] = aet[j][k];
         }
     }
 }
@@ -282,9 +319,11 @@ __device__ __forceinline__ void res_compute_role(const DevCatchment &C, const De
 // ---------------------------------------------------------------------------------------------
 // river role: 4 warps.  Lane = summation chain; thread RES_CT also drives the forcing TMA.
 // ---------------------------------------------------------------------------------------------
-template <int S, bool FAST>
+template <int S, int H, bool FAST>
 __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevBatch &W, const ResPlan &P,
                                                const ResSmem &M) {
+    constexpr int CT = RES_COLS / H;
+    constexpr int THREADS = CT + RES_RIVER;
     const int tid = threadIdx.x;
     const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, nriv = C.nriv;
     const int qbf_stride = P.G * nac_pad * S;
@@ -293,8 +332,8 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
     const uint32_t rain_bytes = (uint32_t)(P.Tt * C.ngp * sizeof(double));
     const uint32_t pet_bytes = (uint32_t)(P.Tt * C.nge * sizeof(double));
     uint32_t tiles_done = 0;
-    const int rlane = tid - RES_CT;
-    constexpr int n_rlanes = RES_THREADS - RES_CT;
+    const int rlane = tid - CT;
+    constexpr int n_rlanes = RES_RIVER;
     const int n_chains = 2 * Mc * nriv;                     // chain id = (pair << 1) | type, pair = member * nriv + river
     // EXACT: one lane per chain, terms added in ascending HRU order (the reference's order).
     // FAST : a team of T lanes per chain (strided partial sums + shuffle tree) -- order is free there.
@@ -305,15 +344,15 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
 
     for (int gi = blockIdx.x; gi < P.n_groups; gi += gridDim.x) {
         const int m_base = gi * Mc;
-        cta_sync();
-        if (tid == RES_CT) {                                // forcing tile 0 of this group
+        cta_sync<THREADS>();
+        if (tid == CT) {                                // forcing tile 0 of this group
             const uint32_t b = tiles_done & 1;
             fence_proxy_async();
             mbar_expect_tx(&M.bars[b], rain_bytes + pet_bytes);
             tma_load_1d(M.forc_s + b * forc_stride, C.rain, rain_bytes, &M.bars[b]);
             tma_load_1d(M.forc_s + b * forc_stride + P.Tt * C.ngp, C.pet, pet_bytes, &M.bars[b]);
         }
-        cta_sync();
+        cta_sync<THREADS>();
 
         double qb_prev[RES_MAXPASS];
 #pragma unroll
@@ -321,7 +360,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
 
         int t = 0;
         for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
-            if (tid == RES_CT && tile + 1 < ntiles) {
+            if (tid == CT && tile + 1 < ntiles) {
                 // prefetch the next tile into the other buffer (everyone left it at the last barrier)
                 const uint32_t nb = (tiles_done & 1) ^ 1;
                 const size_t t_next = (size_t)(tile + 1) * P.Tt;
@@ -338,7 +377,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
                 const bool drain = (t == C.nstep);
                 const long long c0 = P.dbg ? clock64() : 0;
                 const double *qbf_cur = M.qbf_s + (t & 1) * qbf_stride;
-                const double *ex_prev = M.ex_s + ((t & 1) ^ 1) * (S * RES_CT);
+                const double *ex_prev = M.ex_s + ((t & 1) ^ 1) * (S * RES_COLS);
 #pragma unroll
                 for (int q = 0; q < RES_MAXPASS; ++q) {
                     if (q * chains_per_pass < n_chains) {                 // uniform over the river warps
@@ -355,7 +394,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
                             if (drain) end = beg;
                         } else {
                             lst = M.ro_s; beg = P.rivo_beg[r]; end = P.rivo_beg[r + 1];
-                            val = ex_prev + kk * RES_CT + gg * nac_pad; vstride = 1; cstride = 0; f0 = 1.0;
+                            val = ex_prev + kk * RES_COLS + gg * nac_pad; vstride = 1; cstride = 0; f0 = 1.0;
                         }
                         if (!live) end = beg;
                         const double *cf = M.rqc_s + (cstride ? 0 : P.nq);
@@ -393,7 +432,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
                 }
                 if (P.dbg) busy += clock64() - c0;
                 if (drain) { ++t; break; }
-                cta_sync();
+                cta_sync<THREADS>();
             }
         }
         if (P.dbg && (tid & 31) == 0) P.dbg[blockIdx.x * 20 + (tid >> 5)] = busy;
@@ -401,15 +440,24 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int S, int MODE, bool AET>
-__global__ void __launch_bounds__(RES_THREADS, 1)
+// H = HRU columns per compute thread.  H = 1: 16 compute warps x 112 registers.  H = 2: 8 compute warps
+// x 232 registers, 8 (HRU, member) units per thread of which LG run interleaved in one basic block —
+// fewer, fatter threads trade thread-level for instruction-level parallelism on the FP64 pipe.
+template <int H> struct ResRegs;
+template <> struct ResRegs<1> { static constexpr int compute = 112, river = 32; };   // launch cap 96: (96-32)*128 == (112-96)*512
+template <> struct ResRegs<2> { static constexpr int compute = 232, river = 40; };   // launch cap 168: (168-40)*128 == (232-168)*256
+
+template <int S, int H, int LG, int MODE, bool AET>
+__global__ void __launch_bounds__(RES_COLS / H + RES_RIVER, 1)
 k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
     constexpr bool FAST = MODE != 0;
+    constexpr int CT = RES_COLS / H;
+    constexpr int THREADS = CT + RES_RIVER;
     extern __shared__ __align__(128) unsigned char smem[];
     ResSmem M;
     M.qbf_s = (double *)(smem + P.off_qbf);          // [2][G*nac_pad][S]   qbf tuples, time double buffer
-    M.ex_s = (double *)(smem + P.off_ex);            // [2][S][CT]          ex*ac terms
-    M.cst_s = (double *)(smem + P.off_cst);          // [5][S][CT]          q0, q2, m2, q1, 1/m2
+    M.ex_s = (double *)(smem + P.off_ex);            // [2][S][512]         ex*ac terms
+    M.cst_s = (double *)(smem + P.off_cst);          // [5][S][512]         q0, q2, m2, q1, 1/m2
     M.par_s = (double *)(smem + P.off_par);          // [Mc][npt][RES_PARW]
     M.w_s = (double *)(smem + P.off_w);              // [nnz]    w (EXACT) or w*ac_src (FAST)
     M.src_s = (uint16_t *)(smem + P.off_src);        // [nnz]    thread position of the source HRU
@@ -422,16 +470,16 @@ k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
 
     const int tid = threadIdx.x;
     // ---- one-time CTA setup ----
-    for (int e = tid; e < P.nnz; e += RES_THREADS) {
+    for (int e = tid; e < P.nnz; e += THREADS) {
         const WEntry we = C.w[e];
         M.w_s[e] = FAST ? we.w * we.ac_src : we.w;
         M.src_s[e] = (uint16_t)P.hru_pos[we.src];
     }
-    for (int i = tid; i < P.nac_pad; i += RES_THREADS) {
+    for (int i = tid; i < P.nac_pad; i += THREADS) {
         const int hh = P.thread_hru[i];
         M.ac_s[i] = hh >= 0 ? C.hru[hh].ac : 0.0;
     }
-    for (int i = tid; i < P.nq; i += RES_THREADS) {
+    for (int i = tid; i < P.nq; i += THREADS) {
         const RivChain rc = P.rivq[i];
         M.rq_s[i] = (uint16_t)P.hru_pos[rc.ia];
         if (FAST) {
@@ -441,42 +489,45 @@ k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
         }
     }
     if (tid < 3) M.rqc_s[tid * (P.nq + 1) + P.nq] = 1.0;
-    for (int i = tid; i < C.nac; i += RES_THREADS) M.ro_s[i] = (uint16_t)P.hru_pos[P.rivo[i]];
-    if (tid == RES_CT) {
+    for (int i = tid; i < C.nac; i += THREADS) M.ro_s[i] = (uint16_t)P.hru_pos[P.rivo[i]];
+    if (tid == CT) {
         mbar_init(&M.bars[0], 1);
         mbar_init(&M.bars[1], 1);
         fence_mbar_init();
     }
     __syncthreads();
 
-    // ---- warp-role split with register reallocation (setmaxnreg): per SM sub-partition
-    //      4 compute warps x 112 + 1 river warp x 64 = 512 x 32 registers ----
-    if (tid < RES_CT) {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(RES_REGS_COMPUTE));
-        res_compute_role<S, MODE, AET>(C, W, P, M);
+    // ---- warp-role split with register reallocation (setmaxnreg) ----
+    if (tid < CT) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ResRegs<H>::compute));
+        res_compute_role<S, H, LG, MODE, AET>(C, W, P, M);
     } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(RES_REGS_RIVER));
-        res_river_role<S, FAST>(C, W, P, M);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ResRegs<H>::river));
+        res_river_role<S, H, FAST>(C, W, P, M);
     }
 }
 #undef gc
 
 // ---------------------------------------------------------------------------------------------
-template <int S>
+template <int S, int H, int LG>
 static cudaError_t launch_res(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast, bool aet,
                               int grid, cudaStream_t s) {
     void (*k)(DevCatchment, DevBatch, ResPlan);
     const int mode = !fast ? 0 : (P.lean_ok ? 2 : 1);
-    if (mode == 2) k = aet ? k_physics_resident<S, 2, true> : k_physics_resident<S, 2, false>;
-    else if (mode == 1) k = aet ? k_physics_resident<S, 1, true> : k_physics_resident<S, 1, false>;
-    else k = aet ? k_physics_resident<S, 0, true> : k_physics_resident<S, 0, false>;
+    if (mode == 2) k = aet ? k_physics_resident<S, H, LG, 2, true> : k_physics_resident<S, H, LG, 2, false>;
+    else if (mode == 1) k = aet ? k_physics_resident<S, H, 1, 1, true> : k_physics_resident<S, H, 1, 1, false>;
+    else k = aet ? k_physics_resident<S, H, 1, 0, true> : k_physics_resident<S, H, 1, 0, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
-    k<<<grid, RES_THREADS, P.smem_bytes, s>>>(C, W, P);
+    k<<<grid, RES_COLS / H + RES_RIVER, P.smem_bytes, s>>>(C, W, P);
     return cudaGetLastError();
 }
 
 cudaError_t dcp_launch_physics_resident(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast,
                                         bool aet, int grid, cudaStream_t s) {
-    return launch_res<DCP_RES_S>(C, W, P, fast, aet, grid, s);
+    // the lean (branch-free) step profits from fewer, fatter threads (8 units per thread, DCP_RES_LG2 interleaved);
+    // the branchy exact / generic-fast steps run faster with 16 compute warps
+    const int variant = P.variant ? P.variant : ((fast && P.lean_ok) ? 2 : 1);
+    if (variant == 2) return launch_res<DCP_RES_S, 2, DCP_RES_LG2>(C, W, P, fast, aet, grid, s);
+    return launch_res<DCP_RES_S, 1, DCP_RES_LG>(C, W, P, fast, aet, grid, s);
 }

@@ -134,3 +134,27 @@ def test_resident_matches_streamed_bitwise_in_exact_mode():
     assert np.array_equal(a["perf"], b["perf"], equal_nan=True)
     assert np.array_equal(a["reach_totals"], b["reach_totals"], equal_nan=True)
     assert np.array_equal(a["status"], b["status"])
+
+
+def test_wide_w_large_catchment_goes_streamed():
+    """Config-4-like: more HRUs than the resident kernel holds (nac = 700 > 512) and a wide weighting
+    matrix (64 targets per HRU): AUTO must pick the streamed kernel and stay within tolerance."""
+    cat = synth.synth_catchment(nac=700, nriv=5, npt=1, ngp=4, nge=1, nstep=500, kW=64, seed=synth.BASE_SEED + 4, tree=True)
+    ref, out = _run_both(cat, 48, kernel=0)
+    assert out["stats"]["kernel_used"] == KERNEL_STREAMED
+    print("C4-like:", _check(ref, out))
+
+
+def test_multi_catchment_partition():
+    """Config-5-like: several catchments of different size, dealt to 2 ranks (both emulated on this GPU)."""
+    from decipher_b200.ensemble import run_catchments
+    cats = [synth.synth_catchment(nac=n, nriv=2, npt=1, ngp=2, nge=1, nstep=300, kW=4, seed=100 + n) for n in (30, 120, 64, 200)]
+    mcs = [synth.sample_parameters(1, 12, seeds=(5 + i, 2000)) for i in range(4)]
+    got = {}
+    for rank in range(2):
+        got.update(run_catchments(cats, mcs, rank=rank, world=2, want_q=True))
+    assert sorted(got) == [0, 1, 2, 3]
+    for i, c in enumerate(cats):
+        ref = oracle_run(c, mcs[i].copy(order="F"))
+        compare_flows(got[i]["q"], ref["q"])
+        compare_perf(got[i]["perf"], ref["perf"])
