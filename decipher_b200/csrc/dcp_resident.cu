@@ -509,13 +509,19 @@ k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
 #undef gc
 
 // ---------------------------------------------------------------------------------------------
-template <int S, int H, int LG>
+#ifndef DCP_RES_LEAN_TU
+// ---------------------------------------------------------------------------------------------
+// This TU (built with -fmad=false) holds the EXACT and generic-FAST kernels; the LEAN kernels are
+// instantiated in dcp_resident_lean.cu, which includes this file with FMA contraction enabled — the
+// lean step has no operation-order contract, and contraction removes ~10 % of its FP64 instructions.
+cudaError_t dcp_launch_physics_resident_lean(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool aet,
+                                             int grid, cudaStream_t s);
+
+template <int S, int H>
 static cudaError_t launch_res(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast, bool aet,
                               int grid, cudaStream_t s) {
     void (*k)(DevCatchment, DevBatch, ResPlan);
-    const int mode = !fast ? 0 : (P.lean_ok ? 2 : 1);
-    if (mode == 2) k = aet ? k_physics_resident<S, H, LG, 2, true> : k_physics_resident<S, H, LG, 2, false>;
-    else if (mode == 1) k = aet ? k_physics_resident<S, H, 1, 1, true> : k_physics_resident<S, H, 1, 1, false>;
+    if (fast) k = aet ? k_physics_resident<S, H, 1, 1, true> : k_physics_resident<S, H, 1, 1, false>;
     else k = aet ? k_physics_resident<S, H, 1, 0, true> : k_physics_resident<S, H, 1, 0, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
@@ -525,9 +531,27 @@ static cudaError_t launch_res(const DevCatchment &C, const DevBatch &W, const Re
 
 cudaError_t dcp_launch_physics_resident(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast,
                                         bool aet, int grid, cudaStream_t s) {
-    // the lean (branch-free) step profits from fewer, fatter threads (8 units per thread, DCP_RES_LG2 interleaved);
-    // the branchy exact / generic-fast steps run faster with 16 compute warps
-    const int variant = P.variant ? P.variant : ((fast && P.lean_ok) ? 2 : 1);
-    if (variant == 2) return launch_res<DCP_RES_S, 2, DCP_RES_LG2>(C, W, P, fast, aet, grid, s);
-    return launch_res<DCP_RES_S, 1, DCP_RES_LG>(C, W, P, fast, aet, grid, s);
+    if (fast && P.lean_ok) return dcp_launch_physics_resident_lean(C, W, P, aet, grid, s);
+    // the branchy exact / generic-fast steps run fastest with 16 compute warps
+    return launch_res<DCP_RES_S, 1>(C, W, P, fast, aet, grid, s);
 }
+#else
+// ---------------------------------------------------------------------------------------------
+// LEAN kernels (this translation unit is built with FMA contraction on)
+template <int S, int H, int LG>
+static cudaError_t launch_lean(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool aet, int grid, cudaStream_t s) {
+    void (*k)(DevCatchment, DevBatch, ResPlan) = aet ? k_physics_resident<S, H, LG, 2, true> : k_physics_resident<S, H, LG, 2, false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
+    if (e != cudaSuccess) return e;
+    k<<<grid, RES_COLS / H + RES_RIVER, P.smem_bytes, s>>>(C, W, P);
+    return cudaGetLastError();
+}
+
+cudaError_t dcp_launch_physics_resident_lean(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool aet,
+                                             int grid, cudaStream_t s) {
+    // the branch-free step profits from fewer, fatter threads (8 units per thread, DCP_RES_LG2 interleaved)
+    const int variant = P.variant ? P.variant : 2;
+    if (variant == 2) return launch_lean<DCP_RES_S, 2, DCP_RES_LG2>(C, W, P, aet, grid, s);
+    return launch_lean<DCP_RES_S, 1, DCP_RES_LG>(C, W, P, aet, grid, s);
+}
+#endif
