@@ -4,9 +4,12 @@ import numpy as np
 RTOL = 1e-9      # north_star: flows and NSE/log-NSE within 1e-9 relative in FP64
 
 
-def compare_flows(q_gpu, q_ref, rtol=RTOL):
+def compare_flows(q_gpu, q_ref, rtol=RTOL, floor=1e-3):
     """q: (nriv, nstep, M).  Members whose oracle flows are non-finite are compared by class
-    (finite / non-finite per member) only.  Returns a dict of diagnostics; raises AssertionError."""
+    (finite / non-finite per member) only.  Returns a dict of diagnostics; raises AssertionError.
+    Relative error is taken against max(|q_ref|, floor x mean|q_ref| of the gauge series): flows far
+    below the series scale are differences of O(scale) terms (qb + qof, the store difference in
+    dyna_satzone_analyticalsolver.f90:98) and carry the rounding noise of those terms."""
     assert q_gpu.shape == q_ref.shape
     M = q_ref.shape[2]
     fin_ref = np.isfinite(q_ref).all(axis=(0, 1))
@@ -16,19 +19,22 @@ def compare_flows(q_gpu, q_ref, rtol=RTOL):
     for m in np.where(fin_ref)[0]:
         a, b = q_gpu[:, :, m], q_ref[:, :, m]
         scale = np.abs(b).mean(axis=1, keepdims=True)            # per gauge series scale
-        err = np.abs(a - b) / np.maximum(np.abs(b), 1e-3 * scale + 1e-300)
+        err = np.abs(a - b) / np.maximum(np.abs(b), floor * scale + 1e-300)
         worst = max(worst, float(err.max()))
     assert worst <= rtol, f"max relative flow error {worst:.3e} > {rtol:.1e}"
     return dict(max_rel=worst, n_finite=int(fin_ref.sum()), n_members=M)
 
 
 def compare_perf(p_gpu, p_ref, rtol=RTOL):
+    """NaN / +-inf entries (no valid observations, zero variance of the observations, non-finite flows) must
+    coincide by class; finite entries are compared on 1 - measure, the accumulated ratio."""
     nan_ref, nan_gpu = np.isnan(p_ref), np.isnan(p_gpu)
     assert np.array_equal(nan_ref, nan_gpu), "NaN pattern of performance measures differs"
-    ok = ~nan_ref
+    inf_ref = np.isinf(p_ref)
+    assert np.array_equal(inf_ref, np.isinf(p_gpu)) and np.array_equal(np.sign(p_ref[inf_ref]), np.sign(p_gpu[inf_ref]))
+    ok = np.isfinite(p_ref)
     if not ok.any():
         return dict(max_rel=0.0)
-    # NSE = 1 - sse/sst: the contract is on the measure; compare 1-NSE (the accumulated ratio) relatively
     a, b = 1.0 - p_gpu[ok], 1.0 - p_ref[ok]
     err = np.abs(a - b) / np.maximum(np.abs(b), 1e-300)
     assert err.max() <= rtol, f"max relative error of (1 - measure) {err.max():.3e} > {rtol:.1e}"
