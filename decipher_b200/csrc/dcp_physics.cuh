@@ -240,7 +240,7 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
                                               double qin, HruState &s, LeanOut &o) {
     // root_zone1 (dyna_root_zone1.f90:39-66)
     double srz = s.srz + p;
-    const double pex = fm_max(srz - c.srmax, 0.0);
+    const double pex = fm_relu(srz - c.srmax);
     srz = fm_min(srz, c.srmax);
     double ea = epp * (srz * c.inv_srmax);
     ea = fm_min(fm_min(ea, epp), srz);
@@ -248,17 +248,17 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     // unsat_zone1 (dyna_unsat_zone1.f90:49-78)
     const double sd0 = s.sd;
     double suz = s.suz + pex;
-    const double lim = fm_max(sd0, 0.0);
-    const double exus = fm_max(suz - lim, 0.0);
+    const double lim = fm_relu(sd0);
+    const double exus = fm_relu(suz - lim);
     suz = fm_min(suz, lim);
     const double den = sd0 * c.td;
     double uz2 = g.dt * LEAN_DIV(suz, den);
-    uz2 = (den > 1e-290) ? fm_min(uz2, suz) : suz;       // tiny sd*td: suz/(sd*td) overflows, clipped to suz
-    uz2 = (sd0 > 0.0 && suz > 0.0) ? uz2 : 0.0;
+    uz2 = fm_sel_gt(den, 1e-290, fm_min(uz2, suz), suz); // tiny sd*td: suz/(sd*td) overflows, clipped to suz
+    uz2 = fm_sel_gt(fm_min(sd0, suz), 0.0, uz2, 0.0);    // only when sd > 0 and suz > 0
     suz = suz - uz2;
-    const bool flush = suz < 0.0000001;
-    uz2 = flush ? uz2 + suz : uz2;
-    suz = flush ? 0.0 : suz;
+    const double fl = fm_sel_lt(suz, 0.0000001, suz, 0.0);   // :70-73 flush: what is left goes with the drainage
+    uz2 = uz2 + fl;
+    suz = suz - fl;
     const double uz = uz2 * g.inv_dtt;
     // satzone_analyticalsolver (dyna_satzone_analyticalsolver.f90:60-119), ntt == 1 so qin2 == qin/ac
     const double qin_ac = qin * c.inv_ac;
@@ -275,13 +275,13 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     const double b = (c.q1 * g.dtt) * c.inv_m2;
     const double arg_small = (e1 + b) - a * (e1 - 0.5 * b);      // :76-77 (and :84 when u2 == 0)
     const double arg_reg = fma(e1 - r, e2, r);                    // :80
-    const double arg = (a < DCP_F32_1EM10) ? arg_small : arg_reg;
+    const double arg = fm_sel_lt(a, DCP_F32_1EM10, arg_small, arg_reg);
     double sd = c.m2 * LEAN_LOG(arg);
     o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !(arg > 1e-290 && arg < 1e290);
     double qbf = (sd - sd0) * g.inv_dtt + uz + qin_ac;            // :98
-    double exs = fm_max(-sd, 0.0);                                // :107-112
-    sd = fm_max(sd, 0.0);
-    const double over = fm_max(qbf - c.q0, 0.0);                  // :115-119
+    double exs = fm_relu(-sd);                                    // :107-112
+    sd = fm_relu(sd);
+    const double over = fm_relu(qbf - c.q0);                      // :115-119
     exs = fma(over, g.dtt, exs);
     qbf = fm_min(qbf, c.q0);
     s.sd = sd; s.suz = suz; s.srz = srz; s.qint1 = qin;
