@@ -15,7 +15,7 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "build", "libdecipher_b200.so")
+LIB_PATH = os.environ.get("DCP_B200_LIB") or os.path.join(_HERE, "csrc", "build", "libdecipher_b200.so")   # override: kernel-tuning builds
 
 c_double_p = C.POINTER(C.c_double)
 c_int32_p = C.POINTER(C.c_int32)

@@ -78,11 +78,174 @@ struct dcp_catchment {
     std::vector<double> node_reach_dist, node_down_dist;
     bool has_qobs = false;
     ResPlan plan{};                     // resident-kernel plan (plan.feasible == 0: streamed kernel only)
+    Res2Plan plan2{};                   // second-generation resident kernel (lean arithmetic, own-river catchments)
     int n_sm = 148;
     size_t smem_optin = 0;
     std::string plan_why;               // why the resident kernel is not available
     dcp_run_stats stats{};
 };
+
+namespace {
+
+// Plan of the second-generation resident kernel: ELL schedule of the weight matrix, column tables, river slots.
+void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vector<HruStatic> &hru,
+                 const std::vector<WEntry> &w, const std::vector<int32_t> &thread_hru, const std::vector<int32_t> &hru_pos,
+                 int nac_pad, const std::vector<double> &pet, cudaError_t &e) {
+    const int nac = d->nac, nriv = d->nriv, npt = d->npt, S = 2, COLS = DCP_RES_COMPUTE, TC = 128, H = 4;
+    const DevCatchment &C = c->C;
+    Res2Plan &Q = c->plan2;
+    // every river share of an HRU must sit on its own river ipriv (contribution sums)
+    std::vector<double> cq(nac, 0.0);
+    for (int ia = 0; ia < nac; ++ia)
+        for (int r = 0; r < nriv; ++r) {
+            const double sh = d->rivers[(size_t)r * nac + ia];
+            if (sh == 0.0) continue;
+            if (r != hru[ia].ipriv) return;
+            cq[ia] = C.dtt * hru[ia].w_riv * sh * hru[ia].ac;
+        }
+    const int G = COLS / nac_pad, npb = nac_pad / 32;
+    if (d->ngp > 255 || d->nge > 255 || G * S * npt * 2 + npt * 2 > 65535) return;
+    Q.nac_pad = nac_pad; Q.G = G; Q.Tt = DCP_RES_TT;
+    Q.phase_delay = getenv("DCP_RES_PHASE") ? atoi(getenv("DCP_RES_PHASE")) : 0;
+
+    // ---- ELL schedule per block of 32 positions.  Inside a quarter-warp (8 consecutive positions) one LDS.128
+    // serves the lanes whose source tuples fall in different 16-byte bank classes (position mod 8), so the
+    // entries of each row are ordered step by step to keep the classes of a quarter distinct.  (The order of the
+    // terms of a row is free in the lean policy; the exact policy keeps the reference's ascending-source order.)
+    std::vector<int32_t> ell_base(npb), ell_K(npb);
+    std::vector<double> ell_w;
+    std::vector<uint16_t> ell_src;
+    const bool schedule = !getenv("DCP_RES_NO_ELLSCHED");
+    for (int pb = 0; pb < npb; ++pb) {
+        int K = 0;
+        for (int l = 0; l < 32; ++l) {
+            const int hh = thread_hru[pb * 32 + l];
+            if (hh >= 0) K = std::max(K, hru[hh].row_end - hru[hh].row_beg);
+        }
+        K = (K + 3) / 4 * 4;
+        ell_base[pb] = (int)ell_w.size(); ell_K[pb] = K;
+        const size_t base = ell_w.size();
+        ell_w.resize(base + (size_t)K * 32, 0.0);
+        ell_src.resize(base + (size_t)K * 32, 0);
+        for (int q = 0; q < 4; ++q) {                                   // quarter-warp
+            std::vector<std::vector<int>> rem(8);                       // remaining entry ids per row
+            for (int l = 0; l < 8; ++l) {
+                const int hh = thread_hru[pb * 32 + q * 8 + l];
+                if (hh >= 0) for (int x = hru[hh].row_beg; x < hru[hh].row_end; ++x) rem[l].push_back(x);
+            }
+            for (int k = 0; k < K; ++k) {
+                int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};                 // lanes per bank class at this step
+                int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
+                std::stable_sort(order, order + 8, [&](int a, int b) { return rem[a].size() > rem[b].size(); });
+                for (int oi = 0; oi < 8; ++oi) {
+                    const int l = order[oi], pos = pb * 32 + q * 8 + l;
+                    const size_t o = base + (size_t)k * 32 + q * 8 + l;
+                    const int left = K - k;                              // steps left including this one
+                    int pick = -1;
+                    if (!rem[l].empty()) {
+                        if (!schedule) pick = 0;
+                        else {
+                            int best = 1 << 30;
+                            for (size_t x = 0; x < rem[l].size(); ++x) {
+                                const int cls = hru_pos[w[rem[l][x]].src] & 7;
+                                if (used[cls] < best) { best = used[cls]; pick = (int)x; }
+                            }
+                            // a row with spare steps may wait (zero-weight entry on its own tuple) rather than collide
+                            if (best > 0 && (int)rem[l].size() < left && used[pos & 7] == 0) pick = -1;
+                        }
+                    }
+                    if (pick >= 0) {
+                        const WEntry &we = w[rem[l][pick]];
+                        ell_w[o] = we.w * we.ac_src; ell_src[o] = (uint16_t)hru_pos[we.src];
+                        used[hru_pos[we.src] & 7]++;
+                        rem[l].erase(rem[l].begin() + pick);
+                    } else {
+                        ell_w[o] = 0.0; ell_src[o] = (uint16_t)pos;    // padding: zero weight on the own tuple
+                        used[pos & 7]++;
+                    }
+                }
+            }
+        }
+    }
+    Q.ell_len = (int)ell_w.size();
+    if (Q.ell_len >= (1 << 20)) return;
+
+    // ---- contribution slots: river-major, ascending HRU inside a river; idle positions after the last river ----
+    std::vector<int32_t> rank(nac_pad, 0), rbeg(nriv + 1, 0);
+    int slot = 0;
+    for (int r = 0; r < nriv; ++r) {
+        for (int ia = 0; ia < nac; ++ia) if (hru[ia].ipriv == r) rank[hru_pos[ia]] = slot++;
+        rbeg[r + 1] = slot;
+    }
+    for (int pos = 0; pos < nac_pad; ++pos) if (thread_hru[pos] < 0) rank[pos] = slot++;
+
+    // ---- the 16 blocks of 32 columns are dealt to the 4 compute warps of a team longest-first ----
+    std::vector<int> blocks(16), load(4, 0), cnt(4, 0);
+    for (int i = 0; i < 16; ++i) blocks[i] = i;
+    std::stable_sort(blocks.begin(), blocks.end(), [&](int a, int b) { return ell_K[a % npb] > ell_K[b % npb]; });
+    std::vector<int4> col_i((size_t)H * TC);
+    std::vector<double2> col_d((size_t)H * TC * 2);
+    std::vector<int32_t> col_ia((size_t)H * TC, -1);
+    for (int bi = 0; bi < 16; ++bi) {
+        const int blk = blocks[bi];
+        int wsel = -1;
+        for (int wi = 0; wi < 4; ++wi) if (cnt[wi] < H && (wsel < 0 || load[wi] < load[wsel])) wsel = wi;
+        const int j = cnt[wsel]++;
+        const int g = blk / npb, pb = blk % npb;
+        load[wsel] += ell_K[pb];
+        for (int l = 0; l < 32; ++l) {
+            const int pos = pb * 32 + l, ia = thread_hru[pos], t = wsel * 32 + l;
+            const size_t o = (size_t)j * TC + t;
+            const HruStatic *h = ia >= 0 ? &hru[ia] : nullptr;
+            int4 ci;
+            ci.x = (ell_base[pb] + l) | (ell_K[pb] << 20);
+            ci.y = (h ? h->ippt : 0) | ((h ? h->ipet : 0) << 8) | (g << 16) | (h ? 0 : (int)0x80000000u);
+            ci.z = (g * nac_pad + pos) | ((g * nac_pad) << 16);
+            ci.w = ((g * S * npt + (h ? h->ipar : 0)) * 2) | ((g * nac_pad + rank[pos]) << 16);
+            col_i[o] = ci;
+            col_d[2 * o + 0] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);
+            col_d[2 * o + 1] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);
+            col_ia[o] = ia;
+        }
+    }
+    if (getenv("DCP_RES_DEBUG"))
+        fprintf(stderr, "[dcp plan2] ell_len %d (nnz %zu), K per block:%s; gather steps per warp: %d %d %d %d\n", Q.ell_len,
+                w.size(), [&] { static std::string s2; s2.clear(); for (int pb = 0; pb < npb; ++pb) s2 += " " + std::to_string(ell_K[pb]); return s2.c_str(); }(),
+                load[0], load[1], load[2], load[3]);
+
+    Q.n_teams = G * nriv;
+    Q.team = 32;
+    while (Q.team > 1 && Q.team * Q.n_teams > 64) Q.team >>= 1;
+    Q.n_pass = (Q.n_teams * Q.team + 63) / 64;
+    if (Q.n_pass > 16) return;
+    // shared memory: [shared tables][team 0][team 1]
+    size_t off = 0;
+    auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
+    Q.off_ellw = take((size_t)Q.ell_len * 8);
+    Q.off_ells = take((size_t)Q.ell_len * 2);
+    Q.off_coli = take((size_t)H * TC * 16);
+    Q.off_cold = take((size_t)H * TC * 32);
+    Q.off_rbeg = take((size_t)(nriv + 1) * 4);
+    Q.off_team = (int)((off + 127) & ~(size_t)127);
+    off = 0;
+    Q.off_qbf = take((size_t)2 * COLS * 16);
+    Q.off_con = take((size_t)2 * COLS * 16);
+    Q.off_cst = take((size_t)S * 2 * COLS * 16);
+    Q.off_par = take((size_t)G * S * npt * 2 * 16);
+    Q.off_forc = take((size_t)2 * Q.Tt * (d->ngp + d->nge) * 8);
+    Q.off_bar = take(16);
+    Q.team_bytes = (int)((off + 127) & ~(size_t)127);
+    Q.smem_bytes = Q.off_team + 2 * Q.team_bytes;
+    if ((size_t)Q.smem_bytes > c->smem_optin) return;
+    std::vector<double> pet_pos(pet);
+    for (double &x : pet_pos) x = x > 0.0 ? x : 0.0;
+    auto up = [&](auto &vec, auto **dst) { if (e == cudaSuccess) e = upload(vec, dst, c->owned); };
+    up(ell_w, &Q.ell_w); up(ell_src, &Q.ell_src); up(col_i, &Q.col_i); up(col_d, &Q.col_d); up(col_ia, &Q.col_ia);
+    up(rbeg, &Q.rbeg); up(pet_pos, &Q.pet_pos);
+    Q.feasible = 1;
+}
+
+}  // namespace
 
 extern "C" {
 
@@ -362,6 +525,11 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
                 P.feasible = 1;
                 P.lean_ok = d->ntt == 1;
                 for (int i = 0; i < nac; ++i) if (hru[i].ims_rz != 1 || hru[i].ims_uz != 1) P.lean_ok = 0;
+
+                // ---- second-generation plan (dcp_resident_v2.cu) ----
+                c->plan2 = Res2Plan{};
+                if (P.lean_ok && !getenv("DCP_RES_NO_V2"))
+                    build_plan2(c, d, hru, w, thread_hru, hru_pos, nac_pad, pet, e);
             }
         }
     }
@@ -605,8 +773,18 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             const int grid = std::min(c->n_sm, P.n_groups);
             DevBuf dbg;
             if (getenv("DCP_RES_DEBUG")) { CUDA_TRY(dbg.reserve((size_t)grid * 20 * 8)); CUDA_TRY(cudaMemsetAsync(dbg.p, 0, (size_t)grid * 20 * 8, s)); P.dbg = (long long *)dbg.p; }
+            const bool use_v2 = fast && c->plan2.feasible;
+            Res2Plan Q = c->plan2;
+            int grid2 = 0;
+            if (use_v2) {
+                const int Mv = Q.G * 2;                 // members per team group; two teams per CTA
+                Q.n_groups = (int)((Bn + Mv - 1) / Mv);
+                grid2 = std::min(c->n_sm, (Q.n_groups + 1) / 2);
+                Q.dbg = P.dbg;
+            }
             tm.mark(T_PHYS);
-            CUDA_TRY(dcp_launch_physics_resident(C, W, P, fast, aet, grid, s));
+            if (use_v2) CUDA_TRY(dcp_launch_physics_resident_v2(C, W, Q, aet, grid2, s));
+            else CUDA_TRY(dcp_launch_physics_resident(C, W, P, fast, aet, grid, s));
             ++n_launch; ++n_phys;
             if (P.dbg) {           // per-warp busy cycles of the persistent kernel (tuning aid)
                 std::vector<long long> hb((size_t)grid * 20);

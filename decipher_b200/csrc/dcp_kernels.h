@@ -6,6 +6,9 @@
 #define DCP_RES_S 4                  // member slots per compute thread of the resident kernel
 #define DCP_RES_LG 2                 // member slots interleaved per basic block in the lean step
 #define DCP_RES_LG2 2                // same for the two-columns-per-thread variant
+#ifndef DCP_RES2_LG
+#define DCP_RES2_LG 4                // member slots interleaved per basic block in the second-generation kernel
+#endif
 #define DCP_RES_COMPUTE 512
 #define DCP_RES_MAXPAIRS 256         // (members per CTA) x nriv the river warps can carry (4 warps x 4 passes x 16 pairs)
 #define DCP_RES_TT 64                // forcing tile length (timesteps)
@@ -21,4 +24,6 @@ void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf,
 void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s);
 cudaError_t dcp_launch_physics_resident(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast,
                                         bool aet, int grid, cudaStream_t s);
+cudaError_t dcp_launch_physics_resident_v2(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, bool aet,
+                                           int grid, cudaStream_t s);
 void dcp_launch_debug_fastmath(int op, int64_t n, const double *x, double *y, cudaStream_t s);

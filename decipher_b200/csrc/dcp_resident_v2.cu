@@ -1,0 +1,395 @@
+// dcp_resident_v2.cu — second-generation persistent on-chip kernel for the lean (branch-free, fast
+// arithmetic) step.  Same residency model as dcp_resident.cu (a member's stores stay in registers and
+// its last baseflow in shared memory for the WHOLE simulation; rain/PET tiles arrive by TMA), rebuilt
+// around what the ncu captures of the first generation showed (profiles/r1_ncu_resident_*, r1_ncu_v2_*):
+//
+//   (1) the dynamic_dist gather is bound by shared-memory BANDWIDTH, not latency: every lane reads a
+//       different source tuple, 32-byte tuples collide on four bank classes, and all warps of the CTA
+//       gather at the same time (right after the per-step barrier) while the FP64 pipe idles;
+//   (2) the river warps were as busy as the compute warps: three loads per summed term;
+//   (3) one warp owned the longest W rows and every other warp waited for it at the barrier.
+//
+// Design:
+//   * TWO independent teams per CTA ("virtual CTAs"): team = 4 compute warps + 2 river warps with its
+//     own named barrier, forcing pipeline and member groups; a team runs 2 member slots over all 512 HRU
+//     columns (4 columns per thread).  Members never interact, so the teams drift out of phase and one
+//     team's gather (shared-memory bound) overlaps the other's physics (FP64 bound).  Only the weight
+//     matrix and the per-column tables are shared (read-only).
+//   * gather = ELLPACK SpMM.  W is stored per block of 32 thread positions, step-major, rows padded with
+//     zero weights to the block's longest row; the trip count is warp-uniform and the loop is unrolled
+//     by four with all weight/index loads of a batch issued before the first tuple load.  A tuple is the
+//     16 bytes of the team's two member slots, so one LDS.128 per source and eight bank classes; the
+//     host orders the entries of each row so that the eight lanes of a quarter-warp hit different
+//     classes wherever the catchment allows (conflict-aware ELL schedule, dcp_api.cu).
+//   * river sums by contribution.  Every compute thread publishes, per member slot,
+//         c = (dtt*w_riv*share*ac) * qbf_old + (exs+exus)*ac          (dyna_dynamic_dist.f90:59-61,
+//                                                                      dyna_results_ac.f90:35-38)
+//     into a river-major slot array, so qout(t) = qb(t) + qof(t) (dyna_river.f90:43) is the plain sum of a
+//     contiguous range: the river warps read tuples with no index or coefficient loads and finish with a
+//     shuffle tree.  Needs every HRU's river share to sit on its own river `ipriv` (true for DTA output:
+//     an HRU class carries its gauge id); other catchments use the first generation.
+//   * blocks of 32 positions are dealt to the four compute warps longest-first (LPT) so that the
+//     per-step gather work of the warps is even.
+//
+// Built WITH FMA contraction (no operation-order contract in the lean policy; parity is checked against
+// the oracle at 1e-9).  Hot path citations: RRMODEL/dyna_topmod.f90:92-233, dyna_dynamic_dist.f90:47-67,
+// dyna_root_zone1.f90, dyna_unsat_zone1.f90, dyna_satzone_analyticalsolver.f90, dyna_river.f90:42-49.
+#include "dcp_device.cuh"
+#include "dcp_physics.cuh"
+#include "dcp_kernels.h"
+#include "dcp_resident_common.cuh"
+
+#include <cstdint>
+
+#define R2_COLS DCP_RES_COMPUTE       // 512 unit columns per member slot
+#define R2_TEAMS 2
+#define R2_TC 128                     // compute threads per team (4 columns each)
+#define R2_TR 64                      // river threads per team
+#define R2_TT (R2_TC + R2_TR)         // threads at a team barrier
+#define R2_CT (R2_TEAMS * R2_TC)      // 256 compute threads
+#define R2_THREADS (R2_TEAMS * R2_TT) // 384
+#define R2_REG_COMPUTE 232            // launch cap 168: (168-40)*128 == (232-168)*256
+#define R2_REG_RIVER 40
+#define R2_S 2                        // member slots per team
+#define R2_H 4                        // columns per compute thread
+
+struct R2Smem {                       // team-private views unless noted
+    double2 *qbf_s;       // [2][512]        baseflow tuples (2 member slots), double buffered in time
+    double2 *con_s;       // [2][512]        river contributions by slot, double buffered in time
+    double2 *cst_s;       // [2][2][512]     {q0, q2}, {m2, 1/m2} per (member slot, column)
+    double2 *par_s;       // [Mv][npt][2]    {srmax, 1/srmax}, {td, smax}
+    double *forc_s;       // [2][Tt*(ngp+nge)]
+    uint64_t *bars;       // [2]
+    // shared by both teams (read-only after setup)
+    double *ellw_s;       // [ell_len]
+    uint16_t *ells_s;     // [ell_len]
+    int4 *coli_s;         // [4][128]        per (column slot j, team thread): packed indices
+    double2 *cold_s;      // [4][128][2]     {ac, 1/ac}, {cq, cos(mslp)}
+    int32_t *rbeg_s;      // [nriv+1]
+};
+
+__device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(R2_TT) : "memory"); }
+
+#define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})
+
+// ---------------------------------------------------------------------------------------------
+// compute role: 4 warps per team, thread = 4 HRU columns x 2 member slots
+// ---------------------------------------------------------------------------------------------
+template <bool AET>
+__device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
+                                           const int team, const int tt_id) {
+    constexpr int H = R2_H, S = R2_S;
+    const int B = W.B, npt = C.npt;
+    const int forc_stride = P.Tt * (C.ngp + C.nge);
+    const int par_kstride = npt * 2;
+    const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
+    const int Mv = P.G * S;                                  // members per team group
+    uint32_t tiles_done = 0;
+    long long busy = 0;
+
+    for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
+        const int m_base = vg * Mv;
+        team_sync(team);                                     // previous group fully done with shared memory
+
+        // ---- load the group's initial state (written by k_init_members) ----
+        double sd[H][S], suz[H][S], srz[H][S], aet[H][S];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const int4 ci = M.coli_s[j * R2_TC + tt_id];
+            const int tup = ci.z & 0xffff, g = (ci.y >> 16) & 0x7fff;
+            const int ia = P.col_ia[j * R2_TC + tt_id];
+            const double cosm = M.cold_s[(j * R2_TC + tt_id) * 2 + 1].y;
+            const int ipar = ia >= 0 ? C.hru[ia].ipar : 0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const int m = m_base + g * S + k;
+                sd[j][k] = 1.0; suz[j][k] = 0.0; srz[j][k] = 0.0; aet[j][k] = 0.0;
+                double qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_m2 = 1.0, c_im2 = 1.0;
+                if (ia >= 0 && m < B) {
+                    const size_t o = (size_t)ia * B + m;
+                    sd[j][k] = W.sd[o]; suz[j][k] = W.suz[o]; srz[j][k] = W.srz[o];
+                    c_q0 = W.q0[o]; c_q2 = W.q2[o];
+                    const double szm = W.par[(0 * npt + ipar) * (size_t)B + m];
+                    c_m2 = szm / cosm;                       // dyna_satzone_analyticalsolver.f90:52
+                    c_im2 = cosm / szm;
+                    qb0 = W.qbf0[o];
+                }
+                reinterpret_cast<double *>(M.qbf_s + tup)[k] = qb0;                 // time buffer 0 = step 0's "old" qbf
+                reinterpret_cast<double *>(M.qbf_s + R2_COLS + tup)[k] = 0.0;
+                M.cst_s[(k * 2 + 0) * R2_COLS + tup] = make_double2(c_q0, c_q2);
+                M.cst_s[(k * 2 + 1) * R2_COLS + tup] = make_double2(c_m2, c_im2);
+            }
+        }
+        for (int i = tt_id; i < Mv * npt; i += R2_TC) {      // member parameters -> shared
+            const int jm = i / npt, l = i % npt;
+            const int m = m_base + jm;
+            double srmax = 1.0, td = 1.0, smax = 1.0;
+            if (m < B) {
+                srmax = W.par[(2 * npt + l) * (size_t)B + m];
+                td = W.par[(5 * npt + l) * (size_t)B + m];
+                smax = W.par[(6 * npt + l) * (size_t)B + m];
+            }
+            M.par_s[i * 2 + 0] = make_double2(srmax, 1.0 / srmax);
+            M.par_s[i * 2 + 1] = make_double2(td, smax);
+        }
+        team_sync(team);
+
+        int t = 0;
+        for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
+            const uint32_t b = tiles_done & 1;
+            mbar_wait(&M.bars[b], (tiles_done >> 1) & 1);    // forcing tile landed (TMA, issued by the team's river warp)
+            const double *forc_t = M.forc_s + b * forc_stride;
+            const int t_end = min(C.nstep, t + P.Tt);
+            for (int tt = 0; t < t_end; ++t, ++tt) {
+                const long long c0 = P.dbg ? clock64() : 0;
+                const double2 *qbf_cur = M.qbf_s + (t & 1) * R2_COLS;
+                double2 *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * R2_COLS;
+                double2 *con = M.con_s + (t & 1) * R2_COLS;
+#pragma unroll
+                for (int jp = 0; jp < H; jp += 2) {          // two columns = four (HRU, member) units per basic block
+                    int4 ci[2];
+                    double qin[2][S];
+                    // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52): ELL rows, 4 entries per batch ----
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        ci[jj] = M.coli_s[(jp + jj) * R2_TC + tt_id];
+                        const int ebase = ci[jj].x & 0xfffff, eK = ci[jj].x >> 20;
+                        const double2 *qg = qbf_cur + (int)((uint32_t)ci[jj].z >> 16);  // tuple base of the member sub-group
+                        const double *wp = M.ellw_s + ebase;
+                        const uint16_t *sp = M.ells_s + ebase;
+                        double q0 = 0.0, q1 = 0.0;
+                        for (int e = 0; e < eK; e += 4) {
+                            double w[4]; int so[4]; double2 qv[4];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) { w[u] = wp[(e + u) * 32]; so[u] = sp[(e + u) * 32]; }
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) qv[u] = qg[so[u]];
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) { q0 = fma(qv[u].x, w[u], q0); q1 = fma(qv[u].y, w[u], q1); }
+                        }
+                        qin[jj][0] = q0; qin[jj][1] = q1;
+                    }
+                    // ---- root zone, unsaturated zone, saturated zone: 4 interleaved dependency chains ----
+                    LeanOut lo[2][S];
+                    double cq[2];
+                    bool any_slow = false;
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int j = jp + jj;
+                        const int tup = ci[jj].z & 0xffff;
+                        const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];      // {ac, 1/ac}
+                        const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];      // {cq, cos}
+                        cq[jj] = d1.x;
+                        const double p = forc_t[tt * C.ngp + (ci[jj].y & 0xff)];
+                        const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci[jj].y >> 8) & 0xff)];   // already max(ep, 0)
+#pragma unroll
+                        for (int k = 0; k < S; ++k) {
+                            const double2 c0v = M.cst_s[(k * 2 + 0) * R2_COLS + tup];
+                            const double2 c1v = M.cst_s[(k * 2 + 1) * R2_COLS + tup];
+                            const double2 p0 = M.par_s[(ci[jj].w & 0xffff) + k * par_kstride];
+                            const double2 p1 = M.par_s[(ci[jj].w & 0xffff) + k * par_kstride + 1];
+                            HruConst c;
+                            c.ac = d0.x; c.inv_ac = d0.y;
+                            c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = c1v.x; c.inv_m2 = c1v.y;
+                            c.q1 = c.q0 * d1.y;                                         // dyna_satzone_analyticalsolver.f90:49
+                            c.srmax = p0.x; c.inv_srmax = p0.y; c.td = p1.x; c.smax = p1.y;
+                            c.ims_rz = 1; c.ims_uz = 1;
+                            HruState st;
+                            st.sd = sd[j][k]; st.suz = suz[j][k]; st.srz = srz[j][k]; st.qint1 = 0.0;
+                            hru_step_lean(c, gc, p, epp, qin[jj][k], st, lo[jj][k]);
+                            sd[j][k] = st.sd; suz[j][k] = st.suz; srz[j][k] = st.srz;  // ntt == 1: qint1 is not carried
+                            any_slow |= lo[jj][k].slow;
+                        }
+                    }
+                    if (any_slow) {                                                     // rare: sd > smax, out-of-range exponent
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                            for (int k = 0; k < S; ++k)
+                                if (lo[jj][k].slow) {
+                                    const int j = jp + jj;
+                                    const int tup = ci[jj].z & 0xffff;
+                                    const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];
+                                    const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];
+                                    const double2 c0v = M.cst_s[(k * 2 + 0) * R2_COLS + tup];
+                                    const double2 c1v = M.cst_s[(k * 2 + 1) * R2_COLS + tup];
+                                    HruConst c;
+                                    c.ac = d0.x; c.inv_ac = d0.y;
+                                    c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = c1v.x; c.inv_m2 = c1v.y;
+                                    c.q1 = c.q0 * d1.y;
+                                    c.smax = M.par_s[(ci[jj].w & 0xffff) + k * par_kstride + 1].y;
+                                    hru_step_lean_fixup(c, gc, qin[jj][k], qin[jj][k], sd[j][k], lo[jj][k]);
+                                }
+                    }
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int j = jp + jj;
+                        if (ci[jj].y >= 0) {                                            // live column (bit 31 of .y marks idle ones)
+                            const int tup = ci[jj].z & 0xffff, ctup = (int)((uint32_t)ci[jj].w >> 16);
+                            const double2 qold = qbf_cur[tup];                          // this HRU's baseflow at the start of the step
+                            qbf_nxt[tup] = make_double2(lo[jj][0].qbf, lo[jj][1].qbf);
+                            con[ctup] = make_double2(fma(cq[jj], qold.x, lo[jj][0].exac), fma(cq[jj], qold.y, lo[jj][1].exac));
+                        }
+                        if (AET) {
+#pragma unroll
+                            for (int k = 0; k < S; ++k) aet[j][k] = aet[j][k] + lo[jj][k].ea;
+                        }
+                    }
+                }
+                if (P.dbg) busy += clock64() - c0;
+                team_sync(team);
+            }
+        }
+        if (P.dbg && (tt_id & 31) == 0) P.dbg[blockIdx.x * 12 + team * 4 + (tt_id >> 5)] = busy;
+        if (AET) {
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                const int ia = P.col_ia[j * R2_TC + tt_id];
+                const int g = (M.coli_s[j * R2_TC + tt_id].y >> 16) & 0x7fff;
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                    const int m = m_base + g * S + k;
+                    if (ia >= 0 && m < B) W.aet[(size_t)ia * B + m] = aet[j][k];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// river role: 2 warps per team.  A group of T lanes adds up one (member sub-group, river) range of
+// contribution tuples, one step behind the compute warps; lane 0 also drives the team's forcing TMA.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
+                                         const int team, const int rl) {
+    constexpr int S = R2_S;
+    const int nac_pad = P.nac_pad, B = W.B, nriv = C.nriv;
+    const int forc_stride = P.Tt * (C.ngp + C.nge);
+    const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
+    const uint32_t rain_bytes = (uint32_t)(P.Tt * C.ngp * sizeof(double));
+    const uint32_t pet_bytes = (uint32_t)(P.Tt * C.nge * sizeof(double));
+    const int Mv = P.G * S;
+    uint32_t tiles_done = 0;
+    const int T = P.team, sub = rl & (T - 1);
+    const int sums_per_pass = R2_TR / T;
+    long long busy = 0;
+
+    for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
+        const int m_base = vg * Mv;
+        team_sync(team);
+        if (rl == 0) {                                       // forcing tile 0 of this group
+            const uint32_t b = tiles_done & 1;
+            fence_proxy_async();
+            mbar_expect_tx(&M.bars[b], rain_bytes + pet_bytes);
+            tma_load_1d(M.forc_s + b * forc_stride, C.rain, rain_bytes, &M.bars[b]);
+            tma_load_1d(M.forc_s + b * forc_stride + P.Tt * C.ngp, P.pet_pos, pet_bytes, &M.bars[b]);
+        }
+        team_sync(team);
+
+        // sums the contributions of step tp and streams qout(tp) to global memory (dyna_river.f90:43)
+        auto flush_step = [&](int tp) {
+            const double2 *con = M.con_s + (tp & 1) * R2_COLS;
+            for (int pass = 0; pass < P.n_pass; ++pass) {
+                const int sum_id = pass * sums_per_pass + rl / T;
+                const bool live = sum_id < P.n_teams;
+                const int g = live ? sum_id / nriv : 0, r = live ? sum_id - g * nriv : 0;
+                const int beg = M.rbeg_s[r], end = live ? M.rbeg_s[r + 1] : beg;
+                const double2 *cg = con + g * nac_pad;
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll 4
+                for (int p = beg + sub; p < end; p += T) { const double2 x = cg[p]; a0 += x.x; a1 += x.y; }
+                for (int o = T >> 1; o > 0; o >>= 1) {
+                    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+                    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+                }
+                if (live && sub == 0) {
+                    const int m0 = m_base + g * S;
+                    const size_t tq = (size_t)(tp & W.Rmask);
+                    if (m0 + 0 < B) W.qout[((size_t)(m0 + 0) * nriv + r) * W.R + tq] = a0;
+                    if (m0 + 1 < B) W.qout[((size_t)(m0 + 1) * nriv + r) * W.R + tq] = a1;
+                }
+            }
+        };
+
+        int t = 0;
+        for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
+            if (rl == 0 && tile + 1 < ntiles) {
+                // prefetch the next tile into the other buffer (the team left it at the last barrier)
+                const uint32_t nb = (tiles_done & 1) ^ 1;
+                const size_t t_next = (size_t)(tile + 1) * P.Tt;
+                fence_proxy_async();
+                mbar_expect_tx(&M.bars[nb], rain_bytes + pet_bytes);
+                tma_load_1d(M.forc_s + nb * forc_stride, C.rain + t_next * C.ngp, rain_bytes, &M.bars[nb]);
+                tma_load_1d(M.forc_s + nb * forc_stride + P.Tt * C.ngp, P.pet_pos + t_next * C.nge, pet_bytes, &M.bars[nb]);
+            }
+            const int t_end = min(C.nstep, t + P.Tt);
+            for (; t < t_end; ++t) {
+                const long long c0 = P.dbg ? clock64() : 0;
+                if (t > 0) flush_step(t - 1);                // while the compute warps run step t
+                if (P.dbg) busy += clock64() - c0;
+                team_sync(team);
+            }
+        }
+        flush_step(C.nstep - 1);
+        if (P.dbg && (rl & 31) == 0) P.dbg[blockIdx.x * 12 + 8 + team * 2 + (rl >> 5)] = busy;
+    }
+}
+
+template <bool AET>
+__global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchment C, DevBatch W, Res2Plan P) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int tid = threadIdx.x;
+    // warps 0-3: team 0 compute, 4-7: team 1 compute, 8-9: team 0 river, 10-11: team 1 river
+    const bool is_compute = tid < R2_CT;
+    const int team = is_compute ? tid / R2_TC : (tid - R2_CT) / R2_TR;
+    R2Smem M;
+    unsigned char *tb = smem + P.off_team + (size_t)team * P.team_bytes;
+    M.qbf_s = (double2 *)(tb + P.off_qbf);
+    M.con_s = (double2 *)(tb + P.off_con);
+    M.cst_s = (double2 *)(tb + P.off_cst);
+    M.par_s = (double2 *)(tb + P.off_par);
+    M.forc_s = (double *)(tb + P.off_forc);
+    M.bars = (uint64_t *)(tb + P.off_bar);
+    M.ellw_s = (double *)(smem + P.off_ellw);
+    M.ells_s = (uint16_t *)(smem + P.off_ells);
+    M.coli_s = (int4 *)(smem + P.off_coli);
+    M.cold_s = (double2 *)(smem + P.off_cold);
+    M.rbeg_s = (int32_t *)(smem + P.off_rbeg);
+
+    for (int e = tid; e < P.ell_len; e += R2_THREADS) { M.ellw_s[e] = P.ell_w[e]; M.ells_s[e] = P.ell_src[e]; }
+    for (int i = tid; i < R2_H * R2_TC; i += R2_THREADS) {
+        M.coli_s[i] = P.col_i[i];
+        M.cold_s[2 * i] = P.col_d[2 * i]; M.cold_s[2 * i + 1] = P.col_d[2 * i + 1];
+    }
+    for (int i = tid; i <= C.nriv; i += R2_THREADS) M.rbeg_s[i] = P.rbeg[i];
+    if (!is_compute && (tid - R2_CT) % R2_TR == 0) {
+        mbar_init(&M.bars[0], 1);
+        mbar_init(&M.bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+
+    if (is_compute) {
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R2_REG_COMPUTE));
+        if (P.phase_delay < 0 && team == 1) return;          // tuning experiment: one team only (half the members are skipped)
+        if (team == 1 && P.phase_delay > 0) {                // start the second team out of phase with the first
+            const long long t0 = clock64();
+            while (clock64() - t0 < P.phase_delay) {}
+        }
+        r2_compute<AET>(C, W, P, M, team, tid % R2_TC);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_RIVER));
+        if (P.phase_delay < 0 && team == 1) return;
+        r2_river(C, W, P, M, team, (tid - R2_CT) % R2_TR);
+    }
+}
+#undef gc
+
+cudaError_t dcp_launch_physics_resident_v2(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, bool aet,
+                                           int grid, cudaStream_t s) {
+    void (*k)(DevCatchment, DevBatch, Res2Plan) = aet ? k_physics_resident_v2<true> : k_physics_resident_v2<false>;
+    cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
+    if (e != cudaSuccess) return e;
+    k<<<grid, R2_THREADS, P.smem_bytes, s>>>(C, W, P);
+    return cudaGetLastError();
+}
