@@ -122,7 +122,7 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
             const int hh = thread_hru[pb * 32 + l];
             if (hh >= 0) K = std::max(K, hru[hh].row_end - hru[hh].row_beg);
         }
-        K = (K + 3) / 4 * 4;
+        K = (K + DCP_RES2_GB - 1) / DCP_RES2_GB * DCP_RES2_GB;
         ell_base[pb] = (int)ell_w.size(); ell_K[pb] = K;
         const size_t base = ell_w.size();
         ell_w.resize(base + (size_t)K * 32, 0.0);
@@ -167,9 +167,6 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
             }
         }
     }
-    Q.ell_len = (int)ell_w.size();
-    if (Q.ell_len >= (1 << 20)) return;
-
     // ---- contribution slots: river-major, ascending HRU inside a river; idle positions after the last river ----
     std::vector<int32_t> rank(nac_pad, 0), rbeg(nriv + 1, 0);
     int slot = 0;
@@ -183,35 +180,59 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     std::vector<int> blocks(16), load(4, 0), cnt(4, 0);
     for (int i = 0; i < 16; ++i) blocks[i] = i;
     std::stable_sort(blocks.begin(), blocks.end(), [&](int a, int b) { return ell_K[a % npb] > ell_K[b % npb]; });
-    std::vector<int4> col_i((size_t)H * TC);
-    std::vector<double2> col_d((size_t)H * TC * 2);
-    std::vector<int32_t> col_ia((size_t)H * TC, -1);
+    int slot_blk[4][4];
     for (int bi = 0; bi < 16; ++bi) {
         const int blk = blocks[bi];
         int wsel = -1;
         for (int wi = 0; wi < 4; ++wi) if (cnt[wi] < H && (wsel < 0 || load[wi] < load[wsel])) wsel = wi;
-        const int j = cnt[wsel]++;
-        const int g = blk / npb, pb = blk % npb;
-        load[wsel] += ell_K[pb];
-        for (int l = 0; l < 32; ++l) {
-            const int pos = pb * 32 + l, ia = thread_hru[pos], t = wsel * 32 + l;
-            const size_t o = (size_t)j * TC + t;
-            const HruStatic *h = ia >= 0 ? &hru[ia] : nullptr;
-            int4 ci;
-            ci.x = (ell_base[pb] + l) | (ell_K[pb] << 20);
-            ci.y = (h ? h->ippt : 0) | ((h ? h->ipet : 0) << 8) | (g << 16) | (h ? 0 : (int)0x80000000u);
-            ci.z = (g * nac_pad + pos) | ((g * nac_pad) << 16);
-            ci.w = ((g * S * npt + (h ? h->ipar : 0)) * 2) | ((g * nac_pad + rank[pos]) << 16);
-            col_i[o] = ci;
-            col_d[2 * o + 0] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);
-            col_d[2 * o + 1] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);
-            col_ia[o] = ia;
-        }
+        slot_blk[wsel][cnt[wsel]++] = blk;
+        load[wsel] += ell_K[blk % npb];
     }
+    // ---- flat gather list per compute warp: the four columns of a thread one after the other, step-major over the
+    // lanes, one 8-byte word per entry = the weight with the absolute source tuple index (< 512) in its lowest nine
+    // mantissa bits (weight rounded to the nearest such value: relative change <= 2^-44).  One spare batch of four
+    // steps follows each warp's list (the kernel prefetches one batch ahead). ----
+    auto pack = [](double wv, int idx) {
+        uint64_t b; std::memcpy(&b, &wv, 8);
+        b = ((b + 256) & ~(uint64_t)511) | (uint64_t)idx;
+        double r; std::memcpy(&r, &b, 8); return r;
+    };
+    std::vector<double> ent;
+    std::vector<int4> col_i((size_t)H * TC);
+    std::vector<double2> col_d((size_t)H * TC * 2);
+    std::vector<int32_t> col_ia((size_t)H * TC, -1);
+    for (int wi = 0; wi < 4; ++wi)
+        for (int j = 0; j <= H; ++j) {
+            const size_t fbase = ent.size();
+            if (j == H) { ent.resize(fbase + DCP_RES2_GB * 32, 0.0); break; }
+            const int blk = slot_blk[wi][j], g = blk / npb, pb = blk % npb, K = ell_K[pb];
+            ent.resize(fbase + (size_t)K * 32);
+            for (int k = 0; k < K; ++k)
+                for (int l = 0; l < 32; ++l) {
+                    const size_t o = (size_t)ell_base[pb] + (size_t)k * 32 + l;
+                    ent[fbase + (size_t)k * 32 + l] = pack(ell_w[o], g * nac_pad + ell_src[o]);
+                }
+            for (int l = 0; l < 32; ++l) {
+                const int pos = pb * 32 + l, ia = thread_hru[pos], t = wi * 32 + l;
+                const size_t o = (size_t)j * TC + t;
+                const HruStatic *h = ia >= 0 ? &hru[ia] : nullptr;
+                int4 ci;
+                ci.x = (int)(fbase + l) | (K << 20);
+                ci.y = (h ? h->ippt : 0) | ((h ? h->ipet : 0) << 8) | (g << 16) | (h ? 0 : (int)0x80000000u);
+                ci.z = (g * nac_pad + pos) | ((g * nac_pad) << 16);
+                ci.w = ((g * S * npt + (h ? h->ipar : 0)) * 2) | ((g * nac_pad + rank[pos]) << 16);
+                col_i[o] = ci;
+                col_d[2 * o + 0] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);
+                col_d[2 * o + 1] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);
+                col_ia[o] = ia;
+            }
+        }
     if (getenv("DCP_RES_DEBUG"))
-        fprintf(stderr, "[dcp plan2] ell_len %d (nnz %zu), K per block:%s; gather steps per warp: %d %d %d %d\n", Q.ell_len,
+        fprintf(stderr, "[dcp plan2] gather list %zu entries (nnz %zu), K per block:%s; gather steps per warp: %d %d %d %d\n", ent.size(),
                 w.size(), [&] { static std::string s2; s2.clear(); for (int pb = 0; pb < npb; ++pb) s2 += " " + std::to_string(ell_K[pb]); return s2.c_str(); }(),
                 load[0], load[1], load[2], load[3]);
+    Q.ell_len = (int)ent.size();
+    if (Q.ell_len >= (1 << 20)) return;
 
     Q.n_teams = G * nriv;
     Q.team = 32;
@@ -222,7 +243,6 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     size_t off = 0;
     auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
     Q.off_ellw = take((size_t)Q.ell_len * 8);
-    Q.off_ells = take((size_t)Q.ell_len * 2);
     Q.off_coli = take((size_t)H * TC * 16);
     Q.off_cold = take((size_t)H * TC * 32);
     Q.off_rbeg = take((size_t)(nriv + 1) * 4);
@@ -240,7 +260,7 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     std::vector<double> pet_pos(pet);
     for (double &x : pet_pos) x = x > 0.0 ? x : 0.0;
     auto up = [&](auto &vec, auto **dst) { if (e == cudaSuccess) e = upload(vec, dst, c->owned); };
-    up(ell_w, &Q.ell_w); up(ell_src, &Q.ell_src); up(col_i, &Q.col_i); up(col_d, &Q.col_d); up(col_ia, &Q.col_ia);
+    up(ent, &Q.ell_w); up(col_i, &Q.col_i); up(col_d, &Q.col_d); up(col_ia, &Q.col_ia);
     up(rbeg, &Q.rbeg); up(pet_pos, &Q.pet_pos);
     Q.feasible = 1;
 }

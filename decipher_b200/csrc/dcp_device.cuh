@@ -141,16 +141,17 @@ struct ResPlan {
 // ---- resident kernel, second generation (lean arithmetic only; dcp_resident_v2.cu) ------------------
 // Two independent teams per CTA, each running 2 member slots over all 512 HRU columns (4 columns per
 // compute thread).  The HRU->HRU weights are stored in ELLPACK form per block of 32 thread positions
-// (step-major, rows padded with zero weights to the block's longest row rounded up to 4), and every
-// compute thread publishes its HRU's complete contribution to its river's inflow, so the river warps
-// only add up contiguous ranges.
+// (step-major, rows padded with zero weights to the block's longest row rounded up to 4), flattened per
+// compute warp into one gather list (the thread's four columns one after the other, source tuple index
+// packed into the low mantissa bits of the weight), and every compute thread publishes its HRU's
+// complete contribution to its river's inflow, so the river warps only add up contiguous ranges.
 struct Res2Plan {
     int32_t feasible;
     int32_t nac_pad;                // HRUs per member, padded to a power of two in [32, 512]
     int32_t G;                      // member sub-groups side by side in one team (512 / nac_pad)
     int32_t n_groups;               // team groups of G*2 members: ceil(B / (2G)), set per launch
     int32_t Tt;                     // forcing tile (timesteps) per TMA bulk copy
-    int32_t ell_len;                // ELL entries (padded)
+    int32_t ell_len;                // gather-list entries (padded, all four compute warps)
     int32_t team;                   // river lanes per (sub-group, river) sum (power of two <= 32)
     int32_t n_teams;                // number of such sums: G * nriv
     int32_t n_pass;                 // passes of the team's 64 river lanes over the sums
@@ -158,10 +159,10 @@ struct Res2Plan {
     int32_t smem_bytes, team_bytes;
     int32_t off_team;               // start of the team-private region; offsets below off_forc.. are relative to a team's base
     int32_t off_qbf, off_con, off_cst, off_par, off_forc, off_bar;
-    int32_t off_ellw, off_ells, off_coli, off_cold, off_rbeg;      // shared, absolute
-    const double *ell_w;            // [ell_len] w * ac(src)   (dyna_dynamic_dist.f90:50-51), 0 in padding
-    const uint16_t *ell_src;        // [ell_len] source position inside the member sub-group (tuple index)
-    const int4 *col_i;              // [4][128] x: ell base | K << 20;  y: ippt | ipet << 8 | g << 16 | idle << 31;
+    int32_t off_ellw, off_coli, off_cold, off_rbeg;                // shared, absolute
+    const double *ell_w;            // [ell_len] w * ac(src)   (dyna_dynamic_dist.f90:50-51), 0 in padding; the low 9
+                                    //           mantissa bits hold the source's tuple index (0..511)
+    const int4 *col_i;              // [4][128] x: first gather-list entry of the column | K << 20;  y: ippt | ipet << 8 | g << 16 | idle << 31;
                                     //          z: tuple index | sub-group base << 16;  w: par offset | contribution slot << 16
     const double2 *col_d;           // [4][128][2] {ac, 1/ac}, {dtt*w_riv*share*ac, cos(mslp)}
     const int32_t *col_ia;          // [4][128] HRU of the column (-1 idle)

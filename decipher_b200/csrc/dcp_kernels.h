@@ -6,8 +6,8 @@
 #define DCP_RES_S 4                  // member slots per compute thread of the resident kernel
 #define DCP_RES_LG 2                 // member slots interleaved per basic block in the lean step
 #define DCP_RES_LG2 2                // same for the two-columns-per-thread variant
-#ifndef DCP_RES2_LG
-#define DCP_RES2_LG 4                // member slots interleaved per basic block in the second-generation kernel
+#ifndef DCP_RES2_GB
+#define DCP_RES2_GB 1                // gather batch of the second-generation kernel: W rows are padded to a multiple of it
 #endif
 #define DCP_RES_COMPUTE 512
 #define DCP_RES_MAXPAIRS 256         // (members per CTA) x nriv the river warps can carry (4 warps x 4 passes x 16 pairs)

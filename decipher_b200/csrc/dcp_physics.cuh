@@ -27,6 +27,7 @@ struct StepConst {
 
 struct HruState {
     double sd, suz, srz, qint1;
+    double e1;               // lean step with CARRY: exp(sd/m2) carried from the previous step
 };
 
 struct HruFlux {             // outputs of one step
@@ -236,6 +237,12 @@ struct LeanOut {
 #define LEAN_DIV(a, b) ((a) * fm_rcp(b))
 #endif
 
+// CARRY: the solver's new deficit is sd = m2*log(arg) (:76-84), so the next step's exp(sd/m2) IS this step's
+// `arg` (or 1 when the deficit is clipped at zero, :107-112): the exponential is carried in the state instead of
+// being recomputed (one exp and the quotient correction less per step).  The stored sd stays the rounded
+// m2*log(arg), consistent with the carried value to an ulp each step, so nothing drifts; callers re-derive e1
+// with exp() whenever they replace sd (slow path, initial state).
+template <bool CARRY = false>
 __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst &g, double p, double epp,
                                               double qin, HruState &s, LeanOut &o) {
     // root_zone1 (dyna_root_zone1.f90:39-66)
@@ -267,9 +274,13 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     const double a = (u2 * g.dtt) * c.inv_m2;
     // sd/m2 enters an exponential, so its rounding error is amplified by |sd/m2| (up to a few hundred):
     // one Newton correction makes the quotient faithful to the reference's sd/m2
-    double x1 = sd0 * c.inv_m2;
-    x1 = fma(fma(-x1, c.m2, sd0), c.inv_m2, x1);
-    const double e1 = LEAN_EXP(x1);
+    double x1 = 0.0, e1;
+    if (CARRY) e1 = s.e1;
+    else {
+        x1 = sd0 * c.inv_m2;
+        x1 = fma(fma(-x1, c.m2, sd0), c.inv_m2, x1);
+        e1 = LEAN_EXP(x1);
+    }
     const double r = LEAN_DIV(c.q1, u2);
     const double e2 = LEAN_EXP(-a);
     const double b = (c.q1 * g.dtt) * c.inv_m2;
@@ -279,6 +290,7 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     double sd = c.m2 * LEAN_LOG(arg);
     o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !(arg > 1e-290 && arg < 1e290);
     double qbf = (sd - sd0) * g.inv_dtt + uz + qin_ac;            // :98
+    if (CARRY) s.e1 = fm_sel_lt(sd, 0.0, 1.0, arg);               // exp(max(sd, 0)/m2)
     double exs = fm_relu(-sd);                                    // :107-112
     sd = fm_relu(sd);
     const double over = fm_relu(qbf - c.q0);                      // :115-119

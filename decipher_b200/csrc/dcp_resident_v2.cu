@@ -15,12 +15,17 @@
 //     columns (4 columns per thread).  Members never interact, so the teams drift out of phase and one
 //     team's gather (shared-memory bound) overlaps the other's physics (FP64 bound).  Only the weight
 //     matrix and the per-column tables are shared (read-only).
-//   * gather = ELLPACK SpMM.  W is stored per block of 32 thread positions, step-major, rows padded with
-//     zero weights to the block's longest row; the trip count is warp-uniform and the loop is unrolled
-//     by four with all weight/index loads of a batch issued before the first tuple load.  A tuple is the
-//     16 bytes of the team's two member slots, so one LDS.128 per source and eight bank classes; the
-//     host orders the entries of each row so that the eight lanes of a quarter-warp hit different
-//     classes wherever the catchment allows (conflict-aware ELL schedule, dcp_api.cu).
+//   * gather = ELLPACK SpMM over one flat list per thread.  W is stored per block of 32 thread positions,
+//     step-major, rows padded with zero weights to the block's longest row; the four columns of a thread follow
+//     one another in the list, so the trip counts are warp-uniform and the list is walked with a one-entry
+//     look-ahead (the first entry of the next step is requested before the barrier).  An entry is ONE 8-byte
+//     word: the weight with the source's tuple index in its nine lowest mantissa bits (|dw/w| <= 2^-44), i.e.
+//     one LDS.64 per entry and no index array.  A tuple is the 16 bytes of the team's two member slots, so one
+//     LDS.128 per source and eight bank classes; the host orders the entries of each row so that the eight
+//     lanes of a quarter-warp hit different classes wherever the catchment allows (dcp_api.cu).
+//     Measured (profiles/r1_ncu_resident_v2*.txt): the gather is ~28 % of a compute warp's time for ~14 % of
+//     its instructions (LDS latency + MIO queue), the reason the FP64 pipe sits near 40 %.
+//   * exp(sd/m2) is carried in the state instead of being recomputed (hru_step_lean<true>, dcp_physics.cuh).
 //   * river sums by contribution.  Every compute thread publishes, per member slot,
 //         c = (dtt*w_riv*share*ac) * qbf_old + (exs+exus)*ac          (dyna_dynamic_dist.f90:59-61,
 //                                                                      dyna_results_ac.f90:35-38)
@@ -48,10 +53,17 @@
 #define R2_TT (R2_TC + R2_TR)         // threads at a team barrier
 #define R2_CT (R2_TEAMS * R2_TC)      // 256 compute threads
 #define R2_THREADS (R2_TEAMS * R2_TT) // 384
-#define R2_REG_COMPUTE 232            // launch cap 168: (168-40)*128 == (232-168)*256
-#define R2_REG_RIVER 40
+#ifndef R2_REG_COMPUTE
+#define R2_REG_COMPUTE 240            // launch cap 168: (168-24)*128 == (240-168)*256
+#endif
+#ifndef R2_REG_RIVER
+#define R2_REG_RIVER 24
+#endif
 #define R2_S 2                        // member slots per team
 #define R2_H 4                        // columns per compute thread
+#ifndef R2_CARRY_E1
+#define R2_CARRY_E1 1                 // carry exp(sd/m2) from step to step instead of recomputing it (dcp_physics.cuh)
+#endif
 
 struct R2Smem {                       // team-private views unless noted
     double2 *qbf_s;       // [2][512]        baseflow tuples (2 member slots), double buffered in time
@@ -61,8 +73,7 @@ struct R2Smem {                       // team-private views unless noted
     double *forc_s;       // [2][Tt*(ngp+nge)]
     uint64_t *bars;       // [2]
     // shared by both teams (read-only after setup)
-    double *ellw_s;       // [ell_len]
-    uint16_t *ells_s;     // [ell_len]
+    double *ellw_s;       // [ell_len]       packed gather list (weight | source tuple index)
     int4 *coli_s;         // [4][128]        per (column slot j, team thread): packed indices
     double2 *cold_s;      // [4][128][2]     {ac, 1/ac}, {cq, cos(mslp)}
     int32_t *rbeg_s;      // [nriv+1]
@@ -93,6 +104,9 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 
         // ---- load the group's initial state (written by k_init_members) ----
         double sd[H][S], suz[H][S], srz[H][S], aet[H][S];
+#if R2_CARRY_E1
+        double e1s[H][S];
+#endif
 #pragma unroll
         for (int j = 0; j < H; ++j) {
             const int4 ci = M.coli_s[j * R2_TC + tt_id];
@@ -114,6 +128,9 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                     c_im2 = cosm / szm;
                     qb0 = W.qbf0[o];
                 }
+#if R2_CARRY_E1
+                e1s[j][k] = exp(sd[j][k] * c_im2);           // carried exp(sd/m2), see hru_step_lean<true>
+#endif
                 reinterpret_cast<double *>(M.qbf_s + tup)[k] = qb0;                 // time buffer 0 = step 0's "old" qbf
                 reinterpret_cast<double *>(M.qbf_s + R2_COLS + tup)[k] = 0.0;
                 M.cst_s[(k * 2 + 0) * R2_COLS + tup] = make_double2(c_q0, c_q2);
@@ -134,6 +151,14 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
         }
         team_sync(team);
 
+        // first batch of the thread's gather list (time-invariant; re-issued before every barrier so that its
+        // latency is hidden behind the wait)
+        const double *ent0 = M.ellw_s + (M.coli_s[tt_id].x & 0xfffff);
+        constexpr int GB = DCP_RES2_GB;                      // gather batch (entries in flight per tuple round)
+        double wv[GB];
+#pragma unroll
+        for (int u = 0; u < GB; ++u) wv[u] = ent0[u * 32];
+
         int t = 0;
         for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
             const uint32_t b = tiles_done & 1;
@@ -145,29 +170,34 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                 const double2 *qbf_cur = M.qbf_s + (t & 1) * R2_COLS;
                 double2 *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * R2_COLS;
                 double2 *con = M.con_s + (t & 1) * R2_COLS;
+                // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52): the thread's four columns form one flat list
+                // (two columns are gathered ahead of each physics block); the next batch's entries are in flight while
+                // this batch's tuples are fetched ----
+                const double *ep = ent0;
 #pragma unroll
                 for (int jp = 0; jp < H; jp += 2) {          // two columns = four (HRU, member) units per basic block
-                    int4 ci[2];
-                    double qin[2][S];
-                    // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52): ELL rows, 4 entries per batch ----
+                    int4 ci[H];
+                    double qin[H][S];
 #pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        ci[jj] = M.coli_s[(jp + jj) * R2_TC + tt_id];
-                        const int ebase = ci[jj].x & 0xfffff, eK = ci[jj].x >> 20;
-                        const double2 *qg = qbf_cur + (int)((uint32_t)ci[jj].z >> 16);  // tuple base of the member sub-group
-                        const double *wp = M.ellw_s + ebase;
-                        const uint16_t *sp = M.ells_s + ebase;
+                    for (int j = jp; j < jp + 2; ++j) {
+                        ci[j] = M.coli_s[j * R2_TC + tt_id];
+#ifdef R2_TUNE_NO_GATHER                                                                // timing experiment only (wrong results)
+                        const int nb = 0;
+#else
+                        const int nb = (ci[j].x >> 20) / GB;                            // K / batch, warp-uniform
+#endif
                         double q0 = 0.0, q1 = 0.0;
-                        for (int e = 0; e < eK; e += 4) {
-                            double w[4]; int so[4]; double2 qv[4];
+                        for (int bb = 0; bb < nb; ++bb) {
+                            double wc[GB]; double2 qv[GB];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) { w[u] = wp[(e + u) * 32]; so[u] = sp[(e + u) * 32]; }
+                            for (int u = 0; u < GB; ++u) { wc[u] = wv[u]; qv[u] = qbf_cur[__double2loint(wc[u]) & 511]; }
+                            ep += GB * 32;
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) qv[u] = qg[so[u]];
+                            for (int u = 0; u < GB; ++u) wv[u] = ep[u * 32];
 #pragma unroll
-                            for (int u = 0; u < 4; ++u) { q0 = fma(qv[u].x, w[u], q0); q1 = fma(qv[u].y, w[u], q1); }
+                            for (int u = 0; u < GB; ++u) { q0 = fma(qv[u].x, wc[u], q0); q1 = fma(qv[u].y, wc[u], q1); }
                         }
-                        qin[jj][0] = q0; qin[jj][1] = q1;
+                        qin[j][0] = q0; qin[j][1] = q1;
                     }
                     // ---- root zone, unsaturated zone, saturated zone: 4 interleaved dependency chains ----
                     LeanOut lo[2][S];
@@ -176,18 +206,18 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const int j = jp + jj;
-                        const int tup = ci[jj].z & 0xffff;
+                        const int tup = ci[j].z & 0xffff;
                         const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];      // {ac, 1/ac}
                         const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];      // {cq, cos}
                         cq[jj] = d1.x;
-                        const double p = forc_t[tt * C.ngp + (ci[jj].y & 0xff)];
-                        const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci[jj].y >> 8) & 0xff)];   // already max(ep, 0)
+                        const double p = forc_t[tt * C.ngp + (ci[j].y & 0xff)];
+                        const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci[j].y >> 8) & 0xff)];   // already max(ep, 0)
 #pragma unroll
                         for (int k = 0; k < S; ++k) {
                             const double2 c0v = M.cst_s[(k * 2 + 0) * R2_COLS + tup];
                             const double2 c1v = M.cst_s[(k * 2 + 1) * R2_COLS + tup];
-                            const double2 p0 = M.par_s[(ci[jj].w & 0xffff) + k * par_kstride];
-                            const double2 p1 = M.par_s[(ci[jj].w & 0xffff) + k * par_kstride + 1];
+                            const double2 p0 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride];
+                            const double2 p1 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 1];
                             HruConst c;
                             c.ac = d0.x; c.inv_ac = d0.y;
                             c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = c1v.x; c.inv_m2 = c1v.y;
@@ -196,8 +226,14 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                             c.ims_rz = 1; c.ims_uz = 1;
                             HruState st;
                             st.sd = sd[j][k]; st.suz = suz[j][k]; st.srz = srz[j][k]; st.qint1 = 0.0;
-                            hru_step_lean(c, gc, p, epp, qin[jj][k], st, lo[jj][k]);
+#if R2_CARRY_E1
+                            st.e1 = e1s[j][k];
+#endif
+                            hru_step_lean<R2_CARRY_E1 != 0>(c, gc, p, epp, qin[j][k], st, lo[jj][k]);
                             sd[j][k] = st.sd; suz[j][k] = st.suz; srz[j][k] = st.srz;  // ntt == 1: qint1 is not carried
+#if R2_CARRY_E1
+                            e1s[j][k] = st.e1;
+#endif
                             any_slow |= lo[jj][k].slow;
                         }
                     }
@@ -208,7 +244,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                             for (int k = 0; k < S; ++k)
                                 if (lo[jj][k].slow) {
                                     const int j = jp + jj;
-                                    const int tup = ci[jj].z & 0xffff;
+                                    const int tup = ci[j].z & 0xffff;
                                     const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];
                                     const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];
                                     const double2 c0v = M.cst_s[(k * 2 + 0) * R2_COLS + tup];
@@ -217,15 +253,18 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                                     c.ac = d0.x; c.inv_ac = d0.y;
                                     c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = c1v.x; c.inv_m2 = c1v.y;
                                     c.q1 = c.q0 * d1.y;
-                                    c.smax = M.par_s[(ci[jj].w & 0xffff) + k * par_kstride + 1].y;
-                                    hru_step_lean_fixup(c, gc, qin[jj][k], qin[jj][k], sd[j][k], lo[jj][k]);
+                                    c.smax = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 1].y;
+                                    hru_step_lean_fixup(c, gc, qin[j][k], qin[j][k], sd[j][k], lo[jj][k]);
+#if R2_CARRY_E1
+                                    e1s[j][k] = exp(sd[j][k] * c.inv_m2);               // re-derive the carried exponential
+#endif
                                 }
                     }
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const int j = jp + jj;
-                        if (ci[jj].y >= 0) {                                            // live column (bit 31 of .y marks idle ones)
-                            const int tup = ci[jj].z & 0xffff, ctup = (int)((uint32_t)ci[jj].w >> 16);
+                        if (ci[j].y >= 0) {                                             // live column (bit 31 of .y marks idle ones)
+                            const int tup = ci[j].z & 0xffff, ctup = (int)((uint32_t)ci[j].w >> 16);
                             const double2 qold = qbf_cur[tup];                          // this HRU's baseflow at the start of the step
                             qbf_nxt[tup] = make_double2(lo[jj][0].qbf, lo[jj][1].qbf);
                             con[ctup] = make_double2(fma(cq[jj], qold.x, lo[jj][0].exac), fma(cq[jj], qold.y, lo[jj][1].exac));
@@ -236,6 +275,8 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                         }
                     }
                 }
+#pragma unroll
+                for (int u = 0; u < GB; ++u) wv[u] = ent0[u * 32];                     // next step's first gather batch
                 if (P.dbg) busy += clock64() - c0;
                 team_sync(team);
             }
@@ -351,12 +392,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     M.forc_s = (double *)(tb + P.off_forc);
     M.bars = (uint64_t *)(tb + P.off_bar);
     M.ellw_s = (double *)(smem + P.off_ellw);
-    M.ells_s = (uint16_t *)(smem + P.off_ells);
     M.coli_s = (int4 *)(smem + P.off_coli);
     M.cold_s = (double2 *)(smem + P.off_cold);
     M.rbeg_s = (int32_t *)(smem + P.off_rbeg);
 
-    for (int e = tid; e < P.ell_len; e += R2_THREADS) { M.ellw_s[e] = P.ell_w[e]; M.ells_s[e] = P.ell_src[e]; }
+    for (int e = tid; e < P.ell_len; e += R2_THREADS) M.ellw_s[e] = P.ell_w[e];
     for (int i = tid; i < R2_H * R2_TC; i += R2_THREADS) {
         M.coli_s[i] = P.col_i[i];
         M.cold_s[2 * i] = P.col_d[2 * i]; M.cold_s[2 * i + 1] = P.col_d[2 * i + 1];
