@@ -33,7 +33,7 @@ ST_HIST_DROPPED = 0x80
 OPT_CHECK_BALANCE = 0x1
 OPT_DEVICE_BUFFERS = 0x2
 OPT_FAST_MATH = 0x4
-KERNEL_AUTO, KERNEL_STREAMED, KERNEL_RESIDENT = 0, 1, 2
+KERNEL_AUTO, KERNEL_STREAMED, KERNEL_RESIDENT, KERNEL_STEPWISE = 0, 1, 2, 3
 NMEASURE = 2
 
 

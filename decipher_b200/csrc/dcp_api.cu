@@ -79,6 +79,7 @@ struct dcp_catchment {
     bool has_qobs = false;
     ResPlan plan{};                     // resident-kernel plan (plan.feasible == 0: streamed kernel only)
     Res2Plan plan2{};                   // second-generation resident kernel (lean arithmetic, own-river catchments)
+    DensePlan dplan{};                  // stepwise path: ordered river lists, dense W when it pays
     int n_sm = 148;
     size_t smem_optin = 0;
     std::string plan_why;               // why the resident kernel is not available
@@ -553,6 +554,55 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
             }
         }
     }
+    // ---------------- stepwise plan: ordered river lists, dense form of W when it is dense enough ----------------
+    {
+        DensePlan &D = c->dplan;
+        D = DensePlan{};
+        std::vector<int32_t> rq_beg(nriv + 1, 0), rq_idx, ro_beg(nriv + 1, 0), ro_idx;
+        for (int r = 0; r < nriv; ++r) {
+            for (int ia = 0; ia < nac; ++ia) {
+                for (int x = hru[ia].riv_beg; x < hru[ia].riv_end; ++x) if (riv[x].r == r) rq_idx.push_back(x);
+                if (hru[ia].ipriv == r) ro_idx.push_back(ia);
+            }
+            rq_beg[r + 1] = (int)rq_idx.size(); ro_beg[r + 1] = (int)ro_idx.size();
+        }
+        if (rq_idx.empty()) rq_idx.push_back(0);
+        if (ro_idx.empty()) ro_idx.push_back(0);
+        D.nq = (int)riv.size();
+        up(rq_beg, &D.rq_beg); up(rq_idx, &D.rq_idx); up(ro_beg, &D.ro_beg); up(ro_idx, &D.ro_idx);
+        const double density = (double)w.size() / ((double)nac * nac);
+        const double min_density = getenv("DCP_DENSE_MIN_DENSITY") ? atof(getenv("DCP_DENSE_MIN_DENSITY")) : 0.05;
+        D.Mp = (nac + 127) / 128 * 128; D.Kp = (nac + 15) / 16 * 16;
+        const size_t dense_bytes = (size_t)D.Mp * D.Kp * 8;
+        if (density >= min_density && nac >= 128 && dense_bytes <= ((size_t)2 << 30)) {
+            std::vector<double> wd((size_t)D.Mp * D.Kp, 0.0), acs(D.Kp, 0.0);
+            bool dup = false;
+            for (int ia = 0; ia < nac; ++ia) {
+                acs[ia] = hru[ia].ac;
+                for (int x = hru[ia].row_beg; x < hru[ia].row_end; ++x) {
+                    double &cell = wd[(size_t)ia * D.Kp + w[x].src];
+                    if (cell != 0.0) dup = true;                  // two links between the same pair: keep the sparse form
+                    cell = w[x].w;
+                }
+            }
+            std::vector<int32_t> kt_beg(D.Mp / 128 + 1, 0), kt_idx;
+            for (int bm = 0; bm < D.Mp / 128; ++bm) {
+                for (int kt = 0; kt < D.Kp / 16; ++kt) {
+                    bool any = false;
+                    for (int r = bm * 128; r < bm * 128 + 128 && !any; ++r)
+                        for (int k = kt * 16; k < kt * 16 + 16; ++k) if (wd[(size_t)r * D.Kp + k] != 0.0) { any = true; break; }
+                    if (any) kt_idx.push_back(kt);
+                }
+                kt_beg[bm + 1] = (int)kt_idx.size();
+            }
+            if (kt_idx.empty()) kt_idx.push_back(0);
+            if (!dup) {
+                up(wd, &D.wd); up(acs, &D.acs); up(kt_beg, &D.kt_beg); up(kt_idx, &D.kt_idx);
+                D.dense = 1;
+            }
+        }
+        D.feasible = 1;
+    }
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) {
         const int code = fail(e == cudaErrorMemoryAllocation ? DCP_ERR_NOMEM : DCP_ERR_CUDA, "catchment upload failed: %s",
@@ -586,7 +636,7 @@ struct Carver {                     // carves a slab into aligned arrays
 };
 
 // lays the batch workspace out (base == nullptr: size query only)
-size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, bool aet) {
+size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, bool aet, int stepwise_nq = -1) {
     Carver cv(base);
     const size_t B = W.B, nac = C.nac;
     W.par = cv.take<double>(7 * C.npt * B);
@@ -614,6 +664,11 @@ size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, b
     W.bad = cv.take<int32_t>(C.nriv * B);
     W.status = cv.take<int32_t>(B);
     W.diag = cv.take<double>(3 * B);
+    if (stepwise_nq >= 0) {
+        W.qin_ext = cv.take<double>(nac * B); W.qof_term = cv.take<double>(nac * B);
+        W.qb_term = cv.take<double>((size_t)std::max(stepwise_nq, 1) * B);
+        W.bad_src = cv.take<int32_t>(B);
+    } else { W.qin_ext = W.qof_term = W.qb_term = nullptr; W.bad_src = nullptr; }
     return cv.off + 256;
 }
 
@@ -664,13 +719,18 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     const bool want_perf = perf_out != nullptr;
     // kernel choice: the resident kernel whenever the catchment fits on chip; the balance checks
     // (results_ts / root_zone1 STOP conditions) exist in the streamed kernel only
-    bool use_res = false;
+    bool use_res = false, use_sw = false;
     if (o.kernel == DCP_KERNEL_RESIDENT) {
         if (!c->plan.feasible) return fail(DCP_ERR_UNSUPPORTED, "resident kernel unavailable: %s", c->plan_why.c_str());
         if (check) return fail(DCP_ERR_UNSUPPORTED, "DCP_OPT_CHECK_BALANCE needs the streamed kernel");
         use_res = true;
     } else if (o.kernel == DCP_KERNEL_AUTO) {
         use_res = c->plan.feasible && !check;
+        use_sw = !use_res && !check && c->dplan.feasible;      // catchments too large for the chip: one launch set per step
+    } else if (o.kernel == DCP_KERNEL_STEPWISE) {
+        if (!c->dplan.feasible) return fail(DCP_ERR_UNSUPPORTED, "stepwise kernels unavailable for this catchment");
+        if (check) return fail(DCP_ERR_UNSUPPORTED, "DCP_OPT_CHECK_BALANCE needs the streamed kernel");
+        use_sw = true;
     } else if (o.kernel != DCP_KERNEL_STREAMED) {
         return fail(DCP_ERR_INVALID, "unknown kernel selector %d", o.kernel);
     }
@@ -689,7 +749,9 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     Bmax = std::min<int64_t>(Bmax, n_member);
 
     c->stats = dcp_run_stats{};
-    c->stats.kernel_used = use_res ? DCP_KERNEL_RESIDENT : DCP_KERNEL_STREAMED;
+    c->stats.kernel_used = use_res ? DCP_KERNEL_RESIDENT : use_sw ? DCP_KERNEL_STEPWISE : DCP_KERNEL_STREAMED;
+    const int sw_nq = use_sw ? c->dplan.nq : -1;
+    const bool sw_dense = use_sw && c->dplan.dense && !getenv("DCP_STEPWISE_NO_GEMM");
     EventTimer tm(s);
     int64_t n_launch = 0, n_phys = 0;
     int hist_len_max = 0;
@@ -719,7 +781,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         // ---- first guess of the batch size: everything except the (still unknown) histogram length ----
         for (;;) {
             DevBatch Wq{}; Wq.B = (int)Bn; Wq.Lcap = 1; Wq.R = use_res ? C.nstep : tile + 64;
-            const size_t fixed = carve_batch(nullptr, C, Wq, check, aet) + io_size(Bn);
+            const size_t fixed = carve_batch(nullptr, C, Wq, check, aet, sw_nq) + io_size(Bn);
             if ((double)fixed < 0.9 * mem_budget || Bn <= 1) break;
             Bn = shrink(Bn);
         }
@@ -775,7 +837,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             while (R < tile + Tcap + 1) R <<= 1;
             W.R = R; W.Rmask = R - 1;
         }
-        const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet);
+        const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet, sw_nq);
         if ((double)(ws_bytes + io_bytes) > mem_budget) {
             if (Bn <= 1) return fail(DCP_ERR_NOMEM, "one member needs %zu MB, device has %zu MB free",
                                      (ws_bytes + io_bytes) >> 20, free_b >> 20);
@@ -783,7 +845,8 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             continue;
         }
         CUDA_TRY(c->ws.reserve(ws_bytes));
-        carve_batch(c->ws.p, C, W, check, aet);
+        carve_batch(c->ws.p, C, W, check, aet, sw_nq);
+        if (use_sw) CUDA_TRY(cudaMemsetAsync(W.bad_src, 0, (size_t)Bn * 4, s));
 
         tm.mark(T_INIT);
         dcp_launch_init(C, W, d_mcpar, check, s); ++n_launch;
@@ -823,7 +886,10 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             for (int t0 = 0; t0 < C.nstep; t0 += tile) {
                 const int t1 = std::min(C.nstep, t0 + tile);
                 tm.mark(T_PHYS);
-                dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s); ++n_launch; ++n_phys;
+                if (use_sw) {
+                    CUDA_TRY(dcp_launch_physics_stepwise(C, W, c->dplan, t0, t1, fast, aet, sw_dense, c->n_sm, s));
+                    n_launch += (int64_t)(t1 - t0) * (sw_dense ? 4 : 3); n_phys += t1 - t0;
+                } else { dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s); ++n_launch; ++n_phys; }
                 tm.mark(T_ROUTE);
                 dcp_launch_route(C, W, t0, t1, d_q, s); n_launch += C.qobs ? 3 : 2;
             }

@@ -105,6 +105,25 @@ struct DevBatch {
     // per member
     int32_t *status;                // [B]
     double *diag;                   // [3][B]
+    // stepwise path (dcp_stepwise.cu), null otherwise
+    double *qin_ext;                // [nac][B]  redistributed inflow of the current step
+    double *qb_term;                // [nq][B]   per river entry: (((dtt*qbf)*w_riv)*rivers)*ac of the current step
+    double *qof_term;               // [nac][B]  (exs+exus)*ac of the current step (0 when not positive)
+    int32_t *bad_src;               // [B]       member holds a non-finite baseflow (dense redistribute only)
+};
+
+// ---- stepwise path: plan of the redistribute step and of the ordered river sums -------------------
+struct DensePlan {
+    int32_t feasible;
+    int32_t dense;                  // 1: W is dense enough for the GEMM form (wd/kt_* valid)
+    int32_t Mp, Kp;                 // nac padded to the GEMM tile (128 destinations, 16 sources)
+    int32_t nq;                     // non-zero entries of rivers(:, :)
+    const double *wd;               // [Mp][Kp] wtrans in destination-major dense form (0 where no link)
+    const double *acs;              // [Kp]     ac(src)
+    const int32_t *kt_beg;          // [Mp/128 + 1] per destination block: range in kt_idx
+    const int32_t *kt_idx;          // source tiles (16 wide) holding at least one non-zero of the block
+    const int32_t *rq_beg, *rq_idx; // [nriv+1], river entries (index into DevCatchment::riv) per river, ascending HRU
+    const int32_t *ro_beg, *ro_idx; // [nriv+1], HRUs with ipriv == r, ascending
 };
 
 // ---- resident (persistent, on-chip state) kernel ------------------------------------------------

@@ -67,6 +67,9 @@ extern "C" {
 #define DCP_KERNEL_AUTO      0
 #define DCP_KERNEL_STREAMED  1          /* state streamed through L2/HBM, any nac                     */
 #define DCP_KERNEL_RESIDENT  2          /* persistent kernel, state on chip for the whole simulation  */
+#define DCP_KERNEL_STEPWISE  3          /* one timestep = redistribute (CSR SpMM, or an FP64 GEMM when the
+                                           dynamic_dist matrix is dense) + physics over (HRU, member) +
+                                           ordered river sums; any nac, no balance checks              */
 
 /* number of performance measures per (gauge, member): 1 = NSE, 2 = log-NSE */
 #define DCP_NMEASURE 2
@@ -150,7 +153,7 @@ typedef struct dcp_run_stats {
     double ms_d2h;              /* device->host copies inside the call                                */
     int64_t n_physics_launches;
     int64_t n_launches;         /* all kernels launched by the call                                   */
-    int32_t kernel_used;        /* DCP_KERNEL_STREAMED or DCP_KERNEL_RESIDENT                         */
+    int32_t kernel_used;        /* DCP_KERNEL_STREAMED, _RESIDENT or _STEPWISE                        */
     int32_t hist_len;           /* T of route_processing_build_hist for the slowest member            */
 } dcp_run_stats;
 

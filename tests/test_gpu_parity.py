@@ -136,13 +136,17 @@ def test_resident_matches_streamed_bitwise_in_exact_mode():
     assert np.array_equal(a["status"], b["status"])
 
 
-def test_wide_w_large_catchment_goes_streamed():
+def test_wide_w_large_catchment_leaves_the_chip():
     """Config-4-like: more HRUs than the resident kernel holds (nac = 700 > 512) and a wide weighting
-    matrix (64 targets per HRU): AUTO must pick the streamed kernel and stay within tolerance."""
+    matrix (64 targets per HRU): AUTO must pick the stepwise path (the streamed kernel when the balance
+    checks are requested) and stay within tolerance."""
     cat = synth.synth_catchment(nac=700, nriv=5, npt=1, ngp=4, nge=1, nstep=500, kW=64, seed=synth.BASE_SEED + 4, tree=True)
     ref, out = _run_both(cat, 48, kernel=0)
-    assert out["stats"]["kernel_used"] == KERNEL_STREAMED
+    assert out["stats"]["kernel_used"] == 3
     print("C4-like:", _check(ref, out))
+    ref, out = _run_both(cat, 48, flags=OPT_CHECK_BALANCE, kernel=0)
+    assert out["stats"]["kernel_used"] == KERNEL_STREAMED
+    print("C4-like checked:", _check(ref, out))
 
 
 def test_multi_catchment_partition():
@@ -158,3 +162,68 @@ def test_multi_catchment_partition():
         ref = oracle_run(c, mcs[i].copy(order="F"))
         compare_flows(got[i]["q"], ref["q"])
         compare_perf(got[i]["perf"], ref["perf"])
+
+
+# ---------------------------------------------------------------------------------------------
+# stepwise path (catchments too large for the chip; dense dynamic_dist matrix as an FP64 GEMM)
+# ---------------------------------------------------------------------------------------------
+from decipher_b200.capi import KERNEL_STEPWISE  # noqa: E402
+
+
+def _bitwise(a, b):
+    for k in ("q", "perf", "reach_totals"):
+        assert np.array_equal(a[k], b[k], equal_nan=True), k
+    assert np.array_equal(a["status"], b["status"])
+
+
+@pytest.mark.parametrize("min_density", ["2.0", "0.0"], ids=["csr", "gemm"])
+def test_stepwise_exact_is_bitwise_streamed(min_density, monkeypatch):
+    """EXACT mode: redistribute (sparse CSR, or the dense GEMM with one ascending accumulation chain per output),
+    physics over (HRU, member) and ordered river sums perform the reference's operations in the reference's order,
+    so the result must equal the streamed kernel's bit for bit.  nac = 300 is not a multiple of the GEMM tile,
+    M = 37 is odd (ragged member tile), several time tiles."""
+    monkeypatch.setenv("DCP_DENSE_MIN_DENSITY", min_density)
+    cat = synth.synth_catchment(nac=300, nriv=4, npt=2, ngp=3, nge=2, nstep=400, kW=40, seed=synth.BASE_SEED + 41, tree=True)
+    mc = synth.sample_parameters(cat.npt, 37)
+    dev = DeviceCatchment(cat)
+    a = dev.run(mc.copy(order="F"), kernel=KERNEL_STREAMED, want_q=True, want_totals=True, steps_per_tile=150)
+    b = dev.run(mc.copy(order="F"), kernel=KERNEL_STEPWISE, want_q=True, want_totals=True, steps_per_tile=150)
+    dev.close()
+    assert b["stats"]["kernel_used"] == KERNEL_STEPWISE
+    _bitwise(a, b)
+
+
+def test_stepwise_dense_fast_vs_oracle(monkeypatch):
+    """Config-4-like dense weighting matrix (every HRU drains to every down-slope HRU), FAST arithmetic
+    (one FMA per term, hoisted reciprocals): within the 1e-9 contract of the oracle; AUTO picks the stepwise
+    path for a catchment larger than the resident kernel holds."""
+    monkeypatch.setenv("DCP_DENSE_MIN_DENSITY", "0.05")
+    cat = synth.synth_catchment(nac=600, nriv=5, npt=1, ngp=4, nge=1, nstep=300, kW=600, seed=synth.BASE_SEED + 42, tree=True)
+    ref, out = _run_both(cat, 40, flags=OPT_FAST_MATH, kernel=0)
+    assert out["stats"]["kernel_used"] == KERNEL_STEPWISE
+    print("C4-dense fast:", _check(ref, out))
+    ref, out = _run_both(cat, 40, kernel=KERNEL_STEPWISE)
+    print("C4-dense exact:", _check(ref, out))
+
+
+def test_stepwise_nonfinite_members_match_streamed(monkeypatch):
+    """Non-finite baseflows must reach exactly the HRUs the reference's sparse scatter reaches (0 * inf would
+    poison every destination in a plain GEMM): the dense redistribute stages zeros, flags the member and the
+    flagged members are redone in sparse form.  Two triggers: szm = 0 for two members (NaN from the first step,
+    the other members stay finite), and an infinite rainfall depth on one rain grid at step 100 (every member)."""
+    monkeypatch.setenv("DCP_DENSE_MIN_DENSITY", "0.0")
+    cat = synth.synth_catchment(nac=200, nriv=4, npt=1, ngp=2, nge=1, nstep=300, kW=30, seed=synth.BASE_SEED + 43, tree=True)
+    mc = synth.sample_parameters(1, 40)
+    mc[0, 0, 3] = 0.0
+    mc[0, 0, 21] = 0.0
+    for inf_rain in (False, True):
+        if inf_rain:
+            cat.rain[1, 100] = np.inf
+        dev = DeviceCatchment(cat)
+        a = dev.run(mc.copy(order="F"), kernel=KERNEL_STREAMED, want_q=True, want_totals=True)
+        b = dev.run(mc.copy(order="F"), kernel=KERNEL_STEPWISE, want_q=True, want_totals=True)
+        dev.close()
+        bad = (~np.isfinite(a["q"])).any(axis=(0, 1))
+        print("non-finite members:", int(bad.sum()), "of 40")
+        assert bad[3] and bad[21] and (inf_rain or bad.sum() == 2)
+        _bitwise(a, b)
