@@ -596,7 +596,13 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
                 kt_beg[bm + 1] = (int)kt_idx.size();
             }
             if (kt_idx.empty()) kt_idx.push_back(0);
+            // destination blocks longest-first, so that the blocks with few source tiles fill the tail of the grid
+            std::vector<int32_t> bm_order(D.Mp / 128);
+            for (int i = 0; i < D.Mp / 128; ++i) bm_order[i] = i;
+            std::stable_sort(bm_order.begin(), bm_order.end(), [&](int a, int b) {
+                return kt_beg[a + 1] - kt_beg[a] > kt_beg[b + 1] - kt_beg[b]; });
             if (!dup) {
+                up(bm_order, &D.bm_order);
                 up(wd, &D.wd); up(acs, &D.acs); up(kt_beg, &D.kt_beg); up(kt_idx, &D.kt_idx);
                 D.dense = 1;
             }

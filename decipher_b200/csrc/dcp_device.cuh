@@ -122,6 +122,7 @@ struct DensePlan {
     const double *acs;              // [Kp]     ac(src)
     const int32_t *kt_beg;          // [Mp/128 + 1] per destination block: range in kt_idx
     const int32_t *kt_idx;          // source tiles (16 wide) holding at least one non-zero of the block
+    const int32_t *bm_order;        // [Mp/128] destination blocks by decreasing number of source tiles (launch order)
     const int32_t *rq_beg, *rq_idx; // [nriv+1], river entries (index into DevCatchment::riv) per river, ascending HRU
     const int32_t *ro_beg, *ro_idx; // [nriv+1], HRUs with ipriv == r, ascending
 };

@@ -71,26 +71,29 @@ k_redistribute_dense(DensePlan D, const double *__restrict__ Bm, double *__restr
     double *Bs = gsm + 2 * GM_BK * GM_BM;                 // [2][BK][BN]
     double *Cs = Bs + 2 * GM_BK * GM_BN;                  // [2][BK]       ac(src) (EXACT)
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    const int n0 = blockIdx.x * GM_BN, bm = blockIdx.y, m0 = bm * GM_BM;
+    const int n0 = blockIdx.x * GM_BN, bm = D.bm_order[blockIdx.y], m0 = bm * GM_BM;
     const int kt_b = D.kt_beg[bm], kt_e = D.kt_beg[bm + 1];
 
     // global -> register staging: A: row tid/2, k half (tid&1)*8;  B: k row tid/16, members (tid&15)*8
     const int a_r = tid >> 1, a_k = (tid & 1) * 8;
     const int b_k = tid >> 4, b_n = (tid & 15) * 8;
-    double ra[8], rb[8], rc = 0.0;
+    double ra[8], rb[8], rc = 0.0, rsc = 0.0;
+    // gload only ISSUES the global loads (the values are first touched in sstore, after the math of the current
+    // tile), so their latency hides behind 1024 DFMAs per thread
     auto gload = [&](int kt) {
         const int k0 = D.kt_idx[kt] * GM_BK;
         const double2 *ap = reinterpret_cast<const double2 *>(D.wd + (size_t)(m0 + a_r) * D.Kp + k0 + a_k);
 #pragma unroll
         for (int i = 0; i < 4; ++i) { const double2 v = __ldg(ap + i); ra[2 * i] = v.x; ra[2 * i + 1] = v.y; }
         const int k = k0 + b_k;
-        const double sc = (k < nac) ? D.acs[k] : 0.0;
+        rsc = (k < nac) ? D.acs[k] : 0.0;
         const double *bp = Bm + (size_t)k * B + n0 + b_n;
+        if (k < nac && n0 + b_n + 8 <= B && (B & 1) == 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            double v = (k < nac && n0 + b_n + i < B) ? bp[i] : 0.0;
-            if (!is_finite_bits(v)) { bad[n0 + b_n + i] = 1; v = 0.0; }
-            rb[i] = EXACT ? v : v * sc;                   // FAST: ac(src) folded into the staged tile
+            for (int i = 0; i < 4; ++i) { const double2 v = reinterpret_cast<const double2 *>(bp)[i]; rb[2 * i] = v.x; rb[2 * i + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rb[i] = (k < nac && n0 + b_n + i < B) ? bp[i] : 0.0;
         }
         if (tid < GM_BK) { const int kk = k0 + tid; rc = kk < nac ? D.acs[kk] : 0.0; }
     };
@@ -98,6 +101,11 @@ k_redistribute_dense(DensePlan D, const double *__restrict__ Bm, double *__restr
         double *a = As + buf * GM_BK * GM_BM, *b = Bs + buf * GM_BK * GM_BN;
 #pragma unroll
         for (int i = 0; i < 8; ++i) a[(a_k + i) * GM_BM + a_r] = ra[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!is_finite_bits(rb[i])) { bad[n0 + b_n + i] = 1; rb[i] = 0.0; }
+            if (!EXACT) rb[i] = rb[i] * rsc;              // FAST: ac(src) folded into the staged tile
+        }
 #pragma unroll
         for (int i = 0; i < 4; ++i) reinterpret_cast<double2 *>(b + b_k * GM_BN + b_n)[i] = make_double2(rb[2 * i], rb[2 * i + 1]);
         if (tid < GM_BK) Cs[buf * GM_BK + tid] = rc;
@@ -241,9 +249,22 @@ k_river_sum(DevCatchment C, DevBatch W, DensePlan D, int t) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     const int B = W.B;
     if (m >= B) return;
-    double qb = 0.0, qof = 0.0;
-    for (int i = D.rq_beg[r]; i < D.rq_beg[r + 1]; ++i) qb = qb + W.qb_term[D.rq_idx[i] * (size_t)B + m];
-    for (int i = D.ro_beg[r]; i < D.ro_beg[r + 1]; ++i) qof = qof + W.qof_term[D.ro_idx[i] * (size_t)B + m];
+    // eight loads in flight per batch, added in list order (the loads are independent, the sum is not)
+    auto ordered_sum = [&](const double *__restrict__ term, const int32_t *__restrict__ idx, int beg, int end) {
+        double acc = 0.0;
+        int i = beg;
+        for (; i + 8 <= end; i += 8) {
+            double v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = term[__ldg(idx + i + u) * (size_t)B + m];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc = acc + v[u];
+        }
+        for (; i < end; ++i) acc = acc + term[__ldg(idx + i) * (size_t)B + m];
+        return acc;
+    };
+    const double qb = ordered_sum(W.qb_term, D.rq_idx, D.rq_beg[r], D.rq_beg[r + 1]);
+    const double qof = ordered_sum(W.qof_term, D.ro_idx, D.ro_beg[r], D.ro_beg[r + 1]);
     W.qout[((size_t)m * C.nriv + r) * W.R + (t & W.Rmask)] = qb + qof;      // dyna_river.f90:43
 }
 
