@@ -295,6 +295,16 @@ def main():
         ach_tf = fpu * units_per_launch / (launch_ms * 1e-3) / 1e12
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         ach_gbs = 80.0 * units_per_launch / (launch_ms * 1e-3) / 1e9
+        # DRAM traffic of the dominant kernel per launch, from the committed ncu capture of this same launch shape
+        # (profiles/r1_ncu_resident_v2_dram_fullsize.csv: dram__bytes_read.sum + dram__bytes_write.sum); null otherwise
+        kname = {1: "k_physics_streamed", 2: "k_physics_resident_v2" if args.math == "fast" else "k_physics_resident",
+                 3: "k_redistribute_* + k_physics_stepwise"}.get(st["kernel_used"], "?")
+        traffic, traffic_src = None, None
+        if kname == "k_physics_resident_v2" and (M, cat.nstep, cat.nac) == (4736, 87600, 500):
+            traffic = 615805952 + 10248028160
+            traffic_src = ("profiles/r1_ncu_resident_v2_dram_fullsize.csv (ncu, same launch shape): 0.62 GB read + 10.25 GB "
+                           "written = the qout(member, river, t) series handed to the routing kernels (9.96 GB algorithmic); "
+                           "0.052 B per member-HRU-timestep")
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_dev_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -307,8 +317,8 @@ def main():
             "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"],
                        "power_w_max": clk.get("power_w_max"), "samples": clk["samples"]},
             "roofline": {"bound": "fp64", "achieved": ach_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach_tf / fp64_peak, "traffic": None,
-                         "kernel": "k_physics_" + {1: "streamed", 2: "resident"}.get(st["kernel_used"], "?"),
+                         "frac": ach_tf / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "kernel": kname,
                          "flops_per_unit": fpu, "units_per_launch": units_per_launch, "launch_ms": launch_ms,
                          "peak_source": "dcp_measure_fp64_peak (DFMA chains, measured in this run; MEASURED_PEAKS.json has no FP64 figure)",
                          "physics_share_of_step": ms_phys / max(ms_dev_max - ms_gather, 1e-9)},
