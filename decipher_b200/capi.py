@@ -187,6 +187,7 @@ def load_library(path: str = LIB_PATH):
     lib.dcp_run_ensemble.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.POINTER(RunOpts),
                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.dcp_get_run_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
+    lib.dcp_route_timeseries.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     lib.dcp_measure_fp64_peak.argtypes = [c_double_p, c_double_p]
     _lib = lib
     return lib
@@ -264,6 +265,28 @@ class DeviceCatchment:
         rc = self.lib.dcp_run_ensemble(self._h, 1, int(M), v(mcpar_ptr), C.byref(opts), v(q_ptr), v(perf_ptr),
                                        v(totals_ptr), v(diag_ptr), v(status_ptr))
         _check(self.lib, rc, "dcp_run_ensemble(device)")
+        return self.stats()
+
+    def route_timeseries(self, velocity: np.ndarray, inflow: np.ndarray):
+        """Standalone router (DTA/route_run_standalone.f90): velocity (n,) metres per timestep, inflow
+        (nriv, nstep, n) Fortran-ordered.  Returns the routed series in the same layout, status words and timings."""
+        cat = self.cat
+        velocity = np.ascontiguousarray(velocity, dtype=np.float64)
+        n = velocity.shape[0]
+        assert inflow.dtype == np.float64 and inflow.flags.f_contiguous and inflow.shape == (cat.nriv, cat.nstep, n)
+        routed = np.empty((cat.nriv, cat.nstep, n), order="F")
+        status = np.zeros(n, dtype=np.int32)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = self.lib.dcp_route_timeseries(self._h, n, p(velocity), p(inflow), p(routed), p(status), 0)
+        _check(self.lib, rc, "dcp_route_timeseries")
+        return dict(routed=routed, status=status, stats=self.stats())
+
+    def route_timeseries_device(self, n: int, velocity_ptr: int, inflow_ptr: int, routed_ptr: int, status_ptr: int = 0):
+        """Same call with DEVICE pointers."""
+        v = lambda x: C.c_void_p(x) if x else None
+        rc = self.lib.dcp_route_timeseries(self._h, int(n), v(velocity_ptr), v(inflow_ptr), v(routed_ptr), v(status_ptr),
+                                           OPT_DEVICE_BUFFERS)
+        _check(self.lib, rc, "dcp_route_timeseries(device)")
         return self.stats()
 
     def stats(self) -> dict:

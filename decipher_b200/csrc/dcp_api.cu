@@ -76,6 +76,7 @@ struct dcp_catchment {
     cudaStream_t stream = nullptr;
     // host copies needed at run time
     std::vector<double> node_reach_dist, node_down_dist;
+    const double *ones_riv = nullptr;   // [nriv] 1.0 (standalone router: no division by frac_sub_area)
     bool has_qobs = false;
     ResPlan plan{};                     // resident-kernel plan (plan.feasible == 0: streamed kernel only)
     Res2Plan plan2{};                   // second-generation resident kernel (lean arithmetic, own-river catchments)
@@ -190,12 +191,12 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
         load[wsel] += ell_K[blk % npb];
     }
     // ---- flat gather list per compute warp: the four columns of a thread one after the other, step-major over the
-    // lanes, one 8-byte word per entry = the weight with the absolute source tuple index (< 512) in its lowest nine
-    // mantissa bits (weight rounded to the nearest such value: relative change <= 2^-44).  One spare batch of four
+    // lanes, one 8-byte word per entry = the weight with the byte offset of the source tuple (index << 4, index < 512)
+    // in mantissa bits 4..12 (weight rounded to the nearest multiple of 2^13 ulp: relative change <= 2^-40).  One spare batch of four
     // steps follows each warp's list (the kernel prefetches one batch ahead). ----
     auto pack = [](double wv, int idx) {
         uint64_t b; std::memcpy(&b, &wv, 8);
-        b = ((b + 256) & ~(uint64_t)511) | (uint64_t)idx;
+        b = ((b + 4096) & ~(uint64_t)8191) | ((uint64_t)idx << 4);
         double r; std::memcpy(&r, &b, 8); return r;
     };
     std::vector<double> ent;
@@ -255,8 +256,8 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     Q.off_par = take((size_t)G * S * npt * 2 * 16);
     Q.off_forc = take((size_t)2 * Q.Tt * (d->ngp + d->nge) * 8);
     Q.off_bar = take(16);
-    Q.team_bytes = (int)((off + 127) & ~(size_t)127);
-    Q.smem_bytes = Q.off_team + 2 * Q.team_bytes;
+    Q.team_bytes = (int)((off + 8191) & ~(size_t)8191);     // team blocks (tuple buffers first) sit on 8 KB boundaries
+    Q.smem_bytes = Q.off_team + 8192 + 2 * Q.team_bytes;    // + the kernel's alignment slack
     if ((size_t)Q.smem_bytes > c->smem_optin) return;
     std::vector<double> pet_pos(pet);
     for (double &x : pet_pos) x = x > 0.0 ? x : 0.0;
@@ -478,6 +479,7 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
     up(cbeg, &C.node_cell_beg); up(cend, &C.node_cell_end); up(reach_dist, &C.node_reach_dist);
     up(down_dist, &C.node_down_dist); up(cell_a, &C.cell_a); up(cell_b, &C.cell_b); up(cell_area, &C.cell_area);
     up(node_input, &C.node_input); up(up_beg, &C.up_beg); up(up_idx, &C.up_idx); up(frac, &C.frac_sub_area);
+    { std::vector<double> ones(nriv, 1.0); up(ones, &c->ones_riv); }
     up(obs, &C.obs); up(tot_ppt, &C.tot_ppt); up(tot_pet, &C.tot_pet); up(tot_frac, &C.tot_frac);
     if (has_qobs) up(qobs, &C.qobs); else C.qobs = nullptr;
     // ---------------- resident-kernel plan ----------------
@@ -926,6 +928,114 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     c->stats.ms_route = sums[T_ROUTE] + sums[T_FIN];
     c->stats.ms_d2h = sums[T_D2H];
     c->stats.n_physics_launches = n_phys;
+    c->stats.n_launches = n_launch;
+    c->stats.hist_len = hist_len_max;
+    return DCP_OK;
+}
+
+int dcp_route_timeseries(dcp_catchment *c, int64_t n_series, const double *velocity, const double *inflow,
+                         double *routed, int32_t *status, int32_t flags) {
+    if (!c || !velocity || !inflow || !routed) return fail(DCP_ERR_INVALID, "null handle, velocity, inflow or routed");
+    if (n_series < 1) return fail(DCP_ERR_INVALID, "n_series < 1");
+    if (flags & ~DCP_OPT_DEVICE_BUFFERS) return fail(DCP_ERR_INVALID, "dcp_route_timeseries takes DCP_OPT_DEVICE_BUFFERS only");
+    CUDA_TRY(cudaSetDevice(c->device));
+    const bool dev_io = (flags & DCP_OPT_DEVICE_BUFFERS) != 0;
+    DevCatchment C = c->C;
+    C.qobs = nullptr;                           // no objective terms
+    C.frac_sub_area = c->ones_riv;              // route_process_run_timeseries returns the plain sums (:685-714)
+    cudaStream_t s = c->stream;
+    c->stats = dcp_run_stats{};
+    EventTimer tm(s);
+    int64_t n_launch = 0;
+    int hist_len_max = 0;
+    size_t free_b = 0, total_b = 0;
+    CUDA_TRY(cudaMemGetInfo(&free_b, &total_b));
+    free_b += c->ws.cap + c->io.cap;
+    const double mem_budget = 0.85 * (double)free_b;
+    const size_t series_elems = (size_t)C.nriv * C.nstep;
+    std::vector<double> v_host;
+    const double *v_all = velocity;
+    if (dev_io) {                               // the slowest velocity of a batch sizes its histograms
+        v_host.resize((size_t)n_series);
+        CUDA_TRY(cudaMemcpy(v_host.data(), velocity, (size_t)n_series * 8, cudaMemcpyDeviceToHost));
+        v_all = v_host.data();
+    }
+    int64_t Bmax = std::min<int64_t>(n_series, 65536);
+    for (int64_t m0 = 0; m0 < n_series;) {
+        int64_t Bn = std::min<int64_t>(Bmax, n_series - m0);
+        double v_min = v_all[m0];
+        for (int64_t i = 0; i < Bn; ++i) {
+            const double v = v_all[m0 + i];
+            if (!(v > 0) || !std::isfinite(v)) return fail(DCP_ERR_INVALID, "velocity of series %lld must be positive and finite (%g)", (long long)(m0 + i), v);
+            v_min = std::min(v_min, v);
+        }
+        double max_reach = 0, max_full = 0;
+        for (int n = 0; n < C.nnode; ++n) {
+            max_reach = std::max(max_reach, c->node_reach_dist[n] / v_min);
+            max_full = std::max(max_full, (c->node_reach_dist[n] + c->node_down_dist[n]) / v_min);
+        }
+        if (max_full > 4.0e6) return fail(DCP_ERR_INVALID, "routing histogram would need %g bins (velocity too small)", max_full);
+        DevBatch W{};
+        W.B = (int)Bn;
+        W.Lcap = (int)std::ceil(max_reach) + 3;
+        hist_len_max = std::max(hist_len_max, (int)std::ceil(max_full) + 1);
+        W.R = C.nstep; W.Rmask = 0x7fffffff;
+        auto carve = [&](void *base) {
+            Carver cv(base);
+            W.dh = cv.take<double>((size_t)C.nnode * W.Lcap * Bn);
+            W.hstart = cv.take<int32_t>((size_t)C.nnode * Bn);
+            W.hbins = cv.take<int32_t>((size_t)C.nnode * Bn);
+            W.qout = cv.take<double>(series_elems * Bn);
+            W.y = cv.take<double>((size_t)C.nnode * C.nstep * Bn);
+            W.bad = cv.take<int32_t>((size_t)C.nriv * Bn);
+            W.status = cv.take<int32_t>(Bn);
+            return cv.off + 256;
+        };
+        const size_t ws_bytes = carve(nullptr);
+        const size_t io_bytes = dev_io ? 256 : (2 * series_elems * Bn + Bn) * 8 + Bn * 4 + 1024;
+        if ((double)(ws_bytes + io_bytes) > mem_budget) {
+            if (Bn <= 1) return fail(DCP_ERR_NOMEM, "one series needs %zu MB, device has %zu MB free", (ws_bytes + io_bytes) >> 20, free_b >> 20);
+            Bmax = std::max<int64_t>(1, Bn / 2);
+            continue;
+        }
+        CUDA_TRY(c->ws.reserve(ws_bytes));
+        CUDA_TRY(c->io.reserve(io_bytes));
+        carve(c->ws.p);
+        const double *d_v = velocity + m0, *d_in = inflow + (size_t)m0 * series_elems;
+        double *d_out = routed + (size_t)m0 * series_elems;
+        int32_t *d_status = status ? status + m0 : nullptr;
+        tm.mark(T_H2D);
+        if (!dev_io) {
+            Carver iocv(c->io.p);
+            double *dv = iocv.take<double>(Bn), *din = iocv.take<double>(series_elems * Bn);
+            d_out = iocv.take<double>(series_elems * Bn);
+            d_status = iocv.take<int32_t>(Bn);
+            CUDA_TRY(cudaMemcpyAsync(dv, velocity + m0, (size_t)Bn * 8, cudaMemcpyHostToDevice, s));
+            CUDA_TRY(cudaMemcpyAsync(din, inflow + (size_t)m0 * series_elems, series_elems * Bn * 8, cudaMemcpyHostToDevice, s));
+            d_v = dv; d_in = din;
+        }
+        tm.mark(T_INIT);
+        dcp_launch_route_prepare(C, W, d_v, d_in, s); n_launch += 2;
+        tm.mark(T_ROUTE);
+        dcp_launch_route(C, W, 0, C.nstep, d_out, s); n_launch += 2;
+        if (d_status) { dcp_launch_route_status(C, W, d_status, s); ++n_launch; }
+        tm.mark(T_D2H);
+        if (!dev_io) {
+            CUDA_TRY(cudaMemcpyAsync(routed + (size_t)m0 * series_elems, d_out, series_elems * Bn * 8, cudaMemcpyDeviceToHost, s));
+            if (status) CUDA_TRY(cudaMemcpyAsync(status + m0, d_status, (size_t)Bn * 4, cudaMemcpyDeviceToHost, s));
+        }
+        tm.mark(-1);
+        CUDA_TRY(cudaStreamSynchronize(s));
+        CUDA_TRY(cudaGetLastError());
+        m0 += Bn;
+    }
+    double sums[T_NTAGS];
+    tm.collect(sums, T_NTAGS);
+    c->stats.ms_total = tm.total();
+    c->stats.ms_h2d = sums[T_H2D];
+    c->stats.ms_init = sums[T_INIT];
+    c->stats.ms_route = sums[T_ROUTE];
+    c->stats.ms_d2h = sums[T_D2H];
     c->stats.n_launches = n_launch;
     c->stats.hist_len = hist_len_max;
     return DCP_OK;

@@ -113,7 +113,7 @@ FM_HD double fm_rcp(double y) {
     return FM_FMA(r, t, r);
 }
 
-// exp(x), |x| <= 700.  Estrin evaluation of the degree-9 polynomial: depth 4 instead of 9 dependent DFMAs.
+// exp(x), |x| <= 700.
 FM_HD double fm_exp(double x) {
     const double t = FM_FMA(x, FMC(0), FMC(3));
     const int32_t k = fm_lo(t);
@@ -121,6 +121,7 @@ FM_HD double fm_exp(double x) {
     double r = FM_FMA(kf, -FMC(1), x);
     r = FM_FMA(kf, -FMC(2), r);
     const double r2 = r * r;
+#ifdef FM_EXP_ESTRIN
     const double p01 = FM_FMA(FMC(5), r, FMC(4));
     const double p23 = FM_FMA(FMC(7), r, FMC(6));
     const double p45 = FM_FMA(FMC(9), r, FMC(8));
@@ -132,6 +133,20 @@ FM_HD double fm_exp(double x) {
     const double r8 = r4 * r4;
     const double s0 = FM_FMA(q1, r4, q0);
     const double p = FM_FMA(p89, r8, s0);
+#else
+    // even / odd Horner chains in r^2: two independent chains of depth 4, ONE coefficient per DFMA (the coefficient
+    // comes straight from the constant bank / a uniform register; Estrin's c1*r + c0 pairs need a vector register
+    // per coefficient, ~20 registers held across the whole time loop)
+    double pe = FM_FMA(FMC(12), r2, FMC(10));
+    double po = FM_FMA(FMC(13), r2, FMC(11));
+    pe = FM_FMA(pe, r2, FMC(8));
+    po = FM_FMA(po, r2, FMC(9));
+    pe = FM_FMA(pe, r2, FMC(6));
+    po = FM_FMA(po, r2, FMC(7));
+    pe = FM_FMA(pe, r2, FMC(4));
+    po = FM_FMA(po, r2, FMC(5));
+    const double p = FM_FMA(po, r, pe);
+#endif
     const double y = 1.0 + FM_FMA(r2, p, r);          // in (0.70, 1.42)
     return fm_make(fm_hi(y) + (k << 20), fm_lo(y));   // * 2^k, result stays normal for |x| <= 700
 }

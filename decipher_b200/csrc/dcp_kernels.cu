@@ -89,6 +89,59 @@ __device__ __forceinline__ double calc_qb(const DevCatchment &C, const DevBatch 
     return warp_sum(part);
 }
 
+// route_processing_build_hist + hist_add_value (DTA/dta_route_processing.f90:154-354, 356-416) for one member / one
+// standalone series with v = metres travelled per timestep (calculate_cell_delay, :419-442, V_MODE_CONSTANT), in the
+// reference's order; returns DCP_ST_* bits
+__device__ __forceinline__ int build_hist_one(const DevCatchment &C, const DevBatch &W, const int m, const double chvdt1) {
+    const int B = W.B;
+    int status = 0;
+    for (int n = 0; n < C.nnode; ++n) {
+        const int cb = C.node_cell_beg[n], ce = C.node_cell_end[n];
+        int hstart = 0, bins = 0;
+        if (cb >= 0) {
+            const double reach_delay = C.node_reach_dist[n] / chvdt1;     // :231
+            const double tdd = C.node_down_dist[n] / chvdt1;              // :241
+            const double full_delay = reach_delay + tdd;                  // :256
+            hstart = (int)floor(tdd) + 1;                                 // :259
+            const int hend = (int)ceil(full_delay) + 1;                   // :260
+            bins = (hend - hstart) + 1;                                   // :312
+            if (bins > W.Lcap || bins < 1) {                              // sized from the slowest member
+                status |= DCP_ST_HIST_DROPPED;
+                bins = bins < 1 ? 0 : W.Lcap;
+            }
+            double *dh = W.dh + ((size_t)m * C.nnode + n) * W.Lcap;       // [member][node][bin], bins contiguous
+            for (int k = 0; k < bins; ++k) dh[k] = 0.0;
+            for (int j = cb; j < ce; ++j) {
+                const double cur_a = C.cell_a[j] / chvdt1;                // :337
+                const double cur_b = C.cell_b[j] / chvdt1;                // :339
+                const double value = C.cell_area[j];
+                const int hist_a = (int)floor(cur_a) + 1;                 // hist_add_value :369-370
+                const int hist_b = (int)floor(cur_b) + 1;
+                if (hist_b > bins || hist_a < 1) {                        // :378-382 drops the cell
+                    status |= DCP_ST_HIST_DROPPED;
+                    continue;
+                }
+                if (hist_a == hist_b) {
+                    const double fr = cur_b - cur_a;
+                    dh[hist_a - 1] = dh[hist_a - 1] + value * fr;
+                } else {
+                    for (int k = hist_a + 1; k <= hist_b - 1; ++k) dh[k - 1] = dh[k - 1] + value;
+                    double fr = (1.0 - (cur_a - (double)hist_a + 1.0));   // :410
+                    dh[hist_a - 1] = dh[hist_a - 1] + (value * fr);
+                    fr = (cur_b - (double)hist_b + 1.0);                  // :413
+                    dh[hist_b - 1] = dh[hist_b - 1] + (value * fr);
+                }
+            }
+            double s = 0.0;                                               // :347
+            for (int k = 0; k < bins; ++k) s += dh[k];
+            for (int k = 0; k < bins; ++k) dh[k] = dh[k] / s;
+        }
+        W.hstart[n * (size_t)B + m] = hstart;
+        W.hbins[n * (size_t)B + m] = bins;
+    }
+    return status;
+}
+
 template <bool CHECK>
 __global__ void __launch_bounds__(128)
 k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7 x B]*/) {
@@ -109,52 +162,7 @@ k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7
     const double chvdt1 = mp[4 * npt + 0] * C.dt;                             // dyna_init_satzone.f90:85
 
     // ---- route_processing_build_hist (DTA/dta_route_processing.f90:154-354), v = chvdt(1); lane 0, reference order ----
-    if (lane == 0) {
-        for (int n = 0; n < C.nnode; ++n) {
-            const int cb = C.node_cell_beg[n], ce = C.node_cell_end[n];
-            int hstart = 0, bins = 0;
-            if (cb >= 0) {
-                const double reach_delay = C.node_reach_dist[n] / chvdt1;     // :231
-                const double tdd = C.node_down_dist[n] / chvdt1;              // :241
-                const double full_delay = reach_delay + tdd;                  // :256
-                hstart = (int)floor(tdd) + 1;                                 // :259
-                const int hend = (int)ceil(full_delay) + 1;                   // :260
-                bins = (hend - hstart) + 1;                                   // :312
-                if (bins > W.Lcap || bins < 1) {                              // sized from the slowest member
-                    status |= DCP_ST_HIST_DROPPED;
-                    bins = bins < 1 ? 0 : W.Lcap;
-                }
-                double *dh = W.dh + ((size_t)m * C.nnode + n) * W.Lcap;       // [member][node][bin], bins contiguous
-                for (int k = 0; k < bins; ++k) dh[k] = 0.0;
-                for (int j = cb; j < ce; ++j) {
-                    const double cur_a = C.cell_a[j] / chvdt1;                // :337
-                    const double cur_b = C.cell_b[j] / chvdt1;                // :339
-                    const double value = C.cell_area[j];
-                    const int hist_a = (int)floor(cur_a) + 1;                 // hist_add_value :369-370
-                    const int hist_b = (int)floor(cur_b) + 1;
-                    if (hist_b > bins || hist_a < 1) {                        // :378-382 drops the cell
-                        status |= DCP_ST_HIST_DROPPED;
-                        continue;
-                    }
-                    if (hist_a == hist_b) {
-                        const double fr = cur_b - cur_a;
-                        dh[hist_a - 1] = dh[hist_a - 1] + value * fr;
-                    } else {
-                        for (int k = hist_a + 1; k <= hist_b - 1; ++k) dh[k - 1] = dh[k - 1] + value;
-                        double fr = (1.0 - (cur_a - (double)hist_a + 1.0));   // :410
-                        dh[hist_a - 1] = dh[hist_a - 1] + (value * fr);
-                        fr = (cur_b - (double)hist_b + 1.0);                  // :413
-                        dh[hist_b - 1] = dh[hist_b - 1] + (value * fr);
-                    }
-                }
-                double s = 0.0;                                               // :347
-                for (int k = 0; k < bins; ++k) s += dh[k];
-                for (int k = 0; k < bins; ++k) dh[k] = dh[k] / s;
-            }
-            W.hstart[n * (size_t)B + m] = hstart;
-            W.hbins[n * (size_t)B + m] = bins;
-        }
-    }
+    if (lane == 0) status |= build_hist_one(C, W, m, chvdt1);
 
     // ---- init_satzone (RRMODEL/dyna_init_satzone.f90:92-213) ----
     // q0 (:108) and the hoisted q2 of dyna_satzone_analyticalsolver.f90:50-51 per HRU: independent, all lanes
@@ -549,6 +557,37 @@ k_objective_sum(DevCatchment C, DevBatch W, int t0, int t1) {
 }
 
 // ------------------------------------------------------------------------------------------------
+// Standalone router (DTA/route_run_standalone.f90:118-189 -> route_processing_build_hist +
+// route_process_run_timeseries, DTA/dta_route_processing.f90:583-630): one histogram set per series
+// from its own velocity, the caller's inflow series laid into the routing layout, then K3a/K3b.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+k_route_prepare(DevCatchment C, DevBatch W, const double *__restrict__ v /*[B]*/) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= W.B) return;
+    W.status[m] = build_hist_one(C, W, m, v[m]);
+    for (int r = 0; r < C.nriv; ++r) W.bad[r * (size_t)W.B + m] = 0;
+}
+
+// inflow [nriv x nstep x B] (ABI layout, river fastest) -> qout [B][nriv][R] (time fastest)
+__global__ void __launch_bounds__(ROUTE_CH)
+k_route_load_inflow(DevCatchment C, DevBatch W, const double *__restrict__ inflow) {
+    const int m = blockIdx.x, t = blockIdx.y * ROUTE_CH + threadIdx.x;
+    if (t >= C.nstep) return;
+    const double *src = inflow + ((size_t)m * C.nstep + t) * C.nriv;
+    for (int r = 0; r < C.nriv; ++r) W.qout[((size_t)m * C.nriv + r) * W.R + t] = src[r];
+}
+
+__global__ void __launch_bounds__(128)
+k_route_status(DevCatchment C, DevBatch W, int32_t *__restrict__ status) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= W.B) return;
+    int st = W.status[m];
+    for (int r = 0; r < C.nriv; ++r) if (W.bad[r * (size_t)W.B + m]) st |= DCP_ST_NONFINITE;
+    status[m] = st;
+}
+
+// ------------------------------------------------------------------------------------------------
 // K4: outputs in the ABI's layouts (member slowest)
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
@@ -673,6 +712,17 @@ void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, 
         dim3 g3(cdiv(W.B, 128), C.nriv);
         k_objective_sum<<<g3, 128, 0, s>>>(C, W, t0, t1);
     }
+}
+
+void dcp_launch_route_prepare(const DevCatchment &C, const DevBatch &W, const double *v, const double *inflow,
+                              cudaStream_t s) {
+    k_route_prepare<<<cdiv(W.B, 128), 128, 0, s>>>(C, W, v);
+    dim3 g(W.B, cdiv(C.nstep, ROUTE_CH));
+    k_route_load_inflow<<<g, ROUTE_CH, 0, s>>>(C, W, inflow);
+}
+
+void dcp_launch_route_status(const DevCatchment &C, const DevBatch &W, int32_t *status, cudaStream_t s) {
+    k_route_status<<<cdiv(W.B, 128), 128, 0, s>>>(C, W, status);
 }
 
 void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,

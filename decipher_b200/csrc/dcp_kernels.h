@@ -19,6 +19,9 @@ void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bo
 void dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,
                                  bool check, bool aet, cudaStream_t s);
 void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s);
+void dcp_launch_route_prepare(const DevCatchment &C, const DevBatch &W, const double *v, const double *inflow,
+                              cudaStream_t s);
+void dcp_launch_route_status(const DevCatchment &C, const DevBatch &W, int32_t *status, cudaStream_t s);
 void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,
                          int32_t *status, cudaStream_t s);
 void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s);

@@ -19,8 +19,8 @@
 //     step-major, rows padded with zero weights to the block's longest row; the four columns of a thread follow
 //     one another in the list, so the trip counts are warp-uniform and the list is walked with a one-entry
 //     look-ahead (the first entry of the next step is requested before the barrier).  An entry is ONE 8-byte
-//     word: the weight with the source's tuple index in its nine lowest mantissa bits (|dw/w| <= 2^-44), i.e.
-//     one LDS.64 per entry and no index array.  A tuple is the 16 bytes of the team's two member slots, so one
+//     word: the weight with the source tuple's byte offset (index << 4) in mantissa bits 4..12 (|dw/w| <= 2^-40), i.e.
+//     one LDS.64 per entry, no index array, and the tuple address is one LOP3 (the tuple buffers are 8 KB aligned).  A tuple is the 16 bytes of the team's two member slots, so one
 //     LDS.128 per source and eight bank classes; the host orders the entries of each row so that the eight
 //     lanes of a quarter-warp hit different classes wherever the catchment allows (dcp_api.cu).
 //     Measured (profiles/r1_ncu_resident_v2*.txt): the gather is ~28 % of a compute warp's time for ~14 % of
@@ -59,6 +59,11 @@
 #ifndef R2_REG_RIVER
 #define R2_REG_RIVER 24
 #endif
+#ifdef DCP_RES2_DEBUG                  // per-warp busy-cycle counters (tuning builds only: two registers and a branch per step)
+#define R2_DBG (P.dbg != nullptr)
+#else
+#define R2_DBG false
+#endif
 #define R2_S 2                        // member slots per team
 #define R2_H 4                        // columns per compute thread
 #ifndef R2_CARRY_E1
@@ -68,7 +73,7 @@
 struct R2Smem {                       // team-private views unless noted
     double2 *qbf_s;       // [2][512]        baseflow tuples (2 member slots), double buffered in time
     double2 *con_s;       // [2][512]        river contributions by slot, double buffered in time
-    double2 *cst_s;       // [2][2][512]     {q0, q2}, {m2, 1/m2} per (member slot, column)
+    double2 *cst_s;       // [2][2][4][128]  {q0, q2}, {m2, 1/m2} per (member slot, word, column slot j, team thread)
     double2 *par_s;       // [Mv][npt][2]    {srmax, 1/srmax}, {td, smax}
     double *forc_s;       // [2][Tt*(ngp+nge)]
     uint64_t *bars;       // [2]
@@ -78,6 +83,17 @@ struct R2Smem {                       // team-private views unless noted
     double2 *cold_s;      // [4][128][2]     {ac, 1/ac}, {cq, cos(mslp)}
     int32_t *rbeg_s;      // [nriv+1]
 };
+
+// Source tuple of one gather entry.  The entry's low word carries the tuple's BYTE offset (index << 4) in bits 4..12
+// and a time buffer of tuples is 8 KB aligned, so the shared-memory address is ONE LOP3 ((lo & 0x1ff0) | base)
+// instead of mask + add + scale.  volatile: ordered against the team barrier (also a volatile asm).
+__device__ __forceinline__ double2 lds_tuple(int lo, uint32_t buf_u32) {
+    uint32_t a;
+    asm("lop3.b32 %0, %1, 0x1ff0, %2, 0xEA;" : "=r"(a) : "r"(lo), "r"(buf_u32));
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
 
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(R2_TT) : "memory"); }
 
@@ -133,8 +149,8 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #endif
                 reinterpret_cast<double *>(M.qbf_s + tup)[k] = qb0;                 // time buffer 0 = step 0's "old" qbf
                 reinterpret_cast<double *>(M.qbf_s + R2_COLS + tup)[k] = 0.0;
-                M.cst_s[(k * 2 + 0) * R2_COLS + tup] = make_double2(c_q0, c_q2);
-                M.cst_s[(k * 2 + 1) * R2_COLS + tup] = make_double2(c_m2, c_im2);
+                M.cst_s[((k * 2 + 0) * H + j) * R2_TC + tt_id] = make_double2(c_q0, c_q2);   // own-column table: [slot][word][column j][thread]
+                M.cst_s[((k * 2 + 1) * H + j) * R2_TC + tt_id] = make_double2(c_m2, c_im2);
             }
         }
         for (int i = tt_id; i < Mv * npt; i += R2_TC) {      // member parameters -> shared
@@ -166,8 +182,9 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
             const double *forc_t = M.forc_s + b * forc_stride;
             const int t_end = min(C.nstep, t + P.Tt);
             for (int tt = 0; t < t_end; ++t, ++tt) {
-                const long long c0 = P.dbg ? clock64() : 0;
+                const long long c0 = R2_DBG ? clock64() : 0;
                 const double2 *qbf_cur = M.qbf_s + (t & 1) * R2_COLS;
+                const uint32_t qcur_u32 = smem_u32(qbf_cur);         // 8 KB aligned (kernel entry), see lds_tuple
                 double2 *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * R2_COLS;
                 double2 *con = M.con_s + (t & 1) * R2_COLS;
                 // ---- dynamic_dist gather (dyna_dynamic_dist.f90:49-52): the thread's four columns form one flat list
@@ -190,7 +207,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                         for (int bb = 0; bb < nb; ++bb) {
                             double wc[GB]; double2 qv[GB];
 #pragma unroll
-                            for (int u = 0; u < GB; ++u) { wc[u] = wv[u]; qv[u] = qbf_cur[__double2loint(wc[u]) & 511]; }
+                            for (int u = 0; u < GB; ++u) { wc[u] = wv[u]; qv[u] = lds_tuple(__double2loint(wc[u]), qcur_u32); }
                             ep += GB * 32;
 #pragma unroll
                             for (int u = 0; u < GB; ++u) wv[u] = ep[u * 32];
@@ -206,7 +223,6 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const int j = jp + jj;
-                        const int tup = ci[j].z & 0xffff;
                         const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];      // {ac, 1/ac}
                         const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];      // {cq, cos}
                         cq[jj] = d1.x;
@@ -214,8 +230,8 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                         const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci[j].y >> 8) & 0xff)];   // already max(ep, 0)
 #pragma unroll
                         for (int k = 0; k < S; ++k) {
-                            const double2 c0v = M.cst_s[(k * 2 + 0) * R2_COLS + tup];
-                            const double2 c1v = M.cst_s[(k * 2 + 1) * R2_COLS + tup];
+                            const double2 c0v = M.cst_s[((k * 2 + 0) * H + j) * R2_TC + tt_id];
+                            const double2 c1v = M.cst_s[((k * 2 + 1) * H + j) * R2_TC + tt_id];
                             const double2 p0 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride];
                             const double2 p1 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 1];
                             HruConst c;
@@ -244,11 +260,10 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                             for (int k = 0; k < S; ++k)
                                 if (lo[jj][k].slow) {
                                     const int j = jp + jj;
-                                    const int tup = ci[j].z & 0xffff;
                                     const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];
                                     const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];
-                                    const double2 c0v = M.cst_s[(k * 2 + 0) * R2_COLS + tup];
-                                    const double2 c1v = M.cst_s[(k * 2 + 1) * R2_COLS + tup];
+                                    const double2 c0v = M.cst_s[((k * 2 + 0) * H + j) * R2_TC + tt_id];
+                                    const double2 c1v = M.cst_s[((k * 2 + 1) * H + j) * R2_TC + tt_id];
                                     HruConst c;
                                     c.ac = d0.x; c.inv_ac = d0.y;
                                     c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = c1v.x; c.inv_m2 = c1v.y;
@@ -277,11 +292,11 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                 }
 #pragma unroll
                 for (int u = 0; u < GB; ++u) wv[u] = ent0[u * 32];                     // next step's first gather batch
-                if (P.dbg) busy += clock64() - c0;
+                if (R2_DBG) busy += clock64() - c0;
                 team_sync(team);
             }
         }
-        if (P.dbg && (tt_id & 31) == 0) P.dbg[blockIdx.x * 12 + team * 4 + (tt_id >> 5)] = busy;
+        if (R2_DBG && (tt_id & 31) == 0) P.dbg[blockIdx.x * 12 + team * 4 + (tt_id >> 5)] = busy;
         if (AET) {
 #pragma unroll
             for (int j = 0; j < H; ++j) {
@@ -365,14 +380,14 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
             }
             const int t_end = min(C.nstep, t + P.Tt);
             for (; t < t_end; ++t) {
-                const long long c0 = P.dbg ? clock64() : 0;
+                const long long c0 = R2_DBG ? clock64() : 0;
                 if (t > 0) flush_step(t - 1);                // while the compute warps run step t
-                if (P.dbg) busy += clock64() - c0;
+                if (R2_DBG) busy += clock64() - c0;
                 team_sync(team);
             }
         }
         flush_step(C.nstep - 1);
-        if (P.dbg && (rl & 31) == 0) P.dbg[blockIdx.x * 12 + 8 + team * 2 + (rl >> 5)] = busy;
+        if (R2_DBG && (rl & 31) == 0) P.dbg[blockIdx.x * 12 + 8 + team * 2 + (rl >> 5)] = busy;
     }
 }
 
@@ -384,7 +399,10 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     const bool is_compute = tid < R2_CT;
     const int team = is_compute ? tid / R2_TC : (tid - R2_CT) / R2_TR;
     R2Smem M;
-    unsigned char *tb = smem + P.off_team + (size_t)team * P.team_bytes;
+    // team blocks start on an 8 KB boundary of the shared window (their first array is the tuple buffer pair, whose
+    // 8 KB halves are addressed by OR-ing the tuple offset into the base: lds_tuple); the plan reserves the slack
+    const uint32_t pad = (8192u - ((smem_u32(smem) + (uint32_t)P.off_team) & 8191u)) & 8191u;
+    unsigned char *tb = smem + P.off_team + pad + (size_t)team * P.team_bytes;
     M.qbf_s = (double2 *)(tb + P.off_qbf);
     M.con_s = (double2 *)(tb + P.off_con);
     M.cst_s = (double2 *)(tb + P.off_cst);

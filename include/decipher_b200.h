@@ -194,6 +194,22 @@ int  dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member,
                       double *q_out, double *perf_out, double *reach_totals,
                       double *init_diag, int32_t *status);
 
+/*
+ * Standalone router: replaces route_processing_build_hist + route_process_run_timeseries
+ * (DTA/dta_route_processing.f90:154-354, 583-630) as driven by DTA/route_run_standalone.f90:118-189,
+ * for n_series independent (velocity, inflow series) pairs over the river network of `c`.
+ *
+ *   velocity  [n_series]                  tdh%v_param(1): metres travelled per timestep
+ *                                         (calculate_cell_delay, dta_route_processing.f90:419-442, V_MODE_CONSTANT)
+ *   inflow    [nriv x nstep x n_series]   timeseries_flow_input: column i feeds node node_to_flow_mapping(i)
+ *   routed    [nriv x nstep x n_series]   timeseries_flow_output: the plain routed sums (NOT divided by
+ *                                         frac_sub_area; that division is dyna_river.f90:57-59)
+ *   status    [n_series] or NULL          DCP_ST_HIST_DROPPED / DCP_ST_NONFINITE
+ *   flags     0 or DCP_OPT_DEVICE_BUFFERS
+ */
+int  dcp_route_timeseries(dcp_catchment *c, int64_t n_series, const double *velocity, const double *inflow,
+                          double *routed, int32_t *status, int32_t flags);
+
 int  dcp_get_run_stats(const dcp_catchment *c, dcp_run_stats *out);
 
 /* Standalone FP64 pipe micro-benchmark (dependency-free DFMA chains) used as the roofline

@@ -739,6 +739,30 @@ int dcp_oracle_build_hist(const dcp_catchment_desc *d, double v, int T_cap, doub
     return tdh.dropped ? 2 : 0;
 }
 
+// Standalone router, same contract as dcp_route_timeseries (include/decipher_b200.h):
+// route_processing_build_hist with v_param(1) = velocity[s], then route_process_run_timeseries
+// (DTA/dta_route_processing.f90:583-630: zero the output, one route_process_run_step per row), as
+// DTA/route_run_standalone.f90:118-189 drives them.  status: DCP_ST_HIST_DROPPED | DCP_ST_NONFINITE.
+int dcp_oracle_route_timeseries(const dcp_catchment_desc *d, int64_t n_series, const double *velocity,
+                                const double *inflow, double *routed, int32_t *status) {
+    if (!d || d->struct_size != (int)sizeof(dcp_catchment_desc)) return DCP_ERR_INVALID;
+    Ctx c = make_ctx(d);
+    const size_t per = (size_t)d->nriv * d->nstep;
+    for (int64_t s = 0; s < n_series; ++s) {
+        Tdh tdh;
+        tdh.v_param = velocity[s];
+        route_processing_build_hist(c, tdh);
+        int st = tdh.dropped ? DCP_ST_HIST_DROPPED : 0;
+        for (int t = 0; t < d->nstep; ++t) {
+            double *out = routed + s * per + (size_t)t * d->nriv;
+            route_process_run_step(c, tdh, inflow + s * per + (size_t)t * d->nriv, out);
+            for (int i = 0; i < d->nriv; ++i) if (!std::isfinite(out[i])) st |= DCP_ST_NONFINITE;
+        }
+        if (status) status[s] = st;
+    }
+    return DCP_OK;
+}
+
 // Same contract as dcp_run_ensemble (include/decipher_b200.h) on host buffers, n_threads worker
 // threads over disjoint members (members are independent: SURVEY §8e).
 int dcp_oracle_run_ensemble(const dcp_catchment_desc *d, int64_t n_member, double *mcpar, int flags,

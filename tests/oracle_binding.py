@@ -31,6 +31,8 @@ def load_oracle(opt="O2"):
     lib.dcp_oracle_genpar.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]
     lib.dcp_oracle_build_hist.argtypes = [C.POINTER(CatchmentDesc), C.c_double, C.c_int, C.c_void_p, C.c_void_p,
                                           C.POINTER(C.c_int32)]
+    lib.dcp_oracle_route_timeseries.argtypes = [C.POINTER(CatchmentDesc), C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                                C.c_void_p]
     _libs[opt] = lib
     return lib
 
@@ -78,3 +80,18 @@ def oracle_build_hist(cat, v, T_cap=4096):
                                              idx.ctypes.data_as(C.c_void_p), C.byref(T))
     del keep
     return rc, hist[:, :T.value].copy(), idx, T.value
+
+
+def oracle_route_timeseries(cat, velocity, inflow, opt="O2"):
+    """Standalone router of the oracle: velocity (n,), inflow (nriv, nstep, n) F-ordered -> routed, status."""
+    desc, keep = cat.to_desc()
+    velocity = np.ascontiguousarray(velocity, dtype=np.float64)
+    n = velocity.shape[0]
+    assert inflow.flags.f_contiguous and inflow.shape == (cat.nriv, cat.nstep, n)
+    routed = np.zeros((cat.nriv, cat.nstep, n), order="F")
+    status = np.zeros(n, dtype=np.int32)
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    rc = load_oracle(opt).dcp_oracle_route_timeseries(C.byref(desc), n, p(velocity), p(inflow), p(routed), p(status))
+    assert rc == 0, rc
+    del keep
+    return routed, status
