@@ -34,7 +34,8 @@ OPT_CHECK_BALANCE = 0x1
 OPT_DEVICE_BUFFERS = 0x2
 OPT_FAST_MATH = 0x4
 KERNEL_AUTO, KERNEL_STREAMED, KERNEL_RESIDENT, KERNEL_STEPWISE = 0, 1, 2, 3
-NMEASURE = 2
+NMEASURE = 5
+PERF_NSE, PERF_LOGNSE, PERF_KGE, PERF_PBIAS, PERF_RMSE = range(5)
 
 
 class CatchmentDesc(C.Structure):

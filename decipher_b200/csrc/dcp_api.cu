@@ -439,6 +439,7 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
                 const double o = qobs[(size_t)t * nriv + g];
                 if (o != d->flow_err) { sum = sum + o; s.n++; }
             }
+            s.sum = sum;
             if (s.n > 0) {
                 s.mean = sum / s.n; s.eps = s.mean / 100;
                 double lsum = 0;
@@ -666,9 +667,12 @@ size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, b
     W.hbins = cv.take<int32_t>(C.nnode * B);
     W.qout = cv.take<double>((size_t)W.R * C.nriv * B);
     W.y = cv.take<double>((size_t)W.R * C.nnode * B);
-    if (C.qobs) { W.d2 = cv.take<double>((size_t)W.R * C.nriv * B); W.dl2 = cv.take<double>((size_t)W.R * C.nriv * B); }
-    else { W.d2 = W.dl2 = nullptr; }
+    if (C.qobs) {
+        W.d2 = cv.take<double>((size_t)W.R * C.nriv * B); W.dl2 = cv.take<double>((size_t)W.R * C.nriv * B);
+        W.qs = cv.take<double>((size_t)W.R * C.nriv * B);
+    } else { W.d2 = W.dl2 = W.qs = nullptr; }
     W.sse = cv.take<double>(C.nriv * B); W.lsse = cv.take<double>(C.nriv * B);
+    W.sq = cv.take<double>(C.nriv * B); W.sqq = cv.take<double>(C.nriv * B); W.sqo = cv.take<double>(C.nriv * B);
     W.bad = cv.take<int32_t>(C.nriv * B);
     W.status = cv.take<int32_t>(B);
     W.diag = cv.take<double>(3 * B);

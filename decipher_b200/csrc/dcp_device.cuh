@@ -47,6 +47,7 @@ struct __align__(8) RivEntry {      // rivers(ia, r) != 0
 
 struct ObsStat {                    // per gauge, host-computed once (member independent)
     double mean, sst, eps, lmean, lsst;
+    double sum;                     // sum of the valid observations (PBIAS)
     int32_t n;
     int32_t pad;
 };
@@ -99,8 +100,10 @@ struct DevBatch {
     double *qout;                   // [B][nriv][R]   river inflow series, time fastest
     double *y;                      // [B][nnode][R]  routed own-reach series
     double *d2, *dl2;               // [B][nriv][R]   per-step objective terms (null without observed flow)
+    double *qs;                     // [B][nriv][R]   routed flow series kept for the moment sums (null without observed flow)
     // objective accumulators [nriv][B]
     double *sse, *lsse;
+    double *sq, *sqq, *sqo;         // sums over the valid steps of q, q*q, q*qobs (KGE, PBIAS)
     int32_t *bad;                   // [nriv][B] non-finite flow seen
     // per member
     int32_t *status;                // [B]

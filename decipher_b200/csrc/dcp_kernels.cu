@@ -270,6 +270,7 @@ k_init_members(DevCatchment C, DevBatch W, double *__restrict__ mcpar /*[npt x 7
     for (int r = lane; r < C.nriv; r += 32) {
         W.sse[r * (size_t)B + m] = 0.0;
         W.lsse[r * (size_t)B + m] = 0.0;
+        W.sq[r * (size_t)B + m] = 0.0; W.sqq[r * (size_t)B + m] = 0.0; W.sqo[r * (size_t)B + m] = 0.0;
         W.bad[r * (size_t)B + m] = 0;
     }
     if (lane == 0) {
@@ -535,6 +536,7 @@ k_route_gauge(DevCatchment C, DevBatch W, int t0, int t1, double *__restrict__ q
         const size_t o2 = ((size_t)m * C.nriv + i) * W.R + (t & W.Rmask);
         W.d2[o2] = d2;
         W.dl2[o2] = dl2;
+        W.qs[o2] = q;
     }
 }
 
@@ -547,13 +549,24 @@ k_objective_sum(DevCatchment C, DevBatch W, int t0, int t1) {
     if (m >= W.B) return;
     const double *d2 = W.d2 + ((size_t)m * C.nriv + i) * W.R;
     const double *dl2 = W.dl2 + ((size_t)m * C.nriv + i) * W.R;
-    double sse = W.sse[i * (size_t)W.B + m], lsse = W.lsse[i * (size_t)W.B + m];
+    const double *qs = W.qs + ((size_t)m * C.nriv + i) * W.R;
+    const size_t a = i * (size_t)W.B + m;
+    double sse = W.sse[a], lsse = W.lsse[a], sq = W.sq[a], sqq = W.sqq[a], sqo = W.sqo[a];
+    const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
     for (int t = t0; t < t1; ++t) {
         sse = sse + d2[t & W.Rmask];
         lsse = lsse + dl2[t & W.Rmask];
+        if (t >= C.t_warm && t < n_t) {                         // moment sums over the valid steps only
+            const double o = C.qobs[(size_t)t * C.nriv + i];
+            if (o != C.flow_err) {
+                const double q = qs[t & W.Rmask];
+                sq = sq + q;
+                sqq = sqq + q * q;
+                sqo = sqo + q * o;
+            }
+        }
     }
-    W.sse[i * (size_t)W.B + m] = sse;
-    W.lsse[i * (size_t)W.B + m] = lsse;
+    W.sse[a] = sse; W.lsse[a] = lsse; W.sq[a] = sq; W.sqq[a] = sqq; W.sqo[a] = sqo;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -603,13 +616,29 @@ k_finalize(DevCatchment C, DevBatch W, double *__restrict__ perf, double *__rest
         const int bad = W.bad[g * (size_t)B + m];
         if (bad) st |= DCP_ST_NONFINITE;
         if (perf) {
-            double nse = nan, lnse = nan;
+            double nse = nan, lnse = nan, kge = nan, pbias = nan, rmse = nan;
             if (C.qobs && !bad && C.obs[g].n > 0) {
-                nse = 1.0 - W.sse[g * (size_t)B + m] / C.obs[g].sst;
-                lnse = 1.0 - W.lsse[g * (size_t)B + m] / C.obs[g].lsst;
+                const ObsStat os = C.obs[g];
+                const size_t a = g * (size_t)B + m;
+                const double sse = W.sse[a], sq = W.sq[a];
+                nse = 1.0 - sse / os.sst;
+                lnse = 1.0 - W.lsse[a] / os.lsst;
+                // KGE (Gupta et al. 2009) from the moment sums, PBIAS, RMSE: DESIGN.md "Objective"
+                const double nn = (double)os.n;
+                const double mean_s = sq / nn;
+                const double var_s = W.sqq[a] / nn - mean_s * mean_s;
+                const double var_o = os.sst / nn;
+                const double cov = W.sqo[a] / nn - mean_s * os.mean;
+                const double r = cov / sqrt(var_s * var_o);
+                const double alpha = sqrt(var_s / var_o);
+                const double beta = mean_s / os.mean;
+                kge = 1.0 - sqrt(((r - 1.0) * (r - 1.0) + (alpha - 1.0) * (alpha - 1.0)) + (beta - 1.0) * (beta - 1.0));
+                pbias = (100.0 * (sq - os.sum)) / os.sum;
+                rmse = sqrt(sse / nn);
             }
-            perf[((size_t)m * nriv + g) * DCP_NMEASURE + 0] = nse;
-            perf[((size_t)m * nriv + g) * DCP_NMEASURE + 1] = lnse;
+            double *pf = perf + ((size_t)m * nriv + g) * DCP_NMEASURE;
+            pf[DCP_PERF_NSE] = nse; pf[DCP_PERF_LOGNSE] = lnse; pf[DCP_PERF_KGE] = kge;
+            pf[DCP_PERF_PBIAS] = pbias; pf[DCP_PERF_RMSE] = rmse;
         }
     }
     if (totals) {

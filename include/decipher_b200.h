@@ -34,7 +34,7 @@
 extern "C" {
 #endif
 
-#define DCP_ABI_VERSION 1
+#define DCP_ABI_VERSION 2   /* 2: DCP_NMEASURE 2 -> 5 (layout of perf_out) and dcp_route_timeseries */
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define DCP_OK               0
@@ -71,8 +71,13 @@ extern "C" {
                                            dynamic_dist matrix is dense) + physics over (HRU, member) +
                                            ordered river sums; any nac, no balance checks              */
 
-/* number of performance measures per (gauge, member): 1 = NSE, 2 = log-NSE */
-#define DCP_NMEASURE 2
+/* performance measures per (gauge, member), in this order (definitions: DESIGN.md "Objective"; none exists upstream) */
+#define DCP_NMEASURE 5
+#define DCP_PERF_NSE    0   /* Nash-Sutcliffe efficiency                                  */
+#define DCP_PERF_LOGNSE 1   /* NSE of ln(max(x, mean_obs/100))                            */
+#define DCP_PERF_KGE    2   /* Kling-Gupta efficiency (2009 form: r, sigma ratio, mean ratio) */
+#define DCP_PERF_PBIAS  3   /* 100 * sum(sim - obs) / sum(obs)                            */
+#define DCP_PERF_RMSE   4   /* root mean square error, m/timestep                         */
 
 /*
  * Static description of one catchment: everything the reference holds after
@@ -180,7 +185,7 @@ int  dcp_catchment_destroy(dcp_catchment *c);
  *                 dyna_init_satzone.f90:203-206 rewrites mcpar(ipar,4).
  *   q_out         [nriv x nstep x n_member] or NULL — routed flow q(iriv,it) in m/timestep
  *                 (dyna_river.f90:57-59), the numbers write_output prints to the .flow file.
- *   perf_out      [DCP_NMEASURE x nriv x n_member] or NULL — NSE, log-NSE (extension).
+ *   perf_out      [DCP_NMEASURE x nriv x n_member] or NULL — NSE, log-NSE, KGE, PBIAS, RMSE (extension).
  *   reach_totals  [3 x nriv x n_member] or NULL — precip, PET, actual-ET totals per reach in mm
  *                 (dyna_write_output.f90:61-77).
  *   init_diag     [3 x n_member] or NULL — mean_q_ac_weighted, qb_tmp, mean_q_ac_weighted_guess

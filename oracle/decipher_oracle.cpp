@@ -572,10 +572,15 @@ void run_member(const Ctx &c, double *mcpar /*[npt x 7]*/, int flags, double *q 
 //   mean_o = sum_V qobs / |V|, eps = mean_o/100, sums ascending in t.
 //   NSE    = 1 - sum_V (q-qobs)^2 / sum_V (qobs-mean_o)^2
 //   logNSE = same on ln(max(x, eps)).
+//   KGE    = 1 - sqrt((r-1)^2 + (alpha-1)^2 + (beta-1)^2) (Gupta et al. 2009) from the moment sums
+//            sq = sum_V q, sqq = sum_V q*q, sqo = sum_V q*qobs:  mean_s = sq/n, var_s = sqq/n - mean_s^2,
+//            var_o = sst/n, cov = sqo/n - mean_s*mean_o, r = cov/sqrt(var_s*var_o), alpha = sqrt(var_s/var_o),
+//            beta = mean_s/mean_o
+//   PBIAS  = 100*(sq - sum_V qobs)/sum_V qobs,   RMSE = sqrt(sse/n).
 // |V| = 0, or any non-finite simulated flow at the gauge => NaN.
 struct ObsStats {
     int n = 0;
-    double mean = 0, sst = 0, eps = 0, lmean = 0, lsst = 0;
+    double mean = 0, sst = 0, eps = 0, lmean = 0, lsst = 0, sum = 0;
 };
 
 inline double lclip(double x, double eps) { return std::log(x > eps ? x : eps); }
@@ -588,6 +593,7 @@ ObsStats obs_stats(const dcp_catchment_desc *d, int g) {
         const double o = d->qobs[(size_t)t * d->nriv + g];
         if (o != d->flow_err) { sum = sum + o; s.n++; }
     }
+    s.sum = sum;
     if (s.n == 0) return s;
     s.mean = sum / s.n;
     s.eps = s.mean / 100;
@@ -611,12 +617,12 @@ ObsStats obs_stats(const dcp_catchment_desc *d, int g) {
 }
 
 void objective(const dcp_catchment_desc *d, const std::vector<ObsStats> &os, const double *q,
-               double *perf /*[2 x nriv]*/) {
+               double *perf /*[DCP_NMEASURE x nriv]*/) {
     const double nan = std::numeric_limits<double>::quiet_NaN();
     const int n_t = std::min(d->nstep, d->nstep_obs);
     for (int g = 0; g < d->nriv; ++g) {
         const ObsStats &s = os[g];
-        double sse = 0, lsse = 0;
+        double sse = 0, lsse = 0, sq = 0, sqq = 0, sqo = 0;
         bool bad = false;
         for (int t = 0; t < d->nstep; ++t)
             if (!std::isfinite(q[(size_t)t * d->nriv + g])) { bad = true; break; }
@@ -627,13 +633,27 @@ void objective(const dcp_catchment_desc *d, const std::vector<ObsStats> &os, con
             sse = sse + (x - o) * (x - o);
             const double dl = lclip(x, s.eps) - lclip(o, s.eps);
             lsse = lsse + dl * dl;
+            sq = sq + x;
+            sqq = sqq + x * x;
+            sqo = sqo + x * o;
         }
+        double *pf = perf + (size_t)DCP_NMEASURE * g;
         if (bad || s.n == 0) {
-            perf[0 + 2 * g] = nan;
-            perf[1 + 2 * g] = nan;
+            for (int k = 0; k < DCP_NMEASURE; ++k) pf[k] = nan;
         } else {
-            perf[0 + 2 * g] = 1 - sse / s.sst;
-            perf[1 + 2 * g] = 1 - lsse / s.lsst;
+            pf[DCP_PERF_NSE] = 1 - sse / s.sst;
+            pf[DCP_PERF_LOGNSE] = 1 - lsse / s.lsst;
+            const double nn = (double)s.n;
+            const double mean_s = sq / nn;
+            const double var_s = sqq / nn - mean_s * mean_s;
+            const double var_o = s.sst / nn;
+            const double cov = sqo / nn - mean_s * s.mean;
+            const double r = cov / std::sqrt(var_s * var_o);
+            const double alpha = std::sqrt(var_s / var_o);
+            const double beta = mean_s / s.mean;
+            pf[DCP_PERF_KGE] = 1.0 - std::sqrt(((r - 1.0) * (r - 1.0) + (alpha - 1.0) * (alpha - 1.0)) + (beta - 1.0) * (beta - 1.0));
+            pf[DCP_PERF_PBIAS] = (100.0 * (sq - s.sum)) / s.sum;
+            pf[DCP_PERF_RMSE] = std::sqrt(sse / nn);
         }
     }
 }

@@ -17,7 +17,7 @@ module decipher_c_api
     integer(c_int32_t), parameter :: DCP_ST_SOLFLAG_MASK = 3, DCP_ST_RZ_BALANCE = 4, DCP_ST_TS_OUTSUM = 8, &
                                      DCP_ST_TS_WBAL = 16, DCP_ST_NONFINITE = 32, DCP_ST_INIT_ITERCAP = 64, &
                                      DCP_ST_HIST_DROPPED = 128
-    integer(c_int), parameter :: DCP_NMEASURE = 2
+    integer(c_int), parameter :: DCP_NMEASURE = 5   ! NSE, log-NSE, KGE, PBIAS, RMSE
 
     type, bind(C) :: dcp_catchment_desc
         integer(c_int32_t) :: struct_size, nac, nriv, npt, nstep, ngp, nge, ntt
@@ -59,7 +59,7 @@ module decipher_c_api
             import :: c_int, c_ptr
             type(c_ptr), value :: handle
         end function
-        ! mcpar(npt,7,n_member) in/out; q_out(nriv,nstep,n_member); perf_out(2,nriv,n_member);
+        ! mcpar(npt,7,n_member) in/out; q_out(nriv,nstep,n_member); perf_out(DCP_NMEASURE,nriv,n_member);
         ! reach_totals(3,nriv,n_member); init_diag(3,n_member); status(n_member).  Pass c_null_ptr to skip an output.
         integer(c_int) function dcp_run_ensemble(handle, first_member, n_member, mcpar, opts, q_out, perf_out, &
                                                  reach_totals, init_diag, status) bind(C, name="dcp_run_ensemble")
@@ -69,6 +69,16 @@ module decipher_c_api
             type(c_ptr), value :: mcpar
             type(dcp_run_opts), intent(in) :: opts
             type(c_ptr), value :: q_out, perf_out, reach_totals, init_diag, status
+        end function
+        ! standalone router (DTA/route_run_standalone.f90): velocity(n_series) in metres per timestep
+        ! (tdh%v_param(1)); inflow(nriv,nstep,n_series) -> routed(nriv,nstep,n_series); status(n_series) or c_null_ptr
+        integer(c_int) function dcp_route_timeseries(handle, n_series, velocity, inflow, routed, status, flags) &
+                                                     bind(C, name="dcp_route_timeseries")
+            import :: c_int, c_int32_t, c_int64_t, c_ptr
+            type(c_ptr), value :: handle
+            integer(c_int64_t), value :: n_series
+            type(c_ptr), value :: velocity, inflow, routed, status
+            integer(c_int32_t), value :: flags
         end function
     end interface
 end module decipher_c_api
