@@ -540,33 +540,52 @@ k_route_gauge(DevCatchment C, DevBatch W, int t0, int t1, double *__restrict__ q
     }
 }
 
-// K3c: sums of the objective terms in ascending time order (one thread per member x gauge; adding the
-// zero of a masked step leaves the sum unchanged, so the result equals a sum over the valid steps only)
-__global__ void __launch_bounds__(128)
+// K3c: sums of the objective terms in ascending time order.  Adding the zero of a masked step leaves a sum
+// unchanged, so every result equals the oracle's sum over the valid steps only, term by term in the same order.
+// One warp = 32 consecutive members of one gauge.  The three series of a member are time-fastest, so a tile of
+// 32 members x 32 steps is read with coalesced 256-byte row loads into shared memory and then walked by
+// lane = member along time (conflict-free: row pitch 33), five independent ordered chains per lane.
+#define OBJ_T 32
+__global__ void __launch_bounds__(32)
 k_objective_sum(DevCatchment C, DevBatch W, int t0, int t1) {
-    const int m = blockIdx.x * blockDim.x + threadIdx.x;
-    const int i = blockIdx.y;
-    if (m >= W.B) return;
-    const double *d2 = W.d2 + ((size_t)m * C.nriv + i) * W.R;
-    const double *dl2 = W.dl2 + ((size_t)m * C.nriv + i) * W.R;
-    const double *qs = W.qs + ((size_t)m * C.nriv + i) * W.R;
-    const size_t a = i * (size_t)W.B + m;
-    double sse = W.sse[a], lsse = W.lsse[a], sq = W.sq[a], sqq = W.sqq[a], sqo = W.sqo[a];
+    __shared__ double s_d2[32][OBJ_T + 1], s_dl2[32][OBJ_T + 1], s_q[32][OBJ_T + 1], s_o[OBJ_T];
+    const int lane = threadIdx.x, i = blockIdx.y;
+    const int m_base = blockIdx.x * 32, m = m_base + lane;
+    const int rows = min(32, W.B - m_base);
     const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
-    for (int t = t0; t < t1; ++t) {
-        sse = sse + d2[t & W.Rmask];
-        lsse = lsse + dl2[t & W.Rmask];
-        if (t >= C.t_warm && t < n_t) {                         // moment sums over the valid steps only
-            const double o = C.qobs[(size_t)t * C.nriv + i];
-            if (o != C.flow_err) {
-                const double q = qs[t & W.Rmask];
-                sq = sq + q;
-                sqq = sqq + q * q;
-                sqo = sqo + q * o;
+    const size_t a = i * (size_t)W.B + (m < W.B ? m : m_base);
+    double sse = W.sse[a], lsse = W.lsse[a], sq = W.sq[a], sqq = W.sqq[a], sqo = W.sqo[a];
+    for (int tb = t0; tb < t1; tb += OBJ_T) {
+        const int t = tb + lane;
+        const bool in = t < t1;
+        const size_t col = (size_t)(t & W.Rmask);
+        for (int r = 0; r < rows; ++r) {                         // coalesced: lanes along time
+            const size_t o = ((size_t)(m_base + r) * C.nriv + i) * W.R + col;
+            s_d2[r][lane] = in ? W.d2[o] : 0.0;
+            s_dl2[r][lane] = in ? W.dl2[o] : 0.0;
+            s_q[r][lane] = in ? W.qs[o] : 0.0;
+        }
+        double ov = C.flow_err;                                  // masked steps carry the missing-data code
+        if (in && t >= C.t_warm && t < n_t) ov = C.qobs[(size_t)t * C.nriv + i];
+        s_o[lane] = ov;
+        __syncwarp();
+        if (lane < rows) {
+#pragma unroll 8
+            for (int k = 0; k < OBJ_T; ++k) {                    // lanes along members, ascending time
+                sse = sse + s_d2[lane][k];
+                lsse = lsse + s_dl2[lane][k];
+                const double o = s_o[k];
+                if (o != C.flow_err) {                           // moment sums over the valid steps only
+                    const double q = s_q[lane][k];
+                    sq = sq + q;
+                    sqq = sqq + q * q;
+                    sqo = sqo + q * o;
+                }
             }
         }
+        __syncwarp();
     }
-    W.sse[a] = sse; W.lsse[a] = lsse; W.sq[a] = sq; W.sqq[a] = sqq; W.sqo[a] = sqo;
+    if (m < W.B) { W.sse[a] = sse; W.lsse[a] = lsse; W.sq[a] = sq; W.sqq[a] = sqq; W.sqo[a] = sqo; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -738,8 +757,8 @@ void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, 
     k_route_conv<<<g1, ROUTE_CH, use_smem ? smem : 0, s>>>(C, W, t0, t1, use_smem);
     k_route_gauge<<<g2, ROUTE_CH, 0, s>>>(C, W, t0, t1, q_out);
     if (C.qobs != nullptr) {
-        dim3 g3(cdiv(W.B, 128), C.nriv);
-        k_objective_sum<<<g3, 128, 0, s>>>(C, W, t0, t1);
+        dim3 g3(cdiv(W.B, 32), C.nriv);
+        k_objective_sum<<<g3, 32, 0, s>>>(C, W, t0, t1);
     }
 }
 
