@@ -39,8 +39,10 @@ def test_cli_matches_oracle(tmp_path):
         assert [float(x) for x in res[j + 1].split()] == pytest.approx(list(ref["reach_totals"][2, :, m]), abs=5.1e-3)
     raw_tab = open(p.out_prefix + "ensemble_perf.bin", "rb").read()
     hdr = np.frombuffer(raw_tab[:24], dtype=np.int64)
-    assert hdr.tolist() == [6, 2, 2]
-    perf = np.frombuffer(raw_tab[24:24 + 8 * 24], dtype=np.float64).reshape((2, 2, 6), order="F")
-    ok = ~np.isnan(ref["perf"])
-    assert np.allclose(1 - perf[ok], 1 - ref["perf"][ok], rtol=1e-9, atol=0)
+    from decipher_b200.capi import NMEASURE
+    from parity import compare_perf
+    assert hdr.tolist() == [6, 2, NMEASURE]
+    n = NMEASURE * 2 * 6
+    perf = np.frombuffer(raw_tab[24:24 + 8 * n], dtype=np.float64).reshape((NMEASURE, 2, 6), order="F")
+    compare_perf(perf, ref["perf"])
     p.close()

@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from decipher_b200 import synth
-from decipher_b200.capi import (DeviceCatchment, KERNEL_STREAMED, OPT_CHECK_BALANCE, OPT_FAST_MATH)
+from decipher_b200.capi import (DeviceCatchment, KERNEL_STREAMED, NMEASURE, OPT_CHECK_BALANCE, OPT_FAST_MATH)
 from oracle_binding import oracle_run
 from parity import compare_close, compare_flows, compare_perf
 
@@ -81,7 +81,7 @@ def test_device_buffers_and_stats():
     ref = oracle_run(cat, mc.copy(order="F"), want_q=False, want_totals=False)
     dev = DeviceCatchment(cat)
     t_mc = torch.from_numpy(np.ascontiguousarray(mc.transpose(2, 1, 0))).cuda()     # (M, 7, npt) C-order == (npt,7,M) F-order
-    t_perf = torch.empty((M, cat.nriv, 2), dtype=torch.float64, device="cuda")
+    t_perf = torch.empty((M, cat.nriv, NMEASURE), dtype=torch.float64, device="cuda")
     t_status = torch.empty(M, dtype=torch.int32, device="cuda")
     st = dev.run_device(t_mc.data_ptr(), M, perf_ptr=t_perf.data_ptr(), status_ptr=t_status.data_ptr())
     torch.cuda.synchronize()
