@@ -64,6 +64,17 @@
 #else
 #define R2_DBG false
 #endif
+#ifndef R2_NACC
+#define R2_NACC 4                     // partial sums per member slot in the gather
+#endif
+#ifndef R2_GATHER_UNROLL
+#define R2_GATHER_UNROLL 1            // x R2_NACC entries per iteration of the gather loop.  Measured on C2 (gpurun_out/y1,y2_variants.log):
+                                      // 1/2/4/8/16 entries per iteration = 4.86/5.38/5.52/5.48/5.27e10 units/s: 4 balance the
+                                      // loads in flight against the size of the loop body (instruction-cache misses)
+#endif
+#if DCP_RES2_GB != 1
+#error "the gather walks its list one entry at a time (DCP_RES2_GB == 1)"
+#endif
 #define R2_S 2                        // member slots per team
 #define R2_H 4                        // columns per compute thread
 #ifndef R2_CARRY_E1
@@ -203,17 +214,35 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #else
                         const int nb = (ci[j].x >> 20) / GB;                            // K / batch, warp-uniform
 #endif
-                        double q0 = 0.0, q1 = 0.0;
-                        for (int bb = 0; bb < nb; ++bb) {
-                            double wc[GB]; double2 qv[GB];
+                        // R2_NACC independent partial sums per member slot: a row of K entries is K dependent DFMAs per
+                        // slot otherwise (8.9 cycles each), the longest chain of the gather phase
+                        double qa[R2_NACC][2];
 #pragma unroll
-                            for (int u = 0; u < GB; ++u) { wc[u] = wv[u]; qv[u] = lds_tuple(__double2loint(wc[u]), qcur_u32); }
-                            ep += GB * 32;
+                        for (int u = 0; u < R2_NACC; ++u) { qa[u][0] = 0.0; qa[u][1] = 0.0; }
+                        constexpr int GU = R2_GATHER_UNROLL;
+                        int bb = 0;
+#pragma unroll GU
+                        for (; bb + R2_NACC <= nb; bb += R2_NACC) {
 #pragma unroll
-                            for (int u = 0; u < GB; ++u) wv[u] = ep[u * 32];
-#pragma unroll
-                            for (int u = 0; u < GB; ++u) { q0 = fma(qv[u].x, wc[u], q0); q1 = fma(qv[u].y, wc[u], q1); }
+                            for (int u = 0; u < R2_NACC; ++u) {
+                                const double wc = wv[0];
+                                const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
+                                ep += 32;
+                                wv[0] = ep[0];
+                                qa[u][0] = fma(qv.x, wc, qa[u][0]); qa[u][1] = fma(qv.y, wc, qa[u][1]);
+                            }
                         }
+#pragma unroll 1
+                        for (; bb < nb; ++bb) {
+                            const double wc = wv[0];
+                            const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
+                            ep += 32;
+                            wv[0] = ep[0];
+                            qa[0][0] = fma(qv.x, wc, qa[0][0]); qa[0][1] = fma(qv.y, wc, qa[0][1]);
+                        }
+                        double q0 = qa[0][0], q1 = qa[0][1];
+#pragma unroll
+                        for (int u = 1; u < R2_NACC; ++u) { q0 += qa[u][0]; q1 += qa[u][1]; }
                         qin[j][0] = q0; qin[j][1] = q1;
                     }
                     // ---- root zone, unsaturated zone, saturated zone: 4 interleaved dependency chains ----
@@ -253,7 +282,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                             any_slow |= lo[jj][k].slow;
                         }
                     }
-                    if (any_slow) {                                                     // rare: sd > smax, out-of-range exponent
+                    if (__builtin_expect(any_slow, 0)) {                                                     // rare: sd > smax, out-of-range exponent
 #pragma unroll
                         for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
