@@ -559,11 +559,18 @@ k_objective_sum(DevCatchment C, DevBatch W, int t0, int t1) {
         const int t = tb + lane;
         const bool in = t < t1;
         const size_t col = (size_t)(t & W.Rmask);
-        for (int r = 0; r < rows; ++r) {                         // coalesced: lanes along time
-            const size_t o = ((size_t)(m_base + r) * C.nriv + i) * W.R + col;
-            s_d2[r][lane] = in ? W.d2[o] : 0.0;
-            s_dl2[r][lane] = in ? W.dl2[o] : 0.0;
-            s_q[r][lane] = in ? W.qs[o] : 0.0;
+        for (int r0 = 0; r0 < rows; r0 += 8) {                   // coalesced: lanes along time; 24 loads in flight
+            double a[8], b[8], c[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const bool ok = in && r0 + u < rows;
+                const size_t o = ((size_t)(m_base + min(r0 + u, rows - 1)) * C.nriv + i) * W.R + col;
+                a[u] = ok ? W.d2[o] : 0.0;
+                b[u] = ok ? W.dl2[o] : 0.0;
+                c[u] = ok ? W.qs[o] : 0.0;
+            }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { s_d2[r0 + u][lane] = a[u]; s_dl2[r0 + u][lane] = b[u]; s_q[r0 + u][lane] = c[u]; }
         }
         double ov = C.flow_err;                                  // masked steps carry the missing-data code
         if (in && t >= C.t_warm && t < n_t) ov = C.qobs[(size_t)t * C.nriv + i];
