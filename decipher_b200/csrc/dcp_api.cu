@@ -15,6 +15,7 @@
 #include <cstdlib>
 #include <limits>
 #include <string>
+#include <functional>
 #include <vector>
 
 namespace {
@@ -118,6 +119,8 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     std::vector<double> ell_w;
     std::vector<uint16_t> ell_src;
     const bool schedule = !getenv("DCP_RES_NO_ELLSCHED");
+    int zero_tuple[8] = {-1, -1, -1, -1, -1, -1, -1, -1};            // an idle thread position per bank class
+    for (int pos = 0; pos < nac_pad; ++pos) if (thread_hru[pos] < 0 && zero_tuple[pos & 7] < 0) zero_tuple[pos & 7] = pos;
     for (int pb = 0; pb < npb; ++pb) {
         int K = 0;
         for (int l = 0; l < 32; ++l) {
@@ -136,47 +139,101 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
                 if (hh >= 0) for (int x = hru[hh].row_beg; x < hru[hh].row_end; ++x) rem[l].push_back(x);
             }
             for (int k = 0; k < K; ++k) {
-                int used[8] = {0, 0, 0, 0, 0, 0, 0, 0};                 // lanes per bank class at this step
+                // One LDS.128 of a quarter-warp costs as many wavefronts as its most loaded 16-byte bank class.  Per step:
+                // a maximum bipartite matching lanes -> classes (Kuhn's augmenting paths, rows without spare steps first)
+                // over the classes each row still has entries in; a row that stays unmatched waits if it has spare steps,
+                // and every waiting or finished row reads a zero-weight entry on a tuple of a still unused class.
+                const int left = K - k;                                  // steps left including this one
+                int owner[8];                                            // class -> lane
+                int cls_of[8];                                           // lane -> class
+                for (int c = 0; c < 8; ++c) { owner[c] = -1; cls_of[c] = -1; }
+                bool has[8][8];
+                for (int l = 0; l < 8; ++l) {
+                    for (int c = 0; c < 8; ++c) has[l][c] = false;
+                    for (int x : rem[l]) has[l][hru_pos[w[x].src] & 7] = true;
+                }
                 int order[8] = {0, 1, 2, 3, 4, 5, 6, 7};
-                std::stable_sort(order, order + 8, [&](int a, int b) { return rem[a].size() > rem[b].size(); });
-                for (int oi = 0; oi < 8; ++oi) {
-                    const int l = order[oi], pos = pb * 32 + q * 8 + l;
-                    const size_t o = base + (size_t)k * 32 + q * 8 + l;
-                    const int left = K - k;                              // steps left including this one
-                    int pick = -1;
-                    if (!rem[l].empty()) {
-                        if (!schedule) pick = 0;
-                        else {
-                            int best = 1 << 30;
-                            for (size_t x = 0; x < rem[l].size(); ++x) {
-                                const int cls = hru_pos[w[rem[l][x]].src] & 7;
-                                if (used[cls] < best) { best = used[cls]; pick = (int)x; }
-                            }
-                            // a row with spare steps may wait (zero-weight entry on its own tuple) rather than collide
-                            if (best > 0 && (int)rem[l].size() < left && used[pos & 7] == 0) pick = -1;
-                        }
+                std::stable_sort(order, order + 8, [&](int a, int b) { return left - (int)rem[a].size() < left - (int)rem[b].size(); });
+                std::function<bool(int, bool *)> augment = [&](int l, bool *seen) {
+                    for (int c = 0; c < 8; ++c) {
+                        if (!has[l][c] || seen[c]) continue;
+                        seen[c] = true;
+                        if (owner[c] < 0 || augment(owner[c], seen)) { owner[c] = l; cls_of[l] = c; return true; }
                     }
-                    if (pick >= 0) {
+                    return false;
+                };
+                if (schedule)
+                    for (int oi = 0; oi < 8; ++oi) {
+                        const int l = order[oi];
+                        if (rem[l].empty()) continue;
+                        bool seen[8] = {false, false, false, false, false, false, false, false};
+                        augment(l, seen);
+                    }
+                int load[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                for (int c = 0; c < 8; ++c) if (owner[c] >= 0) load[c] = 1;
+                for (int oi = 0; oi < 8; ++oi) {                        // rows that could not get a class of their own
+                    const int l = order[oi];
+                    if (rem[l].empty() || cls_of[l] >= 0) continue;
+                    if (schedule && (int)rem[l].size() < left) continue; // spare steps: wait
+                    int best = -1;                                       // must advance: the least loaded class it has
+                    for (int c = 0; c < 8; ++c) if (has[l][c] && (best < 0 || load[c] < load[best])) best = c;
+                    if (!schedule) best = hru_pos[w[rem[l][0]].src] & 7;
+                    cls_of[l] = best; load[best]++;
+                }
+                for (int l = 0; l < 8; ++l) {
+                    const int pos = pb * 32 + q * 8 + l;
+                    const size_t o = base + (size_t)k * 32 + q * 8 + l;
+                    if (cls_of[l] >= 0) {
+                        size_t pick = 0;
+                        while ((hru_pos[w[rem[l][pick]].src] & 7) != cls_of[l]) ++pick;
                         const WEntry &we = w[rem[l][pick]];
                         ell_w[o] = we.w * we.ac_src; ell_src[o] = (uint16_t)hru_pos[we.src];
-                        used[hru_pos[we.src] & 7]++;
                         rem[l].erase(rem[l].begin() + pick);
                     } else {
-                        ell_w[o] = 0.0; ell_src[o] = (uint16_t)pos;    // padding: zero weight on the own tuple
-                        used[pos & 7]++;
+                        // zero weight on an idle position's tuple (always 0.0, so nothing non-finite can leak from another
+                        // HRU) of the least loaded class; without a suitable idle position, on the row's own tuple
+                        int best = -1;
+                        for (int c = 0; c < 8; ++c) if (zero_tuple[c] >= 0 && (best < 0 || load[c] < load[best])) best = c;
+                        if (best >= 0 && load[best] > load[pos & 7]) best = -1;
+                        const int src = best >= 0 ? zero_tuple[best] : pos;
+                        load[src & 7]++;
+                        ell_w[o] = 0.0; ell_src[o] = (uint16_t)src;
                     }
                 }
             }
         }
     }
     // ---- contribution slots: river-major, ascending HRU inside a river; idle positions after the last river ----
+    // The order inside a river's range is free (the river warps add the whole range), so the slots are handed out per
+    // quarter-warp of thread positions with distinct 16-byte bank classes (slot mod 8) wherever the ranges allow: the
+    // compute threads' STS.128 into the slot array is then close to conflict-free (it was 10 wavefronts for 4).
     std::vector<int32_t> rank(nac_pad, 0), rbeg(nriv + 1, 0);
     int slot = 0;
     for (int r = 0; r < nriv; ++r) {
-        for (int ia = 0; ia < nac; ++ia) if (hru[ia].ipriv == r) rank[hru_pos[ia]] = slot++;
+        for (int ia = 0; ia < nac; ++ia) if (hru[ia].ipriv == r) ++slot;
         rbeg[r + 1] = slot;
     }
-    for (int pos = 0; pos < nac_pad; ++pos) if (thread_hru[pos] < 0) rank[pos] = slot++;
+    {
+        const int n_rng = nriv + 1;                                   // last range: idle positions
+        std::vector<std::vector<std::vector<int>>> free_s(n_rng, std::vector<std::vector<int>>(8));
+        for (int r = 0; r < nriv; ++r) for (int x = rbeg[r + 1] - 1; x >= rbeg[r]; --x) free_s[r][x & 7].push_back(x);
+        for (int x = nac_pad - 1; x >= slot; --x) free_s[nriv][x & 7].push_back(x);
+        for (int q0 = 0; q0 < nac_pad; q0 += 8) {
+            bool used[8] = {false, false, false, false, false, false, false, false};
+            for (int pos = q0; pos < q0 + 8; ++pos) {
+                const int ia = thread_hru[pos], r = ia >= 0 ? hru[ia].ipriv : nriv;
+                int pick = -1;
+                for (int c = 0; c < 8; ++c)                           // an unused class with the most free slots
+                    if (!used[c] && !free_s[r][c].empty() && (pick < 0 || free_s[r][c].size() > free_s[r][pick].size())) pick = c;
+                if (pick < 0)
+                    for (int c = 0; c < 8; ++c)
+                        if (!free_s[r][c].empty() && (pick < 0 || free_s[r][c].size() > free_s[r][pick].size())) pick = c;
+                rank[pos] = free_s[r][pick].back();
+                free_s[r][pick].pop_back();
+                used[pick] = true;
+            }
+        }
+    }
 
     // ---- the 16 blocks of 32 columns are dealt to the 4 compute warps of a team longest-first ----
     std::vector<int> blocks(16), load(4, 0), cnt(4, 0);
@@ -224,8 +281,8 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
                 ci.z = (g * nac_pad + pos) | ((g * nac_pad) << 16);
                 ci.w = ((g * S * npt + (h ? h->ipar : 0)) * 2) | ((g * nac_pad + rank[pos]) << 16);
                 col_i[o] = ci;
-                col_d[2 * o + 0] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);
-                col_d[2 * o + 1] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);
+                col_d[o] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);                 // word-major: a warp's
+                col_d[(size_t)H * TC + o] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);     // LDS.128 spans 512 B
                 col_ia[o] = ia;
             }
         }

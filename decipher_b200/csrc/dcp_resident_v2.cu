@@ -91,7 +91,7 @@ struct R2Smem {                       // team-private views unless noted
     // shared by both teams (read-only after setup)
     double *ellw_s;       // [ell_len]       packed gather list (weight | source tuple index)
     int4 *coli_s;         // [4][128]        per (column slot j, team thread): packed indices
-    double2 *cold_s;      // [4][128][2]     {ac, 1/ac}, {cq, cos(mslp)}
+    double2 *cold_s;      // [2][4][128]     word 0: {ac, 1/ac}, word 1: {cq, cos(mslp)}; thread-fastest (16-byte lane stride)
     int32_t *rbeg_s;      // [nriv+1]
 };
 
@@ -139,7 +139,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
             const int4 ci = M.coli_s[j * R2_TC + tt_id];
             const int tup = ci.z & 0xffff, g = (ci.y >> 16) & 0x7fff;
             const int ia = P.col_ia[j * R2_TC + tt_id];
-            const double cosm = M.cold_s[(j * R2_TC + tt_id) * 2 + 1].y;
+            const double cosm = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id].y;
             const int ipar = ia >= 0 ? C.hru[ia].ipar : 0;
 #pragma unroll
             for (int k = 0; k < S; ++k) {
@@ -252,8 +252,8 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const int j = jp + jj;
-                        const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];      // {ac, 1/ac}
-                        const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];      // {cq, cos}
+                        const double2 d0 = M.cold_s[j * R2_TC + tt_id];      // {ac, 1/ac}
+                        const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];      // {cq, cos}
                         cq[jj] = d1.x;
                         const double p = forc_t[tt * C.ngp + (ci[j].y & 0xff)];
                         const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci[j].y >> 8) & 0xff)];   // already max(ep, 0)
@@ -289,8 +289,8 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                             for (int k = 0; k < S; ++k)
                                 if (lo[jj][k].slow) {
                                     const int j = jp + jj;
-                                    const double2 d0 = M.cold_s[(j * R2_TC + tt_id) * 2 + 0];
-                                    const double2 d1 = M.cold_s[(j * R2_TC + tt_id) * 2 + 1];
+                                    const double2 d0 = M.cold_s[j * R2_TC + tt_id];
+                                    const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];
                                     const double2 c0v = M.cst_s[((k * 2 + 0) * H + j) * R2_TC + tt_id];
                                     const double2 c1v = M.cst_s[((k * 2 + 1) * H + j) * R2_TC + tt_id];
                                     HruConst c;
