@@ -107,7 +107,7 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
             cq[ia] = C.dtt * hru[ia].w_riv * sh * hru[ia].ac;
         }
     const int G = COLS / nac_pad, npb = nac_pad / 32;
-    if (d->ngp > 255 || d->nge > 255 || G * S * npt * 2 + npt * 2 > 65535) return;
+    if (d->ngp > 255 || d->nge > 255 || G * S * npt * 3 + npt * 3 > 65535) return;
     Q.nac_pad = nac_pad; Q.G = G; Q.Tt = DCP_RES_TT;
     Q.phase_delay = getenv("DCP_RES_PHASE") ? atoi(getenv("DCP_RES_PHASE")) : 0;
 
@@ -258,7 +258,7 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     };
     std::vector<double> ent;
     std::vector<int4> col_i((size_t)H * TC);
-    std::vector<double2> col_d((size_t)H * TC * 2);
+    std::vector<double2> col_d((size_t)H * TC * 3);
     std::vector<int32_t> col_ia((size_t)H * TC, -1);
     for (int wi = 0; wi < 4; ++wi)
         for (int j = 0; j <= H; ++j) {
@@ -279,10 +279,11 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
                 ci.x = (int)(fbase + l) | (K << 20);
                 ci.y = (h ? h->ippt : 0) | ((h ? h->ipet : 0) << 8) | (g << 16) | (h ? 0 : (int)0x80000000u);
                 ci.z = (g * nac_pad + pos) | ((g * nac_pad) << 16);
-                ci.w = ((g * S * npt + (h ? h->ipar : 0)) * 2) | ((g * nac_pad + rank[pos]) << 16);
+                ci.w = ((g * S * npt + (h ? h->ipar : 0)) * 3) | ((g * nac_pad + rank[pos]) << 16);
                 col_i[o] = ci;
                 col_d[o] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);                 // word-major: a warp's
                 col_d[(size_t)H * TC + o] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);     // LDS.128 spans 512 B
+                col_d[(size_t)2 * H * TC + o] = make_double2(h ? 1.0 / h->cosm : 1.0, 0.0);
                 col_ia[o] = ia;
             }
         }
@@ -303,14 +304,14 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
     Q.off_ellw = take((size_t)Q.ell_len * 8);
     Q.off_coli = take((size_t)H * TC * 16);
-    Q.off_cold = take((size_t)H * TC * 32);
+    Q.off_cold = take((size_t)H * TC * 48);
     Q.off_rbeg = take((size_t)(nriv + 1) * 4);
     Q.off_team = (int)((off + 127) & ~(size_t)127);
     off = 0;
     Q.off_qbf = take((size_t)2 * COLS * 16);
     Q.off_con = take((size_t)2 * COLS * 16);
-    Q.off_cst = take((size_t)S * 2 * COLS * 16);
-    Q.off_par = take((size_t)G * S * npt * 2 * 16);
+    Q.off_cst = take((size_t)S * COLS * 16);
+    Q.off_par = take((size_t)G * S * npt * 3 * 16);
     Q.off_forc = take((size_t)2 * Q.Tt * (d->ngp + d->nge) * 8);
     Q.off_bar = take(16);
     Q.team_bytes = (int)((off + 8191) & ~(size_t)8191);     // team blocks (tuple buffers first) sit on 8 KB boundaries

@@ -84,14 +84,16 @@
 struct R2Smem {                       // team-private views unless noted
     double2 *qbf_s;       // [2][512]        baseflow tuples (2 member slots), double buffered in time
     double2 *con_s;       // [2][512]        river contributions by slot, double buffered in time
-    double2 *cst_s;       // [2][2][4][128]  {q0, q2}, {m2, 1/m2} per (member slot, word, column slot j, team thread)
-    double2 *par_s;       // [Mv][npt][2]    {srmax, 1/srmax}, {td, smax}
+    double2 *cst_s;       // [2][4][128]     {q0, q2} per (member slot, column slot j, team thread); m2 = szm/cos(mslp) and its
+                          //                 reciprocal are rebuilt from the member's {szm, 1/szm} and the column's {cos, 1/cos}:
+                          //                 two DMULs instead of an LDS.128 per unit and step, and 32 KB less shared memory
+    double2 *par_s;       // [Mv][npt][3]    {srmax, 1/srmax}, {td, smax}, {szm, 1/szm}
     double *forc_s;       // [2][Tt*(ngp+nge)]
     uint64_t *bars;       // [2]
     // shared by both teams (read-only after setup)
     double *ellw_s;       // [ell_len]       packed gather list (weight | source tuple index)
     int4 *coli_s;         // [4][128]        per (column slot j, team thread): packed indices
-    double2 *cold_s;      // [2][4][128]     word 0: {ac, 1/ac}, word 1: {cq, cos(mslp)}; thread-fastest (16-byte lane stride)
+    double2 *cold_s;      // [3][4][128]     word 0: {ac, 1/ac}, 1: {cq, cos(mslp)}, 2: {1/cos(mslp), -}; thread-fastest
     int32_t *rbeg_s;      // [nriv+1]
 };
 
@@ -119,7 +121,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
     constexpr int H = R2_H, S = R2_S;
     const int B = W.B, npt = C.npt;
     const int forc_stride = P.Tt * (C.ngp + C.nge);
-    const int par_kstride = npt * 2;
+    const int par_kstride = npt * 3;
     const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
     const int Mv = P.G * S;                                  // members per team group
     uint32_t tiles_done = 0;
@@ -145,14 +147,13 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
             for (int k = 0; k < S; ++k) {
                 const int m = m_base + g * S + k;
                 sd[j][k] = 1.0; suz[j][k] = 0.0; srz[j][k] = 0.0; aet[j][k] = 0.0;
-                double qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_m2 = 1.0, c_im2 = 1.0;
+                double qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_im2 = 1.0;
                 if (ia >= 0 && m < B) {
                     const size_t o = (size_t)ia * B + m;
                     sd[j][k] = W.sd[o]; suz[j][k] = W.suz[o]; srz[j][k] = W.srz[o];
                     c_q0 = W.q0[o]; c_q2 = W.q2[o];
                     const double szm = W.par[(0 * npt + ipar) * (size_t)B + m];
-                    c_m2 = szm / cosm;                       // dyna_satzone_analyticalsolver.f90:52
-                    c_im2 = cosm / szm;
+                    c_im2 = cosm * (1.0 / szm);              // 1/m2 exactly as the time loop rebuilds it (par_s x cold_s)
                     qb0 = W.qbf0[o];
                 }
 #if R2_CARRY_E1
@@ -160,21 +161,22 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #endif
                 reinterpret_cast<double *>(M.qbf_s + tup)[k] = qb0;                 // time buffer 0 = step 0's "old" qbf
                 reinterpret_cast<double *>(M.qbf_s + R2_COLS + tup)[k] = 0.0;
-                M.cst_s[((k * 2 + 0) * H + j) * R2_TC + tt_id] = make_double2(c_q0, c_q2);   // own-column table: [slot][word][column j][thread]
-                M.cst_s[((k * 2 + 1) * H + j) * R2_TC + tt_id] = make_double2(c_m2, c_im2);
+                M.cst_s[(k * H + j) * R2_TC + tt_id] = make_double2(c_q0, c_q2);    // own-column table: [slot][column j][thread]
             }
         }
         for (int i = tt_id; i < Mv * npt; i += R2_TC) {      // member parameters -> shared
             const int jm = i / npt, l = i % npt;
             const int m = m_base + jm;
-            double srmax = 1.0, td = 1.0, smax = 1.0;
+            double srmax = 1.0, td = 1.0, smax = 1.0, szm = 1.0;
             if (m < B) {
+                szm = W.par[(0 * npt + l) * (size_t)B + m];
                 srmax = W.par[(2 * npt + l) * (size_t)B + m];
                 td = W.par[(5 * npt + l) * (size_t)B + m];
                 smax = W.par[(6 * npt + l) * (size_t)B + m];
             }
-            M.par_s[i * 2 + 0] = make_double2(srmax, 1.0 / srmax);
-            M.par_s[i * 2 + 1] = make_double2(td, smax);
+            M.par_s[i * 3 + 0] = make_double2(srmax, 1.0 / srmax);
+            M.par_s[i * 3 + 1] = make_double2(td, smax);
+            M.par_s[i * 3 + 2] = make_double2(szm, 1.0 / szm);
         }
         team_sync(team);
 
@@ -254,18 +256,19 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                         const int j = jp + jj;
                         const double2 d0 = M.cold_s[j * R2_TC + tt_id];      // {ac, 1/ac}
                         const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];      // {cq, cos}
+                        const double icos = M.cold_s[2 * R2_H * R2_TC + j * R2_TC + tt_id].x;
                         cq[jj] = d1.x;
                         const double p = forc_t[tt * C.ngp + (ci[j].y & 0xff)];
                         const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci[j].y >> 8) & 0xff)];   // already max(ep, 0)
 #pragma unroll
                         for (int k = 0; k < S; ++k) {
-                            const double2 c0v = M.cst_s[((k * 2 + 0) * H + j) * R2_TC + tt_id];
-                            const double2 c1v = M.cst_s[((k * 2 + 1) * H + j) * R2_TC + tt_id];
+                            const double2 c0v = M.cst_s[(k * H + j) * R2_TC + tt_id];
                             const double2 p0 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride];
                             const double2 p1 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 1];
+                            const double2 p2 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 2];
                             HruConst c;
                             c.ac = d0.x; c.inv_ac = d0.y;
-                            c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = c1v.x; c.inv_m2 = c1v.y;
+                            c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = d1.y * p2.y;   // dyna_satzone_analyticalsolver.f90:52
                             c.q1 = c.q0 * d1.y;                                         // dyna_satzone_analyticalsolver.f90:49
                             c.srmax = p0.x; c.inv_srmax = p0.y; c.td = p1.x; c.smax = p1.y;
                             c.ims_rz = 1; c.ims_uz = 1;
@@ -291,11 +294,12 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                                     const int j = jp + jj;
                                     const double2 d0 = M.cold_s[j * R2_TC + tt_id];
                                     const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];
-                                    const double2 c0v = M.cst_s[((k * 2 + 0) * H + j) * R2_TC + tt_id];
-                                    const double2 c1v = M.cst_s[((k * 2 + 1) * H + j) * R2_TC + tt_id];
+                                    const double2 c0v = M.cst_s[(k * H + j) * R2_TC + tt_id];
+                                    const double2 p2 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 2];
+                                    const double icos = M.cold_s[2 * R2_H * R2_TC + j * R2_TC + tt_id].x;
                                     HruConst c;
                                     c.ac = d0.x; c.inv_ac = d0.y;
-                                    c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = c1v.x; c.inv_m2 = c1v.y;
+                                    c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = d1.y * p2.y;   // dyna_satzone_analyticalsolver.f90:52
                                     c.q1 = c.q0 * d1.y;
                                     c.smax = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 1].y;
                                     hru_step_lean_fixup(c, gc, qin[j][k], qin[j][k], sd[j][k], lo[jj][k]);
@@ -446,8 +450,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     for (int e = tid; e < P.ell_len; e += R2_THREADS) M.ellw_s[e] = P.ell_w[e];
     for (int i = tid; i < R2_H * R2_TC; i += R2_THREADS) {
         M.coli_s[i] = P.col_i[i];
-        M.cold_s[2 * i] = P.col_d[2 * i]; M.cold_s[2 * i + 1] = P.col_d[2 * i + 1];
     }
+    for (int i = tid; i < 3 * R2_H * R2_TC; i += R2_THREADS) M.cold_s[i] = P.col_d[i];
     for (int i = tid; i <= C.nriv; i += R2_THREADS) M.rbeg_s[i] = P.rbeg[i];
     if (!is_compute && (tid - R2_CT) % R2_TR == 0) {
         mbar_init(&M.bars[0], 1);
