@@ -122,7 +122,7 @@ program main
     desc%frac_sub_area = c_loc(f_frac); desc%river_data = c_loc(f_rivdata); desc%node_to_flow_mapping = c_loc(f_map)
     desc%rain = c_loc(r_gau_step); desc%pet = c_loc(pe_step)
     desc%qobs = c_null_ptr; desc%nstep_obs = 0; desc%t_warm = 0; desc%flow_err = -9999.0d0
-    ! (to get NSE / log-NSE, make Inputs return qobs_riv_step and flow_err_i and pass them here)
+    ! (to get the performance measures (NSE, log-NSE, KGE, PBIAS, RMSE), make Inputs return qobs_riv_step and flow_err_i and pass them here)
 
     if (dcp_catchment_create(desc, handle) /= DCP_OK) stop 'dcp_catchment_create failed'
 
