@@ -112,6 +112,36 @@ __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0,
 
 #define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})
 
+// Completes a unit whose lean step raised `slow` (sd > smax, exponent out of the fast range, non-finite): the generic
+// saturated-zone statements (hru_step_lean_fixup -> sat_zone_slow) from the saved inputs.  Kept OUT of the time loop's
+// body: it takes the shared-memory addresses of the unit's constant words instead of the constants themselves.
+struct R2Fix { double sd, e1, qbf, exac; };
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+static __device__ __noinline__ R2Fix r2_fix_unit(uint32_t cst_a, uint32_t par_a, uint32_t cold_a, double dtt, double inv_dtt,
+                                                 int ntt, double qin, double uz, double exus, double sd0) {
+    const double2 c0v = lds_d2(cst_a);                                   // {q0, q2}
+    const double2 p1 = lds_d2(par_a + 16), p2 = lds_d2(par_a + 32);      // {td, smax}, {szm, 1/szm}
+    const double2 d0 = lds_d2(cold_a), d1 = lds_d2(cold_a + R2_H * R2_TC * 16);
+    const double icos = lds_d2(cold_a + 2 * R2_H * R2_TC * 16).x;
+    HruConst c;
+    c.ac = d0.x; c.inv_ac = d0.y;
+    c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = d1.y * p2.y;
+    c.q1 = c.q0 * d1.y;
+    c.smax = p1.y;
+    LeanOut o;
+    o.uz = uz; o.exus = exus; o.sd0 = sd0;
+    double sd = sd0;
+    hru_step_lean_fixup(c, StepConst{0.0, dtt, inv_dtt, ntt}, qin, qin, sd, o);
+    R2Fix f;
+    f.sd = sd; f.qbf = o.qbf; f.exac = o.exac;
+    f.e1 = exp(sd * c.inv_m2);                                           // re-derive the carried exponential
+    return f;
+}
+
 // ---------------------------------------------------------------------------------------------
 // compute role: 4 warps per team, thread = 4 HRU columns x 2 member slots
 // ---------------------------------------------------------------------------------------------
@@ -292,19 +322,15 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                             for (int k = 0; k < S; ++k)
                                 if (lo[jj][k].slow) {
                                     const int j = jp + jj;
-                                    const double2 d0 = M.cold_s[j * R2_TC + tt_id];
-                                    const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];
-                                    const double2 c0v = M.cst_s[(k * H + j) * R2_TC + tt_id];
-                                    const double2 p2 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 2];
-                                    const double icos = M.cold_s[2 * R2_H * R2_TC + j * R2_TC + tt_id].x;
-                                    HruConst c;
-                                    c.ac = d0.x; c.inv_ac = d0.y;
-                                    c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = d1.y * p2.y;   // dyna_satzone_analyticalsolver.f90:52
-                                    c.q1 = c.q0 * d1.y;
-                                    c.smax = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 1].y;
-                                    hru_step_lean_fixup(c, gc, qin[j][k], qin[j][k], sd[j][k], lo[jj][k]);
+                                    // out of line (the loop body must stay small, see R2_GATHER_UNROLL): the unit's constants are
+                                    // re-read from shared memory inside
+                                    const R2Fix f = r2_fix_unit(smem_u32(M.cst_s + (k * H + j) * R2_TC + tt_id),
+                                                                smem_u32(M.par_s + (ci[j].w & 0xffff) + k * par_kstride),
+                                                                smem_u32(M.cold_s + j * R2_TC + tt_id), C.dtt, C.inv_dtt, C.ntt,
+                                                                qin[j][k], lo[jj][k].uz, lo[jj][k].exus, lo[jj][k].sd0);
+                                    sd[j][k] = f.sd; lo[jj][k].qbf = f.qbf; lo[jj][k].exac = f.exac;
 #if R2_CARRY_E1
-                                    e1s[j][k] = exp(sd[j][k] * c.inv_m2);               // re-derive the carried exponential
+                                    e1s[j][k] = f.e1;
 #endif
                                 }
                     }
