@@ -248,7 +248,8 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     // root_zone1 (dyna_root_zone1.f90:39-66)
     double srz = s.srz + p;
     const double pex = fm_relu(srz - c.srmax);
-    srz = fm_min(srz, c.srmax);
+    srz = srz - pex;                                      // min(srz, srmax): one DADD instead of a compare and two selects
+                                                          // (exact whenever srz <= 2 srmax, Sterbenz; an ulp of srz otherwise)
     double ea = epp * (srz * c.inv_srmax);
     ea = fm_min(fm_min(ea, epp), srz);
     srz = srz - ea;
@@ -257,11 +258,14 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     double suz = s.suz + pex;
     const double lim = fm_relu(sd0);
     const double exus = fm_relu(suz - lim);
-    suz = fm_min(suz, lim);
+    suz = suz - exus;                                     // min(suz, lim), as above
     const double den = sd0 * c.td;
     double uz2 = g.dt * LEAN_DIV(suz, den);
-    uz2 = fm_sel_gt(den, 1e-290, fm_min(uz2, suz), suz); // tiny sd*td: suz/(sd*td) overflows, clipped to suz
-    uz2 = fm_sel_gt(fm_min(sd0, suz), 0.0, uz2, 0.0);    // only when sd > 0 and suz > 0
+    // :60-68 drain at most what is there.  No guards are needed around the quotient: with sd <= 0 the store was just
+    // emptied (lim = 0, so suz = 0 and min(x, 0) = 0 for x = +-0 or NaN, because fm_min returns its second operand
+    // unless the first is smaller); with a vanishing sd*td the quotient is +inf or NaN and the same min returns suz,
+    // which is the reference's clip; with suz = 0 the quotient is 0
+    uz2 = fm_min(uz2, suz);
     suz = suz - uz2;
     const double fl = fm_sel_lt(suz, 0.0000001, suz, 0.0);   // :70-73 flush: what is left goes with the drainage
     uz2 = uz2 + fl;
@@ -288,14 +292,17 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     const double arg_reg = fma(e1 - r, e2, r);                    // :80
     const double arg = fm_sel_lt(a, DCP_F32_1EM10, arg_small, arg_reg);
     double sd = c.m2 * LEAN_LOG(arg);
-    o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !(arg > 1e-290 && arg < 1e290);
+    // rare cases: sd0 > smax, exponential arguments beyond 700, an argument of the logarithm that is not a positive
+    // finite number in [2^-963, 2^964) (one unsigned compare of the exponent bits; it rejects the sign bit too)
+    const bool arg_ok = (uint32_t)(fm_hi(arg) - 0x03c00000) < (uint32_t)(0x7c300000 - 0x03c00000);
+    o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !arg_ok;
     double qbf = (sd - sd0) * g.inv_dtt + uz + qin_ac;            // :98
     if (CARRY) s.e1 = fm_sel_lt(sd, 0.0, 1.0, arg);               // exp(max(sd, 0)/m2)
     double exs = fm_relu(-sd);                                    // :107-112
-    sd = fm_relu(sd);
+    sd = sd + exs;                                                // max(sd, 0), exact
     const double over = fm_relu(qbf - c.q0);                      // :115-119
     exs = fma(over, g.dtt, exs);
-    qbf = fm_min(qbf, c.q0);
+    qbf = qbf - over;                                             // min(qbf, q0), as above
     s.sd = sd; s.suz = suz; s.srz = srz; s.qint1 = qin;
     o.qbf = qbf;
     o.exac = (exs + exus) * c.ac;
