@@ -16,6 +16,7 @@ struct HruConst {            // per (HRU, member) constants for one step
     double ac, inv_ac;       // area, 1/area (FAST only)
     double q0, q1, q2;       // q0, q0*cos, q0*cos*exp(-cos*smax/szm)  (dyna_satzone_analyticalsolver.f90:49-51)
     double m2, inv_m2;       // szm/cos (:52), cos/szm (FAST only)
+    double td_dt, dtt_inv_m2; // td/dt and dtt*cos/szm: the folded constants of hru_step_lean<., true>
     double srmax, inv_srmax, td, smax;
     int ims_rz, ims_uz;
 };
@@ -242,7 +243,7 @@ struct LeanOut {
 // being recomputed (one exp and the quotient correction less per step).  The stored sd stays the rounded
 // m2*log(arg), consistent with the carried value to an ulp each step, so nothing drifts; callers re-derive e1
 // with exp() whenever they replace sd (slow path, initial state).
-template <bool CARRY = false>
+template <bool CARRY = false, bool FOLD = false>
 __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst &g, double p, double epp,
                                               double qin, HruState &s, LeanOut &o) {
     // root_zone1 (dyna_root_zone1.f90:39-66)
@@ -251,7 +252,7 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     srz = srz - pex;                                      // min(srz, srmax): one DADD instead of a compare and two selects
                                                           // (exact whenever srz <= 2 srmax, Sterbenz; an ulp of srz otherwise)
     double ea = epp * (srz * c.inv_srmax);
-    ea = fm_min(fm_min(ea, epp), srz);
+    ea = fm_min(ea, srz);                                 // srz <= srmax already, so ea <= ep up to an ulp: min(.., ep) dropped
     srz = srz - ea;
     // unsat_zone1 (dyna_unsat_zone1.f90:49-78)
     const double sd0 = s.sd;
@@ -259,8 +260,9 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     const double lim = fm_relu(sd0);
     const double exus = fm_relu(suz - lim);
     suz = suz - exus;                                     // min(suz, lim), as above
-    const double den = sd0 * c.td;
-    double uz2 = g.dt * LEAN_DIV(suz, den);
+    // FOLD: dt and dtt are folded into per-member constants (td/dt, dtt*cos/szm): three multiplications less per unit
+    const double den = sd0 * (FOLD ? c.td_dt : c.td);
+    double uz2 = FOLD ? LEAN_DIV(suz, den) : g.dt * LEAN_DIV(suz, den);
     // :60-68 drain at most what is there.  No guards are needed around the quotient: with sd <= 0 the store was just
     // emptied (lim = 0, so suz = 0 and min(x, 0) = 0 for x = +-0 or NaN, because fm_min returns its second operand
     // unless the first is smaller); with a vanishing sd*td the quotient is +inf or NaN and the same min returns suz,
@@ -275,7 +277,7 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     const double qin_ac = qin * c.inv_ac;
     const double u = qin_ac + uz;
     const double u2 = c.q2 + u;
-    const double a = (u2 * g.dtt) * c.inv_m2;
+    const double a = FOLD ? u2 * c.dtt_inv_m2 : (u2 * g.dtt) * c.inv_m2;
     // sd/m2 enters an exponential, so its rounding error is amplified by |sd/m2| (up to a few hundred):
     // one Newton correction makes the quotient faithful to the reference's sd/m2
     double x1 = 0.0, e1;
@@ -287,7 +289,7 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     }
     const double r = LEAN_DIV(c.q1, u2);
     const double e2 = LEAN_EXP(-a);
-    const double b = (c.q1 * g.dtt) * c.inv_m2;
+    const double b = FOLD ? c.q1 * c.dtt_inv_m2 : (c.q1 * g.dtt) * c.inv_m2;
     const double arg_small = (e1 + b) - a * (e1 - 0.5 * b);      // :76-77 (and :84 when u2 == 0)
     const double arg_reg = fma(e1 - r, e2, r);                    // :80
     const double arg = fm_sel_lt(a, DCP_F32_1EM10, arg_small, arg_reg);

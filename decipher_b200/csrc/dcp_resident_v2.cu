@@ -87,7 +87,7 @@ struct R2Smem {                       // team-private views unless noted
     double2 *cst_s;       // [2][4][128]     {q0, q2} per (member slot, column slot j, team thread); m2 = szm/cos(mslp) and its
                           //                 reciprocal are rebuilt from the member's {szm, 1/szm} and the column's {cos, 1/cos}:
                           //                 two DMULs instead of an LDS.128 per unit and step, and 32 KB less shared memory
-    double2 *par_s;       // [Mv][npt][3]    {srmax, 1/srmax}, {td, smax}, {szm, 1/szm}
+    double2 *par_s;       // [Mv][npt][3]    {srmax, 1/srmax}, {td/dt, smax}, {szm, dtt/szm}
     double *forc_s;       // [2][Tt*(ngp+nge)]
     uint64_t *bars;       // [2]
     // shared by both teams (read-only after setup)
@@ -124,12 +124,12 @@ __device__ __forceinline__ double2 lds_d2(uint32_t a) {
 static __device__ __noinline__ R2Fix r2_fix_unit(uint32_t cst_a, uint32_t par_a, uint32_t cold_a, double dtt, double inv_dtt,
                                                  int ntt, double qin, double uz, double exus, double sd0) {
     const double2 c0v = lds_d2(cst_a);                                   // {q0, q2}
-    const double2 p1 = lds_d2(par_a + 16), p2 = lds_d2(par_a + 32);      // {td, smax}, {szm, 1/szm}
+    const double2 p1 = lds_d2(par_a + 16), p2 = lds_d2(par_a + 32);      // {td/dt, smax}, {szm, dtt/szm}
     const double2 d0 = lds_d2(cold_a), d1 = lds_d2(cold_a + R2_H * R2_TC * 16);
     const double icos = lds_d2(cold_a + 2 * R2_H * R2_TC * 16).x;
     HruConst c;
     c.ac = d0.x; c.inv_ac = d0.y;
-    c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = d1.y * p2.y;
+    c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = (d1.y * p2.y) * inv_dtt;   // p2.y = dtt/szm
     c.q1 = c.q0 * d1.y;
     c.smax = p1.y;
     LeanOut o;
@@ -205,8 +205,8 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                 smax = W.par[(6 * npt + l) * (size_t)B + m];
             }
             M.par_s[i * 3 + 0] = make_double2(srmax, 1.0 / srmax);
-            M.par_s[i * 3 + 1] = make_double2(td, smax);
-            M.par_s[i * 3 + 2] = make_double2(szm, 1.0 / szm);
+            M.par_s[i * 3 + 1] = make_double2(td / C.dt, smax);           // folded constants of hru_step_lean<., true>
+            M.par_s[i * 3 + 2] = make_double2(szm, C.dtt / szm);
         }
         team_sync(team);
 
@@ -298,16 +298,16 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                             const double2 p2 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 2];
                             HruConst c;
                             c.ac = d0.x; c.inv_ac = d0.y;
-                            c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = d1.y * p2.y;   // dyna_satzone_analyticalsolver.f90:52
+                            c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.dtt_inv_m2 = d1.y * p2.y;   // dyna_satzone_analyticalsolver.f90:52
                             c.q1 = c.q0 * d1.y;                                         // dyna_satzone_analyticalsolver.f90:49
-                            c.srmax = p0.x; c.inv_srmax = p0.y; c.td = p1.x; c.smax = p1.y;
+                            c.srmax = p0.x; c.inv_srmax = p0.y; c.td_dt = p1.x; c.smax = p1.y;
                             c.ims_rz = 1; c.ims_uz = 1;
                             HruState st;
                             st.sd = sd[j][k]; st.suz = suz[j][k]; st.srz = srz[j][k]; st.qint1 = 0.0;
 #if R2_CARRY_E1
                             st.e1 = e1s[j][k];
 #endif
-                            hru_step_lean<R2_CARRY_E1 != 0>(c, gc, p, epp, qin[j][k], st, lo[jj][k]);
+                            hru_step_lean<R2_CARRY_E1 != 0, true>(c, gc, p, epp, qin[j][k], st, lo[jj][k]);
                             sd[j][k] = st.sd; suz[j][k] = st.suz; srz[j][k] = st.srz;  // ntt == 1: qint1 is not carried
 #if R2_CARRY_E1
                             e1s[j][k] = st.e1;
