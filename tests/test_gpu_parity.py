@@ -122,6 +122,15 @@ def test_resident_c2_subset():
     print("resident C2 fast:", _check(ref, out))
 
 
+def test_resident_fast_daily_timestep():
+    """dt = 24 (daily series), ntt = 1: the lean step folds dt and dtt into per-member constants (td/dt, dtt*cos/szm),
+    which is invisible at dt = 1; this case makes the folding visible."""
+    cat = synth.synth_catchment(nac=120, nriv=3, npt=2, ngp=2, nge=1, nstep=900, kW=6, seed=23, tree=True, dt=24.0)
+    ref, out = _run_both(cat, 48, flags=OPT_FAST_MATH, kernel=KERNEL_RESIDENT)
+    assert out["stats"]["kernel_used"] == KERNEL_RESIDENT
+    print("resident fast dt=24:", _check(ref, out))
+
+
 def test_resident_matches_streamed_bitwise_in_exact_mode():
     """Both kernels evaluate the same operations in the same order: exact mode must agree to the bit."""
     cat = synth.synth_catchment(nac=100, nriv=3, npt=2, ngp=2, nge=1, nstep=700, kW=6, seed=11, tree=True)
