@@ -334,15 +334,18 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #endif
                                 }
                     }
+                    // publish: both loads of the old baseflow first (straight-line, so that they overlap), then the stores.
+                    // Idle columns (bit 31 of .y) take part except for the tuple store: their tuples must stay 0.0 (they are
+                    // the zero-weight padding targets of the gather list) and their contribution slots lie past every river.
+                    double2 qold[2];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) qold[jj] = qbf_cur[ci[jp + jj].z & 0xffff];  // baseflow at the start of the step
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const int j = jp + jj;
-                        if (ci[j].y >= 0) {                                             // live column (bit 31 of .y marks idle ones)
-                            const int tup = ci[j].z & 0xffff, ctup = (int)((uint32_t)ci[j].w >> 16);
-                            const double2 qold = qbf_cur[tup];                          // this HRU's baseflow at the start of the step
-                            qbf_nxt[tup] = make_double2(lo[jj][0].qbf, lo[jj][1].qbf);
-                            con[ctup] = make_double2(fma(cq[jj], qold.x, lo[jj][0].exac), fma(cq[jj], qold.y, lo[jj][1].exac));
-                        }
+                        const int tup = ci[j].z & 0xffff, ctup = (int)((uint32_t)ci[j].w >> 16);
+                        if (ci[j].y >= 0) qbf_nxt[tup] = make_double2(lo[jj][0].qbf, lo[jj][1].qbf);
+                        con[ctup] = make_double2(fma(cq[jj], qold[jj].x, lo[jj][0].exac), fma(cq[jj], qold[jj].y, lo[jj][1].exac));
                         if (AET) {
 #pragma unroll
                             for (int k = 0; k < S; ++k) aet[j][k] = aet[j][k] + lo[jj][k].ea;
