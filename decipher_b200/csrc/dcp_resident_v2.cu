@@ -145,7 +145,9 @@ static __device__ __noinline__ R2Fix r2_fix_unit(uint32_t cst_a, uint32_t par_a,
 // ---------------------------------------------------------------------------------------------
 // compute role: 4 warps per team, thread = 4 HRU columns x 2 member slots
 // ---------------------------------------------------------------------------------------------
-template <bool AET>
+// ONEPAR: one parameter layer and one member sub-group per team (C2): the member-parameter words sit at fixed
+// addresses, so their loads are shared by the columns of a block
+template <bool AET, bool ONEPAR>
 __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
                                            const int team, const int tt_id) {
     constexpr int H = R2_H, S = R2_S;
@@ -293,9 +295,9 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #pragma unroll
                         for (int k = 0; k < S; ++k) {
                             const double2 c0v = M.cst_s[(k * H + j) * R2_TC + tt_id];
-                            const double2 p0 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride];
-                            const double2 p1 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 1];
-                            const double2 p2 = M.par_s[(ci[j].w & 0xffff) + k * par_kstride + 2];
+                            const double2 p0 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride];
+                            const double2 p1 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 1];
+                            const double2 p2 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 2];
                             HruConst c;
                             c.ac = d0.x; c.inv_ac = d0.y;
                             c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.dtt_inv_m2 = d1.y * p2.y;   // dyna_satzone_analyticalsolver.f90:52
@@ -453,7 +455,7 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
     }
 }
 
-template <bool AET>
+template <bool AET, bool ONEPAR>
 __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchment C, DevBatch W, Res2Plan P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
@@ -496,7 +498,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
             const long long t0 = clock64();
             while (clock64() - t0 < P.phase_delay) {}
         }
-        r2_compute<AET>(C, W, P, M, team, tid % R2_TC);
+        r2_compute<AET, ONEPAR>(C, W, P, M, team, tid % R2_TC);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_RIVER));
         if (P.phase_delay < 0 && team == 1) return;
@@ -507,7 +509,10 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
 
 cudaError_t dcp_launch_physics_resident_v2(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, bool aet,
                                            int grid, cudaStream_t s) {
-    void (*k)(DevCatchment, DevBatch, Res2Plan) = aet ? k_physics_resident_v2<true> : k_physics_resident_v2<false>;
+    const bool onepar = C.npt == 1 && P.G == 1;
+    void (*k)(DevCatchment, DevBatch, Res2Plan) =
+        aet ? (onepar ? k_physics_resident_v2<true, true> : k_physics_resident_v2<true, false>)
+            : (onepar ? k_physics_resident_v2<false, true> : k_physics_resident_v2<false, false>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
     k<<<grid, R2_THREADS, P.smem_bytes, s>>>(C, W, P);
