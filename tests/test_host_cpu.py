@@ -99,3 +99,27 @@ def test_res_and_flow_writers(project):
     assert res2[res2.index("! PET TOTALS (mm)") + 1] == " 0.40 410.00 0.50"
     assert res2[2].startswith(" Maximum QBF is less than")
     p.close()
+
+
+def test_compare_with_fortran_tool_on_oracle_written_files(tmp_path):
+    """tools/compare_with_fortran.py (the link to the real reference for anyone with a Fortran compiler): its
+    project writer and comparator agree when the member files are written from the oracle's own results with
+    the reference's edit descriptors (C++ host writers)."""
+    import importlib.util
+    import sys
+    spec = importlib.util.spec_from_file_location("cwf", os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                                                      "tools", "compare_with_fortran.py"))
+    cwf = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(cwf)
+    from oracle_binding import oracle_run
+    root = str(tmp_path / "proj")
+    cwf.make_project(root, 4)
+    assert cwf.compare(root) == 2                                     # nothing to compare yet
+    p = host.Project(root, 1, 1, 1)
+    mc = p.genpar(4)
+    ref = oracle_run(p.catchment(), mc.copy(order="F"), flags=0)
+    for m in range(4):
+        p.write_member(m + 1, ref["mcpar"][:, :, m], ref["q"][:, :, m], ref["reach_totals"][:, :, m],
+                       ref["init_diag"][:, m], int(ref["status"][m]))
+    p.close()
+    assert cwf.compare(root) == 0
