@@ -297,10 +297,9 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
     // rare cases: sd0 > smax, exponential arguments beyond 700, an argument of the logarithm that is not a positive
     // finite number in [2^-963, 2^964) (one unsigned compare of the exponent bits; it rejects the sign bit too)
     const bool arg_ok = (uint32_t)(fm_hi(arg) - 0x03c00000) < (uint32_t)(0x7c300000 - 0x03c00000);
-    // a > 700 (or NaN) on the high word: 700.0 = 0x4085e000'00000000; a negative a passes, as with the FP64 compare
-    o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || fm_hi(a) >= 0x4085e000 || !arg_ok;
+    o.slow = !(sd0 <= c.smax) || !(x1 <= 700.0) || !(a <= 700.0) || !arg_ok;
     double qbf = (sd - sd0) * g.inv_dtt + uz + qin_ac;            // :98
-    if (CARRY) s.e1 = fm_hi(sd) < 0 ? 1.0 : arg;                  // exp(max(sd, 0)/m2); sign-bit test (sd = -0.0 only if arg == 1)
+    if (CARRY) s.e1 = fm_sel_lt(sd, 0.0, 1.0, arg);               // exp(max(sd, 0)/m2)
     double exs = fm_relu(-sd);                                    // :107-112
     sd = sd + exs;                                                // max(sd, 0), exact
     const double over = fm_relu(qbf - c.q0);                      // :115-119

@@ -64,9 +64,6 @@
 #else
 #define R2_DBG false
 #endif
-#ifndef R2_ROT
-#define R2_ROT 64                     // thread offset of team 1 into the per-thread tables (two warps)
-#endif
 #ifndef R2_NACC
 #define R2_NACC 4                     // partial sums per member slot in the gather
 #endif
@@ -501,9 +498,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
             const long long t0 = clock64();
             while (clock64() - t0 < P.phase_delay) {}
         }
-        // team 1 walks the shared per-thread tables two warps ahead: compute warp w of team 0 and of team 1 share an SM
-        // sub-partition, and the warps with the longest gather lists (w = 0) should not be neighbours
-        r2_compute<AET, ONEPAR>(C, W, P, M, team, (tid % R2_TC + team * R2_ROT) % R2_TC);
+        r2_compute<AET, ONEPAR>(C, W, P, M, team, tid % R2_TC);
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_RIVER));
         if (P.phase_delay < 0 && team == 1) return;
