@@ -64,6 +64,9 @@
 #else
 #define R2_DBG false
 #endif
+#ifndef R2_LONG
+#define R2_LONG 2                     // x R2_NACC entries per round in a thread's first (longest) column; full-length bench on
+#endif                                // one box (gpurun_out/ab2.log): 1 / 2 / 3 = 8.264 / 8.338 / 8.238e10 units/s
 #ifndef R2_NACC
 #define R2_NACC 4                     // partial sums per member slot in the gather
 #endif
@@ -255,6 +258,23 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                         for (int u = 0; u < R2_NACC; ++u) { qa[u][0] = 0.0; qa[u][1] = 0.0; }
                         constexpr int GU = R2_GATHER_UNROLL;
                         int bb = 0;
+#if R2_LONG > 1                       // wide rounds for the thread's first (longest) column only: a round costs two shared-memory
+                                      // round trips whatever its width (wide rounds for EVERY column grow the loop body and lose 9 %)
+                        if (j == 0) {
+#pragma unroll 1
+                            for (; bb + R2_LONG * R2_NACC <= nb; bb += R2_LONG * R2_NACC) {
+#pragma unroll
+                                for (int u = 0; u < R2_LONG * R2_NACC; ++u) {
+                                    const double wc = wv[0];
+                                    const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
+                                    ep += 32;
+                                    wv[0] = ep[0];
+                                    qa[u % R2_NACC][0] = fma(qv.x, wc, qa[u % R2_NACC][0]);
+                                    qa[u % R2_NACC][1] = fma(qv.y, wc, qa[u % R2_NACC][1]);
+                                }
+                            }
+                        }
+#endif
 #pragma unroll GU
                         for (; bb + R2_NACC <= nb; bb += R2_NACC) {
 #pragma unroll
