@@ -52,6 +52,10 @@ struct DevBuf {                     // growable device allocation
         return e;
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }         // early returns (CUDA_TRY, fail) must not leak the allocation
 };
 
 template <class T>
@@ -366,6 +370,8 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
     if (nac < 1 || nriv < 1 || npt < 1 || d->nstep < 1 || d->ngp < 1 || d->nge < 1 || d->ntt < 1 || !(d->dt > 0))
         return fail(DCP_ERR_INVALID, "non-positive dimension or dt");
     if (nnode < nriv || ncell < 1) return fail(DCP_ERR_INVALID, "routing: nnode (%d) < nriv (%d) or no river cells", nnode, nriv);
+    if (d->qobs != nullptr && d->nstep_obs > 0 && (d->t_warm < 0 || d->t_warm > d->nstep))
+        return fail(DCP_ERR_INVALID, "t_warm (%d) must lie in [0, nstep]", d->t_warm);
     if (!d->ac || !d->st || !d->mslp || !d->ippt || !d->ipet || !d->ipar || !d->ipriv || !d->ims_rz || !d->ims_uz ||
         !d->ntrans || !d->wtrans || !d->rivers || !d->sum_ac_riv || !d->qobs_start || !d->node_gauge_id ||
         !d->node_type || !d->uptree_count || !d->frac_sub_area || !d->river_data || !d->node_to_flow_mapping ||
@@ -951,7 +957,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
                 dbg.release();
             }
             tm.mark(T_ROUTE);
-            dcp_launch_route(C, W, 0, C.nstep, d_q, s); n_launch += C.qobs ? 3 : 2;
+            CUDA_TRY(dcp_launch_route(C, W, 0, C.nstep, d_q, s)); n_launch += C.qobs ? 3 : 2;
         } else {
             for (int t0 = 0; t0 < C.nstep; t0 += tile) {
                 const int t1 = std::min(C.nstep, t0 + tile);
@@ -959,9 +965,9 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
                 if (use_sw) {
                     CUDA_TRY(dcp_launch_physics_stepwise(C, W, c->dplan, t0, t1, fast, aet, sw_dense, c->n_sm, s));
                     n_launch += (int64_t)(t1 - t0) * (sw_dense ? 4 : 3); n_phys += t1 - t0;
-                } else { dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s); ++n_launch; ++n_phys; }
+                } else { CUDA_TRY(dcp_launch_physics_streamed(C, W, t0, t1, fast, check, aet, s)); ++n_launch; ++n_phys; }
                 tm.mark(T_ROUTE);
-                dcp_launch_route(C, W, t0, t1, d_q, s); n_launch += C.qobs ? 3 : 2;
+                CUDA_TRY(dcp_launch_route(C, W, t0, t1, d_q, s)); n_launch += C.qobs ? 3 : 2;
             }
         }
         tm.mark(T_FIN);
@@ -980,7 +986,6 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         CUDA_TRY(cudaGetLastError());
         m0 += Bn;
     }
-    vmin_buf.release();
     double sums[T_NTAGS];
     tm.collect(sums, T_NTAGS);
     c->stats.ms_total = tm.total();
@@ -1079,7 +1084,7 @@ int dcp_route_timeseries(dcp_catchment *c, int64_t n_series, const double *veloc
         tm.mark(T_INIT);
         dcp_launch_route_prepare(C, W, d_v, d_in, s); n_launch += 2;
         tm.mark(T_ROUTE);
-        dcp_launch_route(C, W, 0, C.nstep, d_out, s); n_launch += 2;
+        CUDA_TRY(dcp_launch_route(C, W, 0, C.nstep, d_out, s)); n_launch += 2;
         if (d_status) { dcp_launch_route_status(C, W, d_status, s); ++n_launch; }
         tm.mark(T_D2H);
         if (!dev_io) {
@@ -1106,13 +1111,12 @@ int dcp_route_timeseries(dcp_catchment *c, int64_t n_series, const double *veloc
 int dcp_debug_fastmath(int op, int64_t n, const double *x, double *y) {
     if (dcp_device_count() < 1) return fail(DCP_ERR_NO_DEVICE, "no CUDA device");
     if (op < 0 || op > 2 || n < 1 || !x || !y) return fail(DCP_ERR_INVALID, "bad argument");
-    double *dx = nullptr, *dy = nullptr;
-    CUDA_TRY(cudaMalloc(&dx, n * 8));
-    CUDA_TRY(cudaMalloc(&dy, n * 8));
-    CUDA_TRY(cudaMemcpy(dx, x, n * 8, cudaMemcpyHostToDevice));
-    dcp_launch_debug_fastmath(op, n, dx, dy, 0);
-    CUDA_TRY(cudaMemcpy(y, dy, n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(dx); cudaFree(dy);
+    DevBuf bx, by;
+    CUDA_TRY(bx.reserve(n * 8));
+    CUDA_TRY(by.reserve(n * 8));
+    CUDA_TRY(cudaMemcpy(bx.p, x, n * 8, cudaMemcpyHostToDevice));
+    dcp_launch_debug_fastmath(op, n, (const double *)bx.p, (double *)by.p, 0);
+    CUDA_TRY(cudaMemcpy(y, by.p, n * 8, cudaMemcpyDeviceToHost));
     return DCP_OK;
 }
 

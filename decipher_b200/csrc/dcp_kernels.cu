@@ -725,41 +725,51 @@ void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bo
     else k_init_members<false><<<grid, 128, 0, s>>>(C, W, mcpar);
 }
 
+// The river accumulators take 2*nriv doubles of shared memory per thread: the block shrinks (128 -> 64 -> 32 threads) until
+// they fit the opt-in limit, so catchments with many gauges keep the balance checks; beyond ~450 gauges the launch is refused.
 template <bool FAST, bool CHECK, bool AET>
-static void launch_streamed2(const DevCatchment &C, const DevBatch &W, int t0, int t1, cudaStream_t s) {
-    const int threads = DCP_STREAM_THREADS;
-    const int grid = cdiv(W.B, threads);
+static cudaError_t launch_streamed2(const DevCatchment &C, const DevBatch &W, int t0, int t1, cudaStream_t s) {
+    int dev = 0, optin = 48 * 1024;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    int threads = DCP_STREAM_THREADS;
+    while (threads > 32 && (size_t)2 * C.nriv * threads * sizeof(double) > (size_t)optin) threads >>= 1;
     const size_t smem = (size_t)2 * C.nriv * threads * sizeof(double);
+    if (smem > (size_t)optin) return cudaErrorInvalidConfiguration;
+    const int grid = cdiv(W.B, threads);
+    cudaError_t e = cudaSuccess;
     if (C.npt == 1) {
         auto k = k_physics_streamed<FAST, CHECK, AET, true>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         k<<<grid, threads, smem, s>>>(C, W, t0, t1);
     } else {
         auto k = k_physics_streamed<FAST, CHECK, AET, false>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (smem > 48 * 1024) e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         k<<<grid, threads, smem, s>>>(C, W, t0, t1);
     }
+    return cudaGetLastError();
 }
 
-void dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,
-                                 bool check, bool aet, cudaStream_t s) {
+cudaError_t dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,
+                                        bool check, bool aet, cudaStream_t s) {
     if (check) {            // checked mode always tracks aet (results_ts needs sum_aeout)
-        if (fast) launch_streamed2<true, true, true>(C, W, t0, t1, s);
-        else launch_streamed2<false, true, true>(C, W, t0, t1, s);
+        return fast ? launch_streamed2<true, true, true>(C, W, t0, t1, s) : launch_streamed2<false, true, true>(C, W, t0, t1, s);
     } else if (aet) {
-        if (fast) launch_streamed2<true, false, true>(C, W, t0, t1, s);
-        else launch_streamed2<false, false, true>(C, W, t0, t1, s);
-    } else {
-        if (fast) launch_streamed2<true, false, false>(C, W, t0, t1, s);
-        else launch_streamed2<false, false, false>(C, W, t0, t1, s);
+        return fast ? launch_streamed2<true, false, true>(C, W, t0, t1, s) : launch_streamed2<false, false, true>(C, W, t0, t1, s);
     }
+    return fast ? launch_streamed2<true, false, false>(C, W, t0, t1, s) : launch_streamed2<false, false, false>(C, W, t0, t1, s);
 }
 
-void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s) {
+cudaError_t dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s) {
     const int nchunk = cdiv(t1 - t0, ROUTE_CH);
     const size_t smem = ((size_t)2 * W.Lcap + ROUTE_CH) * sizeof(double);
     const int use_smem = smem <= 96 * 1024;
-    if (use_smem && smem > 48 * 1024) cudaFuncSetAttribute(k_route_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (use_smem && smem > 48 * 1024) {
+        const cudaError_t e = cudaFuncSetAttribute(k_route_conv, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+    }
     dim3 g1(W.B, C.nnode, nchunk), g2(W.B, C.nriv, nchunk);      // members on grid.x (no 65535 limit)
     k_route_conv<<<g1, ROUTE_CH, use_smem ? smem : 0, s>>>(C, W, t0, t1, use_smem);
     k_route_gauge<<<g2, ROUTE_CH, 0, s>>>(C, W, t0, t1, q_out);
@@ -767,6 +777,7 @@ void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, 
         dim3 g3(cdiv(W.B, 32), C.nriv);
         k_objective_sum<<<g3, 32, 0, s>>>(C, W, t0, t1);
     }
+    return cudaGetLastError();
 }
 
 void dcp_launch_route_prepare(const DevCatchment &C, const DevBatch &W, const double *v, const double *inflow,

@@ -16,9 +16,9 @@
 
 void dcp_launch_min_chv(const double *mcpar, int npt, int64_t n_member, double *out, cudaStream_t s);
 void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bool check, cudaStream_t s);
-void dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,
-                                 bool check, bool aet, cudaStream_t s);
-void dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s);
+cudaError_t dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,
+                                        bool check, bool aet, cudaStream_t s);
+cudaError_t dcp_launch_route(const DevCatchment &C, const DevBatch &W, int t0, int t1, double *q_out, cudaStream_t s);
 void dcp_launch_route_prepare(const DevCatchment &C, const DevBatch &W, const double *v, const double *inflow,
                               cudaStream_t s);
 void dcp_launch_route_status(const DevCatchment &C, const DevBatch &W, int32_t *status, cudaStream_t s);
