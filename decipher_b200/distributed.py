@@ -42,6 +42,26 @@ def gather_to_rank0(local, n_total: int, group=None):
     return None
 
 
+class PerfGather:
+    """The end-of-run gather of the per-member measures for EQUAL member blocks: receive buffers are
+    allocated once on rank 0 (`out`: (world, n_local, ...), rank r's block at out[r]) and reused by every call, so a
+    call is exactly one `dist.gather` -- no allocation, no padding copy, no concatenation."""
+
+    def __init__(self, n_local: int, tail_shape, world: int, rank: int, device, dtype=None, group=None):
+        import torch
+        self.group, self.rank = group, rank
+        self.out = None
+        self.outs = None
+        if rank == 0:
+            self.out = torch.empty((world, n_local) + tuple(tail_shape), dtype=dtype or torch.float64, device=device)
+            self.outs = list(self.out.unbind(0))
+
+    def __call__(self, local):
+        import torch.distributed as dist
+        dist.gather(local, self.outs, dst=0, group=self.group)
+        return self.out
+
+
 def lpt_assign(costs, world: int):
     """Longest-processing-time-first assignment of catchments to ranks (multi-catchment runs,
     SURVEY §8e): returns a list of rank ids, one per catchment."""

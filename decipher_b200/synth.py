@@ -14,6 +14,7 @@ Generator recipe: SURVEY.md §8(d).  Seeds: np.random.default_rng(20260119 + con
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, Optional
 
 import numpy as np
@@ -56,7 +57,7 @@ def quant(x, dec):
 
 def make_raw(nac=24, nriv=2, npt=3, ngp=2, nge=1, nstep=8760, kW=4, seed=BASE_SEED, dt=1.0, ntt=1,
              reach_km=(5.0, 30.0), cell_m=50.0, tree=False, nstep_obs: Optional[int] = None,
-             dense_w=False) -> Dict:
+             dense_w=False, qobs_fixture: Optional[str] = "auto") -> Dict:
     rng = np.random.default_rng(seed)
     raw: Dict = dict(nac=nac, nriv=nriv, npt=npt, ngp=ngp, nge=nge, nstep=nstep, dt=float(dt), ntt=int(ntt))
 
@@ -147,6 +148,17 @@ def make_raw(nac=24, nriv=2, npt=3, ngp=2, nge=1, nstep=8760, kW=4, seed=BASE_SE
     qo = quant(np.maximum(qo, 1e-9), 9)
     flow_err = -9999.0
     qo[rng.uniform(size=qo.shape) < 0.01] = flow_err
+    # BASELINE configs 2/3: the observed flow is an oracle run with mid-range parameters, kept as a data
+    # fixture (decipher_b200/data/c2_qobs_oracle.npz, written by tests/golden/make_qobs_c2.py); it applies to exactly the
+    # catchment it was generated for (seed, nstep, nriv), every other shape keeps the linear-reservoir proxy above
+    if qobs_fixture == "auto":
+        qobs_fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "c2_qobs_oracle.npz")
+    if qobs_fixture and os.path.exists(qobs_fixture) and nstep_obs is None:
+        fx = np.load(qobs_fixture)
+        if (int(fx["seed"]), int(fx["nstep"]), int(fx["nriv"])) == (int(seed), int(nstep), int(nriv)) and (nac, kW, dt) == (500, 8, 1.0):
+            qe9 = fx["qobs_e9"].astype(np.float64)
+            qo = np.where(qe9 < 0, flow_err, qe9 / 1e9)
+            raw["qobs_source"] = "oracle run, mid-range parameters, 10 % noise, 1 % missing (data/c2_qobs_oracle.npz)"
     raw.update(qobs=np.asfortranarray(qo), flow_err=flow_err)
     return raw
 
@@ -246,7 +258,7 @@ def assemble(raw: Dict) -> Catchment:
         frac_sub_area=frac, river_data=raw["river_data"],
         node_to_flow_mapping=np.arange(1, nriv + 1, dtype=np.int32),
         rain=raw["rain"], pet=raw["pet"], qobs=qobs, flow_err=ferr, t_warm=0,
-        meta=dict(down=down))
+        meta=dict(down=down, **({'qobs_source': raw['qobs_source']} if 'qobs_source' in raw else {})))
 
 
 # Named configurations of BASELINE.json / SURVEY §8(d).  `members` is the ensemble size the config is

@@ -9,7 +9,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from decipher_b200.distributed import gather_to_rank0, lpt_assign, shard_range
+from decipher_b200.distributed import PerfGather, gather_to_rank0, lpt_assign, shard_range
 
 
 def _free_port():
@@ -27,6 +27,15 @@ def _worker(rank, world, port, n_total, q):
     lo, hi = shard_range(n_total, rank, world)
     local = torch.arange(lo, hi, dtype=torch.float64)[:, None, None] * torch.ones(1, 3, 2, dtype=torch.float64)
     full = gather_to_rank0(local, n_total)
+    # the preallocated equal-block gather used once per run by bench.py / ensemble drivers: two calls reuse the buffers
+    pg = PerfGather(4, (3, 2), world, rank, torch.device("cpu"))
+    for rep in range(2):
+        blk = (torch.arange(4, dtype=torch.float64) + 100 * rank + 1000 * rep)[:, None, None] * torch.ones(1, 3, 2, dtype=torch.float64)
+        got = pg(blk)
+        if rank == 0:
+            assert got.shape == (world, 4, 3, 2) and got.data_ptr() == pg.out.data_ptr()
+            for r in range(world):
+                assert torch.equal(got[r, :, 0, 0], torch.arange(4, dtype=torch.float64) + 100 * r + 1000 * rep)
     if rank == 0:
         q.put(full.numpy())
     dist.barrier()

@@ -85,21 +85,76 @@ def test_invalid_descriptors_are_rejected():
 
 
 def test_full_length_config2_properties():
-    """BASELINE config 2 at its full series length (500 HRUs, 87 600 hourly steps): 16 members against the
-    oracle, the two kernels bit-identical in exact mode, fast within 1e-9 of exact, runs repeatable to the bit."""
+    """BASELINE config 2 at its full series length (500 HRUs, 87 600 hourly steps).  FAST policy (the benchmarked
+    kernel): 512 distinct parameter sets = more than one CTA wave of member groups, every one against the oracle at
+    the 1e-9 contract, flows AND measures.  EXACT policy: the first 16 of them, resident == streamed to the bit.
+    Runs are repeatable to the bit."""
+    import os
     cat = synth.synth_catchment("C2")
     assert cat.nstep == 87600 and cat.nac == 500
-    mc = synth.sample_parameters(1, 16)
-    ref = oracle_run(cat, mc.copy(order="F"), n_threads=16, want_totals=False)
+    M, Mx = 512, 16
+    mc = synth.sample_parameters(1, M)
+    ref = oracle_run(cat, mc.copy(order="F"), n_threads=os.cpu_count() or 16, want_totals=False)
     dev = DeviceCatchment(cat)
-    ex = dev.run(mc.copy(order="F"), kernel=KERNEL_RESIDENT, want_q=True)
-    st = dev.run(mc.copy(order="F"), kernel=KERNEL_STREAMED, want_q=True)
+    ex = dev.run(mc[:, :, :Mx].copy(order="F"), kernel=KERNEL_RESIDENT, want_q=True)
+    st = dev.run(mc[:, :, :Mx].copy(order="F"), kernel=KERNEL_STREAMED, want_q=True)
     fa = dev.run(mc.copy(order="F"), kernel=KERNEL_RESIDENT, flags=OPT_FAST_MATH, want_q=True)
-    fa2 = dev.run(mc.copy(order="F"), kernel=KERNEL_AUTO, flags=OPT_FAST_MATH, want_q=True)
+    fa2 = dev.run(mc.copy(order="F"), kernel=KERNEL_AUTO, flags=OPT_FAST_MATH, want_q=False)
     dev.close()
     assert np.array_equal(ex["q"], st["q"], equal_nan=True) and np.array_equal(ex["perf"], st["perf"], equal_nan=True)
-    assert np.array_equal(fa["q"], fa2["q"], equal_nan=True), "fast runs must be deterministic"
-    print("full length exact:", compare_flows(ex["q"], ref["q"]), compare_perf(ex["perf"], ref["perf"]))
+    assert np.array_equal(fa["perf"], fa2["perf"], equal_nan=True), "fast runs must be deterministic (with and without q_out)"
+    assert np.array_equal(fa["status"], ref["status"]) and np.array_equal(fa["mcpar"], ref["mcpar"])
+    print("full length exact:", compare_flows(ex["q"], ref["q"][:, :, :Mx]), compare_perf(ex["perf"], ref["perf"][:, :, :Mx]))
     print("full length fast :", compare_flows(fa["q"], ref["q"]), compare_perf(fa["perf"], ref["perf"]))
     fin = np.isfinite(ref["q"]).all(axis=(0, 1))
-    assert (ex["q"][:, :, fin] >= 0).all()
+    assert (ex["q"][:, :, fin[:Mx]] >= 0).all()
+
+
+@pytest.mark.parametrize("depth", [4.0e6, 1.0e9])
+def test_balance_stop_conditions_raise_the_oracles_flags(depth):
+    """The reference STOPs when the root-zone store balance (dyna_root_zone1.f90:73-77) or the catchment sums
+    (dyna_results_ts.f90:86-101) do not close.  In exact arithmetic they always close; an absurd rain depth makes
+    the rounding error of the balance itself exceed the thresholds (ulp(4e6 m) = 4.7e-10 > 1e-10; at 1e9 m the
+    1e-6 thresholds of results_ts go too).  Which members trip which check depends on the last bit, so the
+    EXACT policy must raise exactly the oracle's bits, member by member."""
+    cat = synth.synth_catchment("C1", nstep=300)
+    cat.rain[:, 50] = depth
+    mc = synth.sample_parameters(cat.npt, 40)
+    ref = oracle_run(cat, mc.copy(order="F"), flags=OPT_CHECK_BALANCE)
+    bits = 0x4 | 0x8 | 0x10
+    assert (ref["status"] & 0x4).any(), "fixture must trip the root-zone check"
+    if depth >= 1e9:
+        assert (ref["status"] & 0x8).any() and (ref["status"] & 0x10).any(), "fixture must trip both results_ts checks"
+    dev = DeviceCatchment(cat)
+    out = dev.run(mc.copy(order="F"), flags=OPT_CHECK_BALANCE, kernel=KERNEL_AUTO, want_q=True)
+    plain = dev.run(mc.copy(order="F"), flags=0, kernel=KERNEL_STREAMED, want_q=True)
+    dev.close()
+    assert out["stats"]["kernel_used"] == KERNEL_STREAMED          # AUTO routes checked runs to the kernel that has the checks
+    assert np.array_equal(out["status"], ref["status"]), (out["status"] & bits, ref["status"] & bits)
+    assert not (plain["status"] & bits).any()                        # the checks are opt-in; flows are the same either way
+    assert np.array_equal(out["q"], plain["q"], equal_nan=True)
+    compare_flows(out["q"], ref["q"])
+
+
+def test_member_sharding_does_not_change_a_single_bit():
+    """G-independence: the parameter table comes from ONE sequential RANMAR stream and each rank takes a
+    contiguous block, so the measures of the whole ensemble are the same bits whether one device runs all members or
+    two devices (here: two handles on this GPU, each with its own workspace) run half each -- for both policies."""
+    from decipher_b200.distributed import shard_range
+    cat = synth.synth_catchment("C2", nstep=1200)
+    M = 301                                            # odd: ragged blocks, ragged member groups
+    table = synth.sample_parameters(cat.npt, M)
+    for flags in (OPT_FAST_MATH, 0):
+        one = DeviceCatchment(cat)
+        whole = one.run(table.copy(order="F"), flags=flags, kernel=KERNEL_AUTO, want_q=True)
+        one.close()
+        parts = []
+        for rank in range(2):
+            lo, hi = shard_range(M, rank, 2)
+            d = DeviceCatchment(cat)
+            parts.append(d.run(table[:, :, lo:hi].copy(order="F"), flags=flags, kernel=KERNEL_AUTO, want_q=True))
+            d.close()
+        for k in ("q", "perf", "mcpar", "init_diag"):
+            both = np.concatenate([parts[0][k], parts[1][k]], axis=-1)
+            assert np.array_equal(both, whole[k], equal_nan=True), (k, flags)
+        assert np.array_equal(np.concatenate([parts[0]["status"], parts[1]["status"]]), whole["status"])
