@@ -299,9 +299,9 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     if (Q.ell_len >= (1 << 20)) return;
 
     Q.n_teams = G * nriv;
-    Q.team = 32;
-    while (Q.team > 1 && Q.team * Q.n_teams > 64) Q.team >>= 1;
-    Q.n_pass = (Q.n_teams * Q.team + 63) / 64;
+    Q.team = 32;                                            // the 32 lanes of a team's river-sum warp
+    while (Q.team > 1 && Q.team * Q.n_teams > 32) Q.team >>= 1;
+    Q.n_pass = (Q.n_teams * Q.team + 31) / 32;
     if (Q.n_pass > 16) return;
     // shared memory: [shared tables][team 0][team 1]
     size_t off = 0;
@@ -709,7 +709,9 @@ struct Carver {                     // carves a slab into aligned arrays
 };
 
 // lays the batch workspace out (base == nullptr: size query only)
-size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, bool aet, int stepwise_nq = -1) {
+// ring_slots > 0: fused routing (dcp_route_fused.cuh) -- qout / y are rings of R steps per member IN FLIGHT, and the
+// per-step objective series do not exist
+size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, bool aet, int stepwise_nq = -1, int ring_slots = 0) {
     Carver cv(base);
     const size_t B = W.B, nac = C.nac;
     W.par = cv.take<double>(7 * C.npt * B);
@@ -729,9 +731,10 @@ size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, b
     W.dh = cv.take<double>((size_t)C.nnode * W.Lcap * B);
     W.hstart = cv.take<int32_t>(C.nnode * B);
     W.hbins = cv.take<int32_t>(C.nnode * B);
-    W.qout = cv.take<double>((size_t)W.R * C.nriv * B);
-    W.y = cv.take<double>((size_t)W.R * C.nnode * B);
-    if (C.qobs) {
+    W.qout = cv.take<double>((size_t)W.R * C.nriv * (ring_slots > 0 ? (size_t)ring_slots : B));
+    W.y = cv.take<double>((size_t)W.R * C.nnode * (ring_slots > 0 ? (size_t)ring_slots : B));
+    W.q_user = nullptr;
+    if (C.qobs && ring_slots <= 0) {
         W.d2 = cv.take<double>((size_t)W.R * C.nriv * B); W.dl2 = cv.take<double>((size_t)W.R * C.nriv * B);
         W.qs = cv.take<double>((size_t)W.R * C.nriv * B);
     } else { W.d2 = W.dl2 = W.qs = nullptr; }
@@ -824,6 +827,13 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     int64_t Bmax = o.members_per_batch > 0 ? o.members_per_batch : (use_res ? (int64_t)wave * 64 : 131072);
     Bmax = std::min<int64_t>(Bmax, n_member);
 
+    // resident kernels route and score inside the kernel (dcp_route_fused.cuh): rings per member in flight instead of
+    // nstep-long series per member.  (The two-column lean variant of the first generation keeps the separate kernels.)
+    const bool use_v2 = use_res && fast && c->plan2.feasible;
+    const bool v1_two_col = use_res && !use_v2 && fast && c->plan.lean_ok && (c->plan.variant ? c->plan.variant : 2) == 2;
+    const bool fused = use_res && !v1_two_col;
+    const int ring_slots = !fused ? 0 : use_v2 ? c->n_sm * 2 * c->plan2.G * 2 : c->n_sm * c->plan.Mc;
+
     c->stats = dcp_run_stats{};
     c->stats.kernel_used = use_res ? DCP_KERNEL_RESIDENT : use_sw ? DCP_KERNEL_STEPWISE : DCP_KERNEL_STREAMED;
     const int sw_nq = use_sw ? c->dplan.nq : -1;
@@ -856,8 +866,8 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         int64_t Bn = std::min<int64_t>(Bmax, n_member - m0);
         // ---- first guess of the batch size: everything except the (still unknown) histogram length ----
         for (;;) {
-            DevBatch Wq{}; Wq.B = (int)Bn; Wq.Lcap = 1; Wq.R = use_res ? C.nstep : tile + 64;
-            const size_t fixed = carve_batch(nullptr, C, Wq, check, aet, sw_nq) + io_size(Bn);
+            DevBatch Wq{}; Wq.B = (int)Bn; Wq.Lcap = 1; Wq.R = fused ? 512 : use_res ? C.nstep : tile + 64;
+            const size_t fixed = carve_batch(nullptr, C, Wq, check, aet, sw_nq, ring_slots) + io_size(Bn);
             if ((double)fixed < 0.9 * mem_budget || Bn <= 1) break;
             Bn = shrink(Bn);
         }
@@ -906,14 +916,18 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         W.Lcap = (int)std::ceil(max_reach) + 3;
         const int Tcap = (int)std::ceil(max_full) + 3;
         hist_len_max = std::max(hist_len_max, Tcap - 2);
-        if (use_res || tile >= C.nstep) {        // whole series resident in the flow buffers: no ring
+        if (fused) {                             // rings: histogram span + the tile being filled + the tile being routed
+            int R = 1;
+            while (R < Tcap + DCP_RT_SLACK_STEPS) R <<= 1;
+            W.R = R; W.Rmask = R - 1;
+        } else if (use_res || tile >= C.nstep) { // whole series resident in the flow buffers: no ring
             W.R = C.nstep; W.Rmask = 0x7fffffff;
         } else {
             int R = 1;
             while (R < tile + Tcap + 1) R <<= 1;
             W.R = R; W.Rmask = R - 1;
         }
-        const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet, sw_nq);
+        const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet, sw_nq, ring_slots);
         if ((double)(ws_bytes + io_bytes) > mem_budget) {
             if (Bn <= 1) return fail(DCP_ERR_NOMEM, "one member needs %zu MB, device has %zu MB free",
                                      (ws_bytes + io_bytes) >> 20, free_b >> 20);
@@ -921,7 +935,8 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             continue;
         }
         CUDA_TRY(c->ws.reserve(ws_bytes));
-        carve_batch(c->ws.p, C, W, check, aet, sw_nq);
+        carve_batch(c->ws.p, C, W, check, aet, sw_nq, ring_slots);
+        W.q_user = fused ? d_q : nullptr;
         if (use_sw) CUDA_TRY(cudaMemsetAsync(W.bad_src, 0, (size_t)Bn * 4, s));
 
         tm.mark(T_INIT);
@@ -932,7 +947,6 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             const int grid = std::min(c->n_sm, P.n_groups);
             DevBuf dbg;
             if (getenv("DCP_RES_DEBUG")) { CUDA_TRY(dbg.reserve((size_t)grid * 20 * 8)); CUDA_TRY(cudaMemsetAsync(dbg.p, 0, (size_t)grid * 20 * 8, s)); P.dbg = (long long *)dbg.p; }
-            const bool use_v2 = fast && c->plan2.feasible;
             Res2Plan Q = c->plan2;
             int grid2 = 0;
             if (use_v2) {
@@ -957,7 +971,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
                 dbg.release();
             }
             tm.mark(T_ROUTE);
-            CUDA_TRY(dcp_launch_route(C, W, 0, C.nstep, d_q, s)); n_launch += C.qobs ? 3 : 2;
+            if (!fused) { CUDA_TRY(dcp_launch_route(C, W, 0, C.nstep, d_q, s)); n_launch += C.qobs ? 3 : 2; }
         } else {
             for (int t0 = 0; t0 < C.nstep; t0 += tile) {
                 const int t1 = std::min(C.nstep, t0 + tile);

@@ -97,8 +97,10 @@ struct DevBatch {
     double *dh;                     // [B][nnode][Lcap] normalised delay histograms (bins contiguous)
     int32_t *hstart;                // [nnode][B]  node_hist_indexes(:,1)
     int32_t *hbins;                 // [nnode][B]  bin count
-    double *qout;                   // [B][nriv][R]   river inflow series, time fastest
-    double *y;                      // [B][nnode][R]  routed own-reach series
+    double *qout;                   // [B][nriv][R]   river inflow series, time fastest; fused routing (dcp_route_fused.cuh):
+                                    //                [slots][nriv][R] rings, one slot per member in flight
+    double *y;                      // [B][nnode][R]  routed own-reach series ([slots][nnode][R] when fused)
+    double *q_user;                 // fused routing: the caller's flow output [nriv x nstep x B] (ABI layout) or null
     double *d2, *dl2;               // [B][nriv][R]   per-step objective terms (null without observed flow)
     double *qs;                     // [B][nriv][R]   routed flow series kept for the moment sums (null without observed flow)
     // objective accumulators [nriv][B]

@@ -26,11 +26,16 @@
 #include "dcp_physics.cuh"
 #include "dcp_kernels.h"
 #include "dcp_resident_common.cuh"
+#include "dcp_route_fused.cuh"
 
 #include <cstdint>
 
 #define RES_COLS DCP_RES_COMPUTE      // unit columns per member slot (= HRU positions across the CTA)
 #define RES_RIVER 128                 // one warpgroup of river warps
+#define RES_ROUTE 32                  // H == 1 kernels: one more warp routes finished tiles and adds up the objective terms
+                                      // (dcp_route_fused.cuh); it is not part of the per-step CTA barrier
+// hand-over river warps -> routing warp: once per DCP_RT_TILE steps and per member group
+__device__ __forceinline__ void res_ab_sync() { asm volatile("bar.sync 2, %0;" ::"n"(RES_RIVER + RES_ROUTE) : "memory"); }
 #define RES_MAXPASS 4                 // chains per river lane
 #define RES_PARW 6                    // srmax, td, smax, szm, 1/srmax, 1/szm
 
@@ -292,6 +297,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
                                                const ResSmem &M) {
     constexpr int CT = RES_COLS / H;
     constexpr int THREADS = CT + RES_RIVER;
+    constexpr bool FUSED = H == 1;                          // qout goes to the member slot's ring, a routing warp follows
     const int tid = threadIdx.x;
     const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, nriv = C.nriv;
     const int qbf_stride = P.G * nac_pad * S;
@@ -312,6 +318,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
 
     for (int gi = blockIdx.x; gi < P.n_groups; gi += gridDim.x) {
         const int m_base = gi * Mc;
+        if (FUSED) res_ab_sync();                       // the routing warp is done with the rings of the previous group
         cta_sync<THREADS>();
         if (tid == CT) {                                // forcing tile 0 of this group
             const uint32_t b = tiles_done & 1;
@@ -393,12 +400,13 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
                         if (type == 0 && live && sub == 0) {
                             const int m = m_base + jm;
                             if (t > 0 && m < B)
-                                W.qout[((size_t)m * nriv + r) * W.R + ((t - 1) & W.Rmask)] = qb_prev[q] + qof;   // dyna_river.f90:43
+                                W.qout[((size_t)(FUSED ? blockIdx.x * Mc + jm : m) * nriv + r) * W.R + ((t - 1) & W.Rmask)] = qb_prev[q] + qof;   // dyna_river.f90:43
                         }
                         if (type == 0) qb_prev[q] = acc;
                     }
                 }
                 if (P.dbg) busy += clock64() - c0;
+                if (FUSED && t > 0 && (((t - 1) & (DCP_RT_TILE - 1)) == DCP_RT_TILE - 1 || drain)) res_ab_sync();   // tile of qout complete
                 if (drain) { ++t; break; }
                 cta_sync<THREADS>();
             }
@@ -412,11 +420,22 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
 // x 232 registers, 8 (HRU, member) units per thread of which LG run interleaved in one basic block —
 // fewer, fatter threads trade thread-level for instruction-level parallelism on the FP64 pipe.
 template <int H> struct ResRegs;
-template <> struct ResRegs<1> { static constexpr int compute = 112, river = 32; };   // launch cap 96: (96-32)*128 == (112-96)*512
+template <> struct ResRegs<1> { static constexpr int compute = 112, river = 32, route = 64; };   // launch cap 96: (96-32)*128 == (112-96)*512
 template <> struct ResRegs<2> { static constexpr int compute = 232, river = 40; };   // launch cap 168: (168-40)*128 == (232-168)*256
 
+// routing warp of the H == 1 kernels: one tile behind the river warps (dcp_route_fused.cuh)
+__device__ __forceinline__ void res_route_role(const DevCatchment &C, const DevBatch &W, const ResPlan &P) {
+    for (int gi = blockIdx.x; gi < P.n_groups; gi += gridDim.x) {
+        res_ab_sync();                                  // group start (pairs with the river warps')
+        for (int t0 = 0; t0 < C.nstep; t0 += DCP_RT_TILE) {
+            res_ab_sync();                              // qout of [t0, t0 + tile) is in the rings
+            rt_tile(C, W, gi * P.Mc, P.Mc, blockIdx.x * P.Mc, t0, min(C.nstep, t0 + DCP_RT_TILE));
+        }
+    }
+}
+
 template <int S, int H, int LG, int MODE, bool AET>
-__global__ void __launch_bounds__(RES_COLS / H + RES_RIVER, 1)
+__global__ void __launch_bounds__(RES_COLS / H + RES_RIVER + (H == 1 ? RES_ROUTE : 0), 1)
 k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
     constexpr bool FAST = MODE != 0;
     constexpr int CT = RES_COLS / H;
@@ -469,9 +488,12 @@ k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
     if (tid < CT) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ResRegs<H>::compute));
         res_compute_role<S, H, LG, MODE, AET>(C, W, P, M);
-    } else {
+    } else if (tid < THREADS) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ResRegs<H>::river));
         res_river_role<S, H, FAST>(C, W, P, M);
+    } else if (H == 1) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ResRegs<1>::route));
+        res_route_role(C, W, P);
     }
 }
 #undef gc
@@ -493,7 +515,7 @@ static cudaError_t launch_res(const DevCatchment &C, const DevBatch &W, const Re
     else k = aet ? k_physics_resident<S, H, 1, 0, true> : k_physics_resident<S, H, 1, 0, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
-    k<<<grid, RES_COLS / H + RES_RIVER, P.smem_bytes, s>>>(C, W, P);
+    k<<<grid, RES_COLS / H + RES_RIVER + (H == 1 ? RES_ROUTE : 0), P.smem_bytes, s>>>(C, W, P);
     return cudaGetLastError();
 }
 
@@ -511,7 +533,7 @@ static cudaError_t launch_lean(const DevCatchment &C, const DevBatch &W, const R
     void (*k)(DevCatchment, DevBatch, ResPlan) = aet ? k_physics_resident<S, H, LG, 2, true> : k_physics_resident<S, H, LG, 2, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
-    k<<<grid, RES_COLS / H + RES_RIVER, P.smem_bytes, s>>>(C, W, P);
+    k<<<grid, RES_COLS / H + RES_RIVER + (H == 1 ? RES_ROUTE : 0), P.smem_bytes, s>>>(C, W, P);
     return cudaGetLastError();
 }
 

@@ -43,21 +43,27 @@
 #include "dcp_physics.cuh"
 #include "dcp_kernels.h"
 #include "dcp_resident_common.cuh"
+#include "dcp_route_fused.cuh"
 
 #include <cstdint>
 
 #define R2_COLS DCP_RES_COMPUTE       // 512 unit columns per member slot
 #define R2_TEAMS 2
 #define R2_TC 128                     // compute threads per team (4 columns each)
-#define R2_TR 64                      // river threads per team
-#define R2_TT (R2_TC + R2_TR)         // threads at a team barrier
+#define R2_TR 64                      // river threads per team: warp A sums the river contributions of every step (and drives
+                                      // the forcing TMA), warp B routes finished tiles and accumulates the objective sums
+#define R2_TA 32                      // lanes of warp A
+#define R2_TT (R2_TC + R2_TA)         // threads at a team's per-step barrier (warp B is not part of it)
 #define R2_CT (R2_TEAMS * R2_TC)      // 256 compute threads
 #define R2_THREADS (R2_TEAMS * R2_TT) // 384
 #ifndef R2_REG_COMPUTE
 #define R2_REG_COMPUTE 240            // launch cap 168: (168-24)*128 == (240-168)*256
 #endif
 #ifndef R2_REG_RIVER
-#define R2_REG_RIVER 24
+#define R2_REG_RIVER 24               // warp A
+#endif
+#ifndef R2_REG_ROUTE
+#define R2_REG_ROUTE 40               // warp B; 8 x 240 + 2 x 24 + 2 x 40 = 2048 registers per lane slot = the whole file
 #endif
 #ifdef DCP_RES2_DEBUG                  // per-warp busy-cycle counters (tuning builds only: two registers and a branch per step)
 #define R2_DBG (P.dbg != nullptr)
@@ -112,6 +118,8 @@ __device__ __forceinline__ double2 lds_tuple(int lo, uint32_t buf_u32) {
 }
 
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(R2_TT) : "memory"); }
+// hand-over between a team's river-sum warp (A) and its routing warp (B): once per DCP_RT_TILE steps and per member group
+__device__ __forceinline__ void ab_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 3), "n"(R2_TR) : "memory"); }
 
 #define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})
 
@@ -397,8 +405,9 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 }
 
 // ---------------------------------------------------------------------------------------------
-// river role: 2 warps per team.  A group of T lanes adds up one (member sub-group, river) range of
-// contribution tuples, one step behind the compute warps; lane 0 also drives the team's forcing TMA.
+// river role, warp A of a team.  A group of T lanes adds up one (member sub-group, river) range of
+// contribution tuples, one step behind the compute warps, and stores qout(t) into the q RING of the member's
+// slot (dcp_route_fused.cuh); lane 0 also drives the team's forcing TMA.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
                                          const int team, const int rl) {
@@ -411,11 +420,13 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
     const int Mv = P.G * S;
     uint32_t tiles_done = 0;
     const int T = P.team, sub = rl & (T - 1);
-    const int sums_per_pass = R2_TR / T;
+    const int sums_per_pass = R2_TA / T;
+    const int sl_base = (blockIdx.x * R2_TEAMS + team) * Mv; // ring slots of this team (one per member in flight)
     long long busy = 0;
 
     for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
         const int m_base = vg * Mv;
+        ab_sync(team);                                       // warp B is done with the rings of the previous group
         team_sync(team);
         if (rl == 0) {                                       // forcing tile 0 of this group
             const uint32_t b = tiles_done & 1;
@@ -445,10 +456,11 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
                 if (live && sub == 0) {
                     const int m0 = m_base + g * S;
                     const size_t tq = (size_t)(tp & W.Rmask);
-                    if (m0 + 0 < B) W.qout[((size_t)(m0 + 0) * nriv + r) * W.R + tq] = a0;
-                    if (m0 + 1 < B) W.qout[((size_t)(m0 + 1) * nriv + r) * W.R + tq] = a1;
+                    if (m0 + 0 < B) W.qout[((size_t)(sl_base + g * S + 0) * nriv + r) * W.R + tq] = a0;
+                    if (m0 + 1 < B) W.qout[((size_t)(sl_base + g * S + 1) * nriv + r) * W.R + tq] = a1;
                 }
             }
+            if ((tp & (DCP_RT_TILE - 1)) == DCP_RT_TILE - 1 || tp == C.nstep - 1) ab_sync(team);   // tile complete: hand over to warp B
         };
 
         int t = 0;
@@ -475,11 +487,28 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// routing role, warp B of a team: route_process_run_step + river's division by frac_sub_area + the objective sums
+// for every finished tile of DCP_RT_TILE steps (dcp_route_fused.cuh), one tile behind warp A.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void r2_route(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const int team) {
+    const int Mv = P.G * R2_S;
+    const int sl_base = (blockIdx.x * R2_TEAMS + team) * Mv;
+    for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
+        const int m_base = vg * Mv;
+        ab_sync(team);                                       // group start (pairs with warp A's)
+        for (int t0 = 0; t0 < C.nstep; t0 += DCP_RT_TILE) {
+            ab_sync(team);                                   // qout of [t0, t0 + tile) is in the rings
+            rt_tile(C, W, m_base, Mv, sl_base, t0, min(C.nstep, t0 + DCP_RT_TILE));
+        }
+    }
+}
+
 template <bool AET, bool ONEPAR>
 __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchment C, DevBatch W, Res2Plan P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
-    // warps 0-3: team 0 compute, 4-7: team 1 compute, 8-9: team 0 river, 10-11: team 1 river
+    // warps 0-3: team 0 compute, 4-7: team 1 compute, 8: team 0 river sums (A), 9: team 0 routing (B), 10-11: the same for team 1
     const bool is_compute = tid < R2_CT;
     const int team = is_compute ? tid / R2_TC : (tid - R2_CT) / R2_TR;
     R2Smem M;
@@ -519,10 +548,14 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
             while (clock64() - t0 < P.phase_delay) {}
         }
         r2_compute<AET, ONEPAR>(C, W, P, M, team, tid % R2_TC);
-    } else {
+    } else if ((tid - R2_CT) % R2_TR < R2_TA) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_RIVER));
         if (P.phase_delay < 0 && team == 1) return;
         r2_river(C, W, P, M, team, (tid - R2_CT) % R2_TR);
+    } else {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_ROUTE));
+        if (P.phase_delay < 0 && team == 1) return;
+        r2_route(C, W, P, team);
     }
 }
 #undef gc
