@@ -72,6 +72,15 @@ class RunStats(C.Structure):
                 ("kernel_used", C.c_int32), ("hist_len", C.c_int32)]
 
 
+MAX_RANKS = 16
+
+
+class MultiStats(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("used_nccl", C.c_int32), ("kernel_used", C.c_int32), ("reserved", C.c_int32),
+                ("ms_wall", C.c_double), ("ms_gather", C.c_double), ("ms_busy_max", C.c_double), ("ms_busy_sum", C.c_double),
+                ("ms_rank_device", C.c_double * MAX_RANKS), ("ms_rank_wall", C.c_double * MAX_RANKS)]
+
+
 def _f64(a, order="F"):
     return np.require(np.asarray(a, dtype=np.float64), requirements=["A", "O"] + (["F"] if order == "F" else ["C"]))
 
@@ -190,6 +199,12 @@ def load_library(path: str = LIB_PATH):
     lib.dcp_get_run_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
     lib.dcp_route_timeseries.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     lib.dcp_measure_fp64_peak.argtypes = [c_double_p, c_double_p]
+    lib.dcp_comm_init.argtypes = [C.c_int, c_int32_p, C.POINTER(C.c_void_p)]
+    lib.dcp_comm_destroy.argtypes = [C.c_void_p]
+    lib.dcp_comm_size.argtypes = [C.c_void_p]
+    lib.dcp_comm_uses_nccl.argtypes = [C.c_void_p]
+    lib.dcp_run_ensemble_multi.argtypes = [C.c_void_p, C.POINTER(CatchmentDesc), C.c_int64, C.c_void_p, C.POINTER(RunOpts),
+                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(MultiStats)]
     _lib = lib
     return lib
 
@@ -294,6 +309,61 @@ class DeviceCatchment:
         s = RunStats()
         _check(self.lib, self.lib.dcp_get_run_stats(self._h, C.byref(s)), "dcp_get_run_stats")
         return {k: getattr(s, k) for k, _ in RunStats._fields_}
+
+
+class Communicator:
+    """dcp_comm: the ranks (one device each, or several ranks on one device for testing) of a multi-GPU run in ONE process."""
+
+    def __init__(self, n_ranks: int, devices=None):
+        self.lib = load_library()
+        self._h = C.c_void_p()
+        dv = None
+        if devices is not None:
+            self._dev = _i32(devices)
+            assert len(self._dev) == n_ranks
+            dv = self._dev.ctypes.data_as(c_int32_p)
+        _check(self.lib, self.lib.dcp_comm_init(int(n_ranks), dv, C.byref(self._h)), "dcp_comm_init")
+
+    @property
+    def uses_nccl(self):
+        return bool(self.lib.dcp_comm_uses_nccl(self._h))
+
+    def run(self, cat: Catchment, mcpar: np.ndarray, *, flags=0, kernel=KERNEL_AUTO, want_q=False, want_perf=True,
+            want_totals=False, members_per_batch=0):
+        """dcp_run_ensemble_multi: the whole (npt, 7, M) table over every rank; same outputs as DeviceCatchment.run."""
+        assert mcpar.dtype == np.float64 and mcpar.flags.f_contiguous and mcpar.shape[:2] == (cat.npt, 7)
+        M = mcpar.shape[2]
+        desc, keep = cat.to_desc()
+        q = np.empty((cat.nriv, cat.nstep, M), order="F") if want_q else None
+        perf = np.empty((NMEASURE, cat.nriv, M), order="F") if want_perf else None
+        tot = np.empty((3, cat.nriv, M), order="F") if want_totals else None
+        diag = np.empty((3, M), order="F")
+        status = np.zeros(M, dtype=np.int32)
+        opts = make_opts(flags, kernel, members_per_batch, 0)
+        st = MultiStats()
+
+        def p(a):
+            return a.ctypes.data_as(C.c_void_p) if a is not None else None
+        rc = self.lib.dcp_run_ensemble_multi(self._h, C.byref(desc), int(M), p(mcpar), C.byref(opts), p(q), p(perf), p(tot),
+                                             p(diag), p(status), C.byref(st))
+        del keep
+        _check(self.lib, rc, "dcp_run_ensemble_multi")
+        n = st.n_ranks
+        stats = dict(n_ranks=n, used_nccl=bool(st.used_nccl), kernel_used=st.kernel_used, ms_wall=st.ms_wall, ms_gather=st.ms_gather,
+                     ms_busy_max=st.ms_busy_max, ms_busy_sum=st.ms_busy_sum, ms_rank_device=list(st.ms_rank_device[:n]),
+                     ms_rank_wall=list(st.ms_rank_wall[:n]))
+        return dict(q=q, perf=perf, reach_totals=tot, init_diag=diag, status=status, mcpar=mcpar, stats=stats)
+
+    def close(self):
+        if self._h:
+            self.lib.dcp_comm_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def measure_fp64_peak():

@@ -72,6 +72,8 @@ cudaError_t upload(const std::vector<T> &v, const T **dst, std::vector<void *> &
 
 }  // namespace
 
+void dcp_internal_set_error(const char *msg) { g_err = msg ? msg : ""; }
+
 struct dcp_catchment {
     int device = 0;
     DevCatchment C{};
@@ -317,7 +319,8 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     Q.off_cst = take((size_t)S * COLS * 16);
     Q.off_par = take((size_t)G * S * npt * 3 * 16);
     Q.off_forc = take((size_t)2 * Q.Tt * (d->ngp + d->nge) * 8);
-    Q.off_bar = take(16);
+    Q.off_bar = take(32);
+    Q.off_sz = take((size_t)S * COLS * 16);                  // parked {srz, suz} of the split-barrier step
     Q.team_bytes = (int)((off + 8191) & ~(size_t)8191);     // team blocks (tuple buffers first) sit on 8 KB boundaries
     Q.smem_bytes = Q.off_team + 8192 + 2 * Q.team_bytes;    // + the kernel's alignment slack
     if ((size_t)Q.smem_bytes > c->smem_optin) return;

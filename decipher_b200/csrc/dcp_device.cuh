@@ -183,7 +183,7 @@ struct Res2Plan {
     int32_t phase_delay;            // cycles the second team waits at kernel start (0: none)
     int32_t smem_bytes, team_bytes;
     int32_t off_team;               // start of the team-private region; offsets below off_forc.. are relative to a team's base
-    int32_t off_qbf, off_con, off_cst, off_par, off_forc, off_bar;
+    int32_t off_qbf, off_con, off_cst, off_par, off_forc, off_bar, off_sz;
     int32_t off_ellw, off_coli, off_cold, off_rbeg;                // shared, absolute
     const double *ell_w;            // [ell_len] w * ac(src)   (dyna_dynamic_dist.f90:50-51), 0 in padding; the low 9
                                     //           mantissa bits hold the source's tuple index (0..511)

@@ -15,6 +15,7 @@
 #define DCP_RT_SLACK_STEPS 129        // = DCP_RT_SLACK of dcp_route_fused.cuh: ring length >= histogram span + two hand-over tiles + 1
 #define DCP_FORCING_PAD 64           // forcing arrays are zero-padded to a multiple of this many steps
 
+void dcp_internal_set_error(const char *msg);       // sets the calling thread's dcp_last_error() text (dcp_multi.cu)
 void dcp_launch_min_chv(const double *mcpar, int npt, int64_t n_member, double *out, cudaStream_t s);
 void dcp_launch_init(const DevCatchment &C, const DevBatch &W, double *mcpar, bool check, cudaStream_t s);
 cudaError_t dcp_launch_physics_streamed(const DevCatchment &C, const DevBatch &W, int t0, int t1, bool fast,

@@ -98,7 +98,9 @@ struct R2Smem {                       // team-private views unless noted
                           //                 two DMULs instead of an LDS.128 per unit and step, and 32 KB less shared memory
     double2 *par_s;       // [Mv][npt][3]    {srmax, 1/srmax}, {td/dt, smax}, {szm, dtt/szm}
     double *forc_s;       // [2][Tt*(ngp+nge)]
-    uint64_t *bars;       // [2]
+    uint64_t *bars;       // [2] forcing tiles (TMA) + [1] the split per-step barrier (R2_SPLIT)
+    double2 *sz_s;        // [2][4][128]     {srz, suz} per (member slot, column slot j, team thread), own-column: the two upper stores
+                          //                 are parked here while the thread gathers and solves the saturated zone (R2_SPLIT)
     // shared by both teams (read-only after setup)
     double *ellw_s;       // [ell_len]       packed gather list (weight | source tuple index)
     int4 *coli_s;         // [4][128]        per (column slot j, team thread): packed indices
@@ -120,6 +122,16 @@ __device__ __forceinline__ double2 lds_tuple(int lo, uint32_t buf_u32) {
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(R2_TT) : "memory"); }
 // hand-over between a team's river-sum warp (A) and its routing warp (B): once per DCP_RT_TILE steps and per member group
 __device__ __forceinline__ void ab_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 3), "n"(R2_TR) : "memory"); }
+
+// Split per-step barrier (R2_SPLIT): mbarrier with one arrival per compute thread and per lane of warp A.  A thread ARRIVES as
+// soon as it has published its step and waits for the phase only when it needs the other warps' results, so the work
+// that depends on nothing but the thread's own stores (root zone + unsaturated zone of the NEXT step) fills the wait.
+__device__ __forceinline__ void step_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+#ifndef R2_SPLIT
+#define R2_SPLIT 1
+#endif
 
 #define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})
 
@@ -405,6 +417,240 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 }
 
 // ---------------------------------------------------------------------------------------------
+// compute role with the SPLIT per-step barrier (R2_SPLIT): per step
+//     wait(step t-1 published by everyone) -> gather -> saturated zone -> publish -> ARRIVE(t) -> root + unsat zone of t+1
+// The unit's srz / suz are only touched by the upper zones, so they live in an own-column shared slot while the thread
+// gathers and solves (registers: sd, exp(sd/m2), uz, exus per unit -- the same 4 doubles per unit as the fused step).
+// ---------------------------------------------------------------------------------------------
+template <bool AET, bool ONEPAR>
+__device__ __forceinline__ void r2_compute_split(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
+                                                 const int team, const int tt_id) {
+    constexpr int H = R2_H, S = R2_S;
+    const int B = W.B, npt = C.npt;
+    const int forc_stride = P.Tt * (C.ngp + C.nge);
+    const int par_kstride = npt * 3;
+    const int Mv = P.G * S;
+    uint32_t tiles_done = 0, steps_done = 0;
+    uint64_t *sbar = &M.bars[2];
+
+    for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
+        const int m_base = vg * Mv;
+        team_sync(team);                                     // previous group fully done with shared memory
+
+        double sd[H][S], e1s[H][S], uzv[H][S], exv[H][S], aet[H][S];
+#pragma unroll
+        for (int j = 0; j < H; ++j) {
+            const int4 ci = M.coli_s[j * R2_TC + tt_id];
+            const int tup = ci.z & 0xffff, g = (ci.y >> 16) & 0x7fff;
+            const int ia = P.col_ia[j * R2_TC + tt_id];
+            const double cosm = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id].y;
+            const int ipar = ia >= 0 ? C.hru[ia].ipar : 0;
+#pragma unroll
+            for (int k = 0; k < S; ++k) {
+                const int m = m_base + g * S + k;
+                sd[j][k] = 1.0; aet[j][k] = 0.0;
+                double suz0 = 0.0, srz0 = 0.0, qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_im2 = 1.0;
+                if (ia >= 0 && m < B) {
+                    const size_t o = (size_t)ia * B + m;
+                    sd[j][k] = W.sd[o]; suz0 = W.suz[o]; srz0 = W.srz[o];
+                    c_q0 = W.q0[o]; c_q2 = W.q2[o];
+                    const double szm = W.par[(0 * npt + ipar) * (size_t)B + m];
+                    c_im2 = cosm * (1.0 / szm);
+                    qb0 = W.qbf0[o];
+                }
+                e1s[j][k] = exp(sd[j][k] * c_im2);
+                reinterpret_cast<double *>(M.qbf_s + tup)[k] = qb0;
+                reinterpret_cast<double *>(M.qbf_s + R2_COLS + tup)[k] = 0.0;
+                M.cst_s[(k * H + j) * R2_TC + tt_id] = make_double2(c_q0, c_q2);
+                M.sz_s[(k * H + j) * R2_TC + tt_id] = make_double2(srz0, suz0);
+            }
+        }
+        for (int i = tt_id; i < Mv * npt; i += R2_TC) {      // member parameters -> shared
+            const int jm = i / npt, l = i % npt;
+            const int m = m_base + jm;
+            double srmax = 1.0, td = 1.0, smax = 1.0, szm = 1.0;
+            if (m < B) {
+                szm = W.par[(0 * npt + l) * (size_t)B + m];
+                srmax = W.par[(2 * npt + l) * (size_t)B + m];
+                td = W.par[(5 * npt + l) * (size_t)B + m];
+                smax = W.par[(6 * npt + l) * (size_t)B + m];
+            }
+            M.par_s[i * 3 + 0] = make_double2(srmax, 1.0 / srmax);
+            M.par_s[i * 3 + 1] = make_double2(td / C.dt, smax);
+            M.par_s[i * 3 + 2] = make_double2(szm, C.dtt / szm);
+        }
+        team_sync(team);
+
+        // root zone + unsaturated zone of step `tn` for all of the thread's units (own state + forcing only)
+        auto upper = [&](const double *forc_t, int tt) {
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                const int4 ci = M.coli_s[j * R2_TC + tt_id];
+                const double p = forc_t[tt * C.ngp + (ci.y & 0xff)];
+                const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci.y >> 8) & 0xff)];     // already max(ep, 0)
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                    const double2 p0 = M.par_s[(ONEPAR ? 0 : (ci.w & 0xffff)) + k * par_kstride];
+                    const double2 p1 = M.par_s[(ONEPAR ? 0 : (ci.w & 0xffff)) + k * par_kstride + 1];
+                    double2 *slot = M.sz_s + (k * H + j) * R2_TC + tt_id;
+                    double2 z = *slot;
+                    double ea;
+                    hru_lean_upper(LeanUpperConst{p0.x, p0.y, p1.x}, C.inv_dtt, p, epp, sd[j][k], z.x, z.y, uzv[j][k], exv[j][k], ea);
+                    *slot = z;
+                    if (AET) aet[j][k] = aet[j][k] + ea;
+                }
+            }
+        };
+
+        const double *ent0 = M.ellw_s + (M.coli_s[tt_id].x & 0xfffff);
+        double wv0 = ent0[0];
+
+        int t = 0;
+        const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
+        mbar_wait(&M.bars[tiles_done & 1], (tiles_done >> 1) & 1);                   // forcing tile 0
+        upper(M.forc_s + (tiles_done & 1) * forc_stride, 0);
+        for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
+            const int t_end = min(C.nstep, t + P.Tt);
+            for (int tt = 0; t < t_end; ++t, ++tt, ++steps_done) {
+                const double2 *qbf_cur = M.qbf_s + (t & 1) * R2_COLS;
+                const uint32_t qcur_u32 = smem_u32(qbf_cur);
+                double2 *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * R2_COLS;
+                double2 *con = M.con_s + (t & 1) * R2_COLS;
+                // everyone has published step t-1 (and warp A is done with the contribution buffer this step overwrites)
+                if (t > 0) mbar_wait(sbar, (steps_done - 1) & 1);
+                const double *ep = ent0;
+#pragma unroll
+                for (int jp = 0; jp < H; jp += 2) {
+                    int4 ci[H];
+                    double qin[H][S];
+#pragma unroll
+                    for (int j = jp; j < jp + 2; ++j) {
+                        ci[j] = M.coli_s[j * R2_TC + tt_id];
+                        const int nb = ci[j].x >> 20;
+                        double qa[R2_NACC][2];
+#pragma unroll
+                        for (int u = 0; u < R2_NACC; ++u) { qa[u][0] = 0.0; qa[u][1] = 0.0; }
+                        int bb = 0;
+#if R2_LONG > 1
+                        if (j == 0) {
+#pragma unroll 1
+                            for (; bb + R2_LONG * R2_NACC <= nb; bb += R2_LONG * R2_NACC) {
+#pragma unroll
+                                for (int u = 0; u < R2_LONG * R2_NACC; ++u) {
+                                    const double wc = wv0;
+                                    const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
+                                    ep += 32;
+                                    wv0 = ep[0];
+                                    qa[u % R2_NACC][0] = fma(qv.x, wc, qa[u % R2_NACC][0]);
+                                    qa[u % R2_NACC][1] = fma(qv.y, wc, qa[u % R2_NACC][1]);
+                                }
+                            }
+                        }
+#endif
+#pragma unroll 1
+                        for (; bb + R2_NACC <= nb; bb += R2_NACC) {
+#pragma unroll
+                            for (int u = 0; u < R2_NACC; ++u) {
+                                const double wc = wv0;
+                                const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
+                                ep += 32;
+                                wv0 = ep[0];
+                                qa[u][0] = fma(qv.x, wc, qa[u][0]); qa[u][1] = fma(qv.y, wc, qa[u][1]);
+                            }
+                        }
+#pragma unroll 1
+                        for (; bb < nb; ++bb) {
+                            const double wc = wv0;
+                            const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
+                            ep += 32;
+                            wv0 = ep[0];
+                            qa[0][0] = fma(qv.x, wc, qa[0][0]); qa[0][1] = fma(qv.y, wc, qa[0][1]);
+                        }
+                        double q0 = qa[0][0], q1 = qa[0][1];
+#pragma unroll
+                        for (int u = 1; u < R2_NACC; ++u) { q0 += qa[u][0]; q1 += qa[u][1]; }
+                        qin[j][0] = q0; qin[j][1] = q1;
+                    }
+                    // ---- saturated zone: 4 interleaved dependency chains ----
+                    double qbn[2][S], exac[2][S], sd0[2][S], cq[2];
+                    bool slow[2][S], any_slow = false;
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int j = jp + jj;
+                        const double2 d0 = M.cold_s[j * R2_TC + tt_id];                          // {ac, 1/ac}
+                        const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];           // {cq, cos}
+                        const double icos = M.cold_s[2 * R2_H * R2_TC + j * R2_TC + tt_id].x;
+                        cq[jj] = d1.x;
+#pragma unroll
+                        for (int k = 0; k < S; ++k) {
+                            const double2 c0v = M.cst_s[(k * H + j) * R2_TC + tt_id];
+                            const double2 p1 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 1];
+                            const double2 p2 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 2];
+                            LeanSatConst c;
+                            c.ac = d0.x; c.inv_ac = d0.y; c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.dtt_inv_m2 = d1.y * p2.y;
+                            c.q1 = c.q0 * d1.y; c.smax = p1.y;
+                            sd0[jj][k] = sd[j][k];
+                            slow[jj][k] = hru_lean_sat(c, C.dtt, C.inv_dtt, qin[j][k], uzv[j][k], exv[j][k], sd[j][k], e1s[j][k], qbn[jj][k], exac[jj][k]);
+                            any_slow |= slow[jj][k];
+                        }
+                    }
+                    if (__builtin_expect(any_slow, 0)) {                                         // rare: sd > smax, out-of-range exponent
+#pragma unroll
+                        for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                            for (int k = 0; k < S; ++k)
+                                if (slow[jj][k]) {
+                                    const int j = jp + jj;
+                                    const R2Fix f = r2_fix_unit(smem_u32(M.cst_s + (k * H + j) * R2_TC + tt_id),
+                                                                smem_u32(M.par_s + (ci[j].w & 0xffff) + k * par_kstride),
+                                                                smem_u32(M.cold_s + j * R2_TC + tt_id), C.dtt, C.inv_dtt, C.ntt,
+                                                                qin[j][k], uzv[j][k], exv[j][k], sd0[jj][k]);
+                                    sd[j][k] = f.sd; qbn[jj][k] = f.qbf; exac[jj][k] = f.exac; e1s[j][k] = f.e1;
+                                }
+                    }
+                    double2 qold[2];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) qold[jj] = qbf_cur[ci[jp + jj].z & 0xffff];
+#pragma unroll
+                    for (int jj = 0; jj < 2; ++jj) {
+                        const int j = jp + jj;
+                        const int tup = ci[j].z & 0xffff, ctup = (int)((uint32_t)ci[j].w >> 16);
+                        if (ci[j].y >= 0) qbf_nxt[tup] = make_double2(qbn[jj][0], qbn[jj][1]);
+                        con[ctup] = make_double2(fma(cq[jj], qold[jj].x, exac[jj][0]), fma(cq[jj], qold[jj].y, exac[jj][1]));
+                    }
+                }
+                step_arrive(sbar);                                                               // step t published
+                wv0 = ent0[0];                                                                   // next step's first gather entry
+                // ---- root zone + unsaturated zone of step t+1 while the other warps finish step t ----
+                if (t + 1 < C.nstep) {
+                    uint32_t td = tiles_done;
+                    int ttn = tt + 1;
+                    if (ttn == P.Tt) {                                                           // first step of the next forcing tile
+                        ++td; ttn = 0;
+                        mbar_wait(&M.bars[td & 1], (td >> 1) & 1);
+                    }
+                    upper(M.forc_s + (td & 1) * forc_stride, ttn);
+                }
+            }
+        }
+        // the last step's phase: nobody waits for it inside the loop, so consume it here (keeps the parity count in step)
+        mbar_wait(sbar, (steps_done - 1) & 1);
+        if (AET) {
+#pragma unroll
+            for (int j = 0; j < H; ++j) {
+                const int ia = P.col_ia[j * R2_TC + tt_id];
+                const int g = (M.coli_s[j * R2_TC + tt_id].y >> 16) & 0x7fff;
+#pragma unroll
+                for (int k = 0; k < S; ++k) {
+                    const int m = m_base + g * S + k;
+                    if (ia >= 0 && m < B) W.aet[(size_t)ia * B + m] = aet[j][k];
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // river role, warp A of a team.  A group of T lanes adds up one (member sub-group, river) range of
 // contribution tuples, one step behind the compute warps, and stores qout(t) into the q RING of the member's
 // slot (dcp_route_fused.cuh); lane 0 also drives the team's forcing TMA.
@@ -422,6 +668,7 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
     const int T = P.team, sub = rl & (T - 1);
     const int sums_per_pass = R2_TA / T;
     const int sl_base = (blockIdx.x * R2_TEAMS + team) * Mv; // ring slots of this team (one per member in flight)
+    uint32_t steps_done = 0;
     long long busy = 0;
 
     for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
@@ -479,7 +726,13 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
                 const long long c0 = R2_DBG ? clock64() : 0;
                 if (t > 0) flush_step(t - 1);                // while the compute warps run step t
                 if (R2_DBG) busy += clock64() - c0;
+#if R2_SPLIT
+                step_arrive(&M.bars[2]);                     // done with the contribution buffer of step t-1 ...
+                mbar_wait(&M.bars[2], steps_done & 1);       // ... and step t is published
+                ++steps_done;
+#else
                 team_sync(team);
+#endif
             }
         }
         flush_step(C.nstep - 1);
@@ -522,6 +775,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     M.par_s = (double2 *)(tb + P.off_par);
     M.forc_s = (double *)(tb + P.off_forc);
     M.bars = (uint64_t *)(tb + P.off_bar);
+    M.sz_s = (double2 *)(tb + P.off_sz);
     M.ellw_s = (double *)(smem + P.off_ellw);
     M.coli_s = (int4 *)(smem + P.off_coli);
     M.cold_s = (double2 *)(smem + P.off_cold);
@@ -536,6 +790,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     if (!is_compute && (tid - R2_CT) % R2_TR == 0) {
         mbar_init(&M.bars[0], 1);
         mbar_init(&M.bars[1], 1);
+        mbar_init(&M.bars[2], R2_TT);                        // split per-step barrier: 128 compute threads + warp A
         fence_mbar_init();
     }
     __syncthreads();
@@ -547,7 +802,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
             const long long t0 = clock64();
             while (clock64() - t0 < P.phase_delay) {}
         }
+#if R2_SPLIT
+        r2_compute_split<AET, ONEPAR>(C, W, P, M, team, tid % R2_TC);
+#else
         r2_compute<AET, ONEPAR>(C, W, P, M, team, tid % R2_TC);
+#endif
     } else if ((tid - R2_CT) % R2_TR < R2_TA) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_RIVER));
         if (P.phase_delay < 0 && team == 1) return;

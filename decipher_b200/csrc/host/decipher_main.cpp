@@ -5,10 +5,21 @@
 // mirrors `program main` (RRMODEL/dyna_main.f90:85-206): reads project.dat / settings / params /
 // model_structure and the DTA files, samples every parameter set with RANMAR (bit-exact with the
 // reference, which draws them inside the loop from the same single stream), then makes ONE
-// dcp_run_ensemble call on the GPU instead of the serial `do i_mc` loop and writes the same
-// mc_id_%08d.res / .flow files plus a binary table of performance measures.
+// dcp_run_ensemble call on the GPU (dcp_run_ensemble_multi over -gpus N devices) instead of the serial `do i_mc`
+// loop and writes the same mc_id_%08d.res / .flow files plus a binary table of parameters and performance measures.
+//
+// Output at ensemble scale (the reference writes two text files per member,
+// RRMODEL/dyna_write_output.f90:44-100, dyna_file_open.f90:26-41):
+//   -no-flow               measures only: <prefix>ensemble_perf.bin, nothing per member
+//   -write-members a:b,c   text .res/.flow files for the selected members only (1-based, ranges inclusive)
+//   -flow-bin              the selected members' flow series as FP64 in <prefix>ensemble_flow.bin (text .flow keeps
+//                          ~4 significant digits of m/timestep flows; the binary file carries every bit)
+//   ensemble_perf.bin v2   header {magic "DCPPERF2", int64 numsim, nriv, nmeasure, npt}, then mcpar[npt x 7 x numsim]
+//                          (AFTER the srinit clip, the values the .res table prints), perf[nmeasure x nriv x numsim],
+//                          status[numsim] -- the sampled parameter sets sit next to their measures
 #include "dcp_host.h"
 
+#include <algorithm>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -18,12 +29,16 @@
 
 static void usage() {
     fprintf(stderr,
-            "usage: decipher_b200_run [-auto <file>] [-ids P C F] [-dir <workdir>] [-members N] [-no-flow] [-fast] [-check]\n"
+            "usage: decipher_b200_run [-auto <file>] [-ids P C F] [-dir <workdir>] [-members N] [-no-flow] [-write-members LIST]\n"
+            "                         [-flow-bin] [-gpus N] [-fast] [-check]\n"
             "  -auto <file>   three lines: project id, catchment-setup id, input-setup id (as the reference)\n"
             "  -ids P C F     the same three ids on the command line\n"
             "  -dir <workdir> directory holding project.dat (default: current directory)\n"
             "  -members N     override numsim of params.dat\n"
             "  -no-flow       do not write per-member .res/.flow text files (large ensembles)\n"
+            "  -write-members LIST  per-member files for these members only, e.g. 1:10,250,9000:9003 (1-based, inclusive)\n"
+            "  -flow-bin      also write the selected members' flows as FP64 to <prefix>ensemble_flow.bin\n"
+            "  -gpus N        spread the members over N devices (dcp_run_ensemble_multi; one gather of the measures)\n"
             "  -fast          DCP_OPT_FAST_MATH;  -check  DCP_OPT_CHECK_BALANCE (results_ts STOP conditions as flags)\n");
 }
 
@@ -32,8 +47,9 @@ int main(int argc, char **argv) {
     std::string workdir = ".", auto_file;
     int ids[3] = {0, 0, 0};
     long members = -1;
-    bool write_text = true;
-    int flags = 0;
+    bool write_text = true, flow_bin = false;
+    std::string member_list;
+    int flags = 0, n_gpus = 1;
     for (int i = 1; i < argc; ++i) {
         const std::string a = argv[i];
         if (a == "-auto" && i + 1 < argc) auto_file = argv[++i];
@@ -41,6 +57,9 @@ int main(int argc, char **argv) {
         else if (a == "-dir" && i + 1 < argc) workdir = argv[++i];
         else if (a == "-members" && i + 1 < argc) members = atol(argv[++i]);
         else if (a == "-no-flow") write_text = false;
+        else if (a == "-write-members" && i + 1 < argc) member_list = argv[++i];
+        else if (a == "-flow-bin") flow_bin = true;
+        else if (a == "-gpus" && i + 1 < argc) n_gpus = atoi(argv[++i]);
         else if (a == "-fast") flags |= DCP_OPT_FAST_MATH;
         else if (a == "-check") flags |= DCP_OPT_CHECK_BALANCE;
         else { usage(); return 2; }
@@ -66,13 +85,36 @@ int main(int argc, char **argv) {
     FILE *log = fopen(dcph_log_path(M), "w");
     if (log) fprintf(log, " --- DYMOND ---\n \n Reading in project files\n Number of HRUs %d\n", d->nac);
 
+    // members whose series are wanted on the host: all (reference behaviour), none (-no-flow) or the -write-members list
+    std::vector<long> selected;                       // 0-based, ascending, unique
+    if (!member_list.empty()) {
+        const char *p = member_list.c_str();
+        while (*p) {
+            char *e = nullptr;
+            long a = strtol(p, &e, 10), b = a;
+            if (e == p) { fprintf(stderr, "-write-members: cannot parse '%s'\n", p); return 2; }
+            if (*e == ':') { p = e + 1; b = strtol(p, &e, 10); if (e == p) { fprintf(stderr, "-write-members: bad range\n"); return 2; } }
+            if (a < 1 || b < a || b > numsim) { fprintf(stderr, "-write-members: %ld:%ld outside 1..%ld\n", a, b, numsim); return 2; }
+            for (long m = a; m <= b; ++m) selected.push_back(m - 1);
+            p = e;
+            if (*p == ',') ++p;
+            else if (*p) { fprintf(stderr, "-write-members: unexpected '%c'\n", *p); return 2; }
+        }
+        std::sort(selected.begin(), selected.end());
+        selected.erase(std::unique(selected.begin(), selected.end()), selected.end());
+        write_text = true;
+    } else if (write_text) {
+        for (long m = 0; m < numsim; ++m) selected.push_back(m);
+    }
+
     if (dcp_device_count() < 1) { fprintf(stderr, "no CUDA device: this build has no CPU fallback\n"); return 1; }
+    if (n_gpus < 1 || n_gpus > DCP_MAX_RANKS) { fprintf(stderr, "-gpus must be in 1..%d\n", DCP_MAX_RANKS); return 2; }
     dcp_catchment *cat = nullptr;
     if (dcp_catchment_create(d, &cat) != DCP_OK) { fprintf(stderr, "dcp_catchment_create: %s\n", dcp_last_error()); return 1; }
 
     const size_t npar = (size_t)d->npt * 7;
     std::vector<double> mcpar(npar * numsim), perf((size_t)DCP_NMEASURE * d->nriv * numsim),
-        totals((size_t)3 * d->nriv * numsim), diag((size_t)3 * numsim);
+        totals(n_gpus > 1 ? 0 : (size_t)3 * d->nriv * numsim), diag((size_t)3 * numsim);
     std::vector<int32_t> status(numsim);
     dcph_genpar(M, numsim, mcpar.data());
     if (log) fprintf(log, " \n Looping through simulations...\n");
@@ -81,33 +123,71 @@ int main(int argc, char **argv) {
     opts.struct_size = sizeof(opts);
     opts.flags = flags;
     const auto t0 = std::chrono::steady_clock::now();
-    // text output needs the flow series on the host: run those members in chunks that fit in memory
-    const long chunk = write_text ? std::max<long>(1, std::min<long>(numsim, (long)(2e9 / (8.0 * d->nriv * d->nstep)))) : numsim;
-    std::vector<double> q;
-    if (write_text) q.resize((size_t)d->nriv * d->nstep * chunk);
-    for (long m0 = 0; m0 < numsim; m0 += chunk) {
-        const long n = std::min(chunk, numsim - m0);
-        const int rc = dcp_run_ensemble(cat, m0 + 1, n, mcpar.data() + npar * m0, &opts, write_text ? q.data() : nullptr,
-                                        perf.data() + (size_t)DCP_NMEASURE * d->nriv * m0, totals.data() + (size_t)3 * d->nriv * m0,
-                                        diag.data() + (size_t)3 * m0, status.data() + m0);
+    // (1) every member: measures, reach totals, diagnostics, status -- nothing of length nstep leaves the device
+    if (n_gpus > 1) {
+        dcp_comm *comm = nullptr;
+        if (dcp_comm_init(n_gpus, nullptr, &comm) != DCP_OK) { fprintf(stderr, "dcp_comm_init: %s\n", dcp_last_error()); return 1; }
+        dcp_multi_stats ms{};
+        // reach totals are only printed for the selected members (re-run below), so the multi-device pass gathers measures only
+        if (dcp_run_ensemble_multi(comm, d, numsim, mcpar.data(), &opts, nullptr, perf.data(), nullptr, diag.data(), status.data(), &ms) != DCP_OK) {
+            fprintf(stderr, "dcp_run_ensemble_multi: %s\n", dcp_last_error());
+            return 1;
+        }
+        printf(" %d devices%s: slowest rank %.1f ms busy, mean %.1f ms, gather %.2f ms\n", ms.n_ranks, ms.used_nccl ? " (NCCL gather)" : "",
+               ms.ms_busy_max, ms.ms_busy_sum / ms.n_ranks, ms.ms_gather);
+        dcp_comm_destroy(comm);
+    } else {
+        const int rc = dcp_run_ensemble(cat, 1, numsim, mcpar.data(), &opts, nullptr, perf.data(), totals.data(), diag.data(), status.data());
         if (rc != DCP_OK) { fprintf(stderr, "dcp_run_ensemble: %s\n", dcp_last_error()); return 1; }
-        if (write_text)
-            for (long m = 0; m < n; ++m) {
-                printf(" Running sim %12ld\n", m0 + m + 1);
-                if (dcph_write_member(M, m0 + m + 1, mcpar.data() + npar * (m0 + m), q.data() + (size_t)d->nriv * d->nstep * m,
-                                      totals.data() + (size_t)3 * d->nriv * (m0 + m), diag.data() + (size_t)3 * (m0 + m),
-                                      status[m0 + m], 0) != DCP_OK) {
-                    fprintf(stderr, "write_output: %s\n", dcph_last_error());
-                    return 1;
-                }
-            }
     }
+    // (2) the selected members again, in chunks that fit in host memory, with their flow series: text files in the
+    //     reference's formats and / or the binary flow table.  Members are independent, so re-running a subset gives
+    //     the same bits as the ensemble pass.
+    FILE *fbin = nullptr;
+    if (flow_bin && !selected.empty()) {
+        const std::string fn = std::string(dcph_out_prefix(M)) + "ensemble_flow.bin";
+        fbin = fopen(fn.c_str(), "wb");
+        if (!fbin) { fprintf(stderr, "cannot open %s\n", fn.c_str()); return 1; }
+        const char magic[8] = {'D', 'C', 'P', 'F', 'L', 'O', 'W', '1'};
+        const int64_t hdr[3] = {(int64_t)selected.size(), d->nriv, d->nstep};
+        fwrite(magic, 1, 8, fbin); fwrite(hdr, 8, 3, fbin);
+        for (long m : selected) { const int64_t id = m + 1; fwrite(&id, 8, 1, fbin); }       // member ids, then q[nriv x nstep] each
+    }
+    const long chunk = std::max<long>(1, (long)(2e9 / (8.0 * d->nriv * d->nstep)));
+    std::vector<double> q, mc_sel, perf_sel, tot_sel, diag_sel;
+    std::vector<int32_t> st_sel;
+    for (size_t s0 = 0; s0 < selected.size(); s0 += chunk) {
+        const long n = (long)std::min<size_t>(chunk, selected.size() - s0);
+        q.resize((size_t)d->nriv * d->nstep * n); mc_sel.resize(npar * n); perf_sel.resize((size_t)DCP_NMEASURE * d->nriv * n);
+        tot_sel.resize((size_t)3 * d->nriv * n); diag_sel.resize((size_t)3 * n); st_sel.resize(n);
+        // parameter sets BEFORE the clip are needed as input: regenerate the table once (cheap, bit-exact RANMAR)
+        static std::vector<double> mc_in;
+        if (mc_in.empty()) { mc_in.resize(npar * numsim); dcph_genpar(M, numsim, mc_in.data()); }
+        for (long k = 0; k < n; ++k) std::memcpy(&mc_sel[npar * k], &mc_in[npar * selected[s0 + k]], npar * 8);
+        const int rc = dcp_run_ensemble(cat, selected[s0] + 1, n, mc_sel.data(), &opts, q.data(), perf_sel.data(), tot_sel.data(),
+                                        diag_sel.data(), st_sel.data());
+        if (rc != DCP_OK) { fprintf(stderr, "dcp_run_ensemble (selected members): %s\n", dcp_last_error()); return 1; }
+        for (long k = 0; k < n; ++k) {
+            const long m = selected[s0 + k];
+            printf(" Running sim %12ld\n", m + 1);
+            if (dcph_write_member(M, m + 1, &mc_sel[npar * k], &q[(size_t)d->nriv * d->nstep * k], &tot_sel[(size_t)3 * d->nriv * k],
+                                  &diag_sel[(size_t)3 * k], st_sel[k], 0) != DCP_OK) {
+                fprintf(stderr, "write_output: %s\n", dcph_last_error());
+                return 1;
+            }
+            if (fbin) fwrite(&q[(size_t)d->nriv * d->nstep * k], 8, (size_t)d->nriv * d->nstep, fbin);
+        }
+    }
+    if (fbin) fclose(fbin);
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-    // binary performance table: header (int64 numsim, nriv, nmeasure) then perf, status
+    // binary table: the sampled parameter sets (after the srinit clip) next to their measures
     const std::string table = std::string(dcph_out_prefix(M)) + "ensemble_perf.bin";
     if (FILE *f = fopen(table.c_str(), "wb")) {
-        const int64_t hdr[3] = {numsim, d->nriv, DCP_NMEASURE};
-        fwrite(hdr, 8, 3, f);
+        const char magic[8] = {'D', 'C', 'P', 'P', 'E', 'R', 'F', '2'};
+        const int64_t hdr[4] = {numsim, d->nriv, DCP_NMEASURE, d->npt};
+        fwrite(magic, 1, 8, f);
+        fwrite(hdr, 8, 4, f);
+        fwrite(mcpar.data(), 8, mcpar.size(), f);
         fwrite(perf.data(), 8, perf.size(), f);
         fwrite(status.data(), 4, status.size(), f);
         fclose(f);

@@ -108,3 +108,28 @@ def write_project(raw: Dict, root: str, ll: np.ndarray, ul: np.ndarray, numsim: 
     with open(os.path.join(root, "auto.dat"), "w") as f:
         f.write("1\n1\n1\n")
     return root
+
+
+def read_perf_table(path: str) -> Dict:
+    """<prefix>ensemble_perf.bin written by decipher_b200_run (v2): the sampled parameter sets (after the srinit clip of
+    dyna_init_satzone.f90:203-206) next to their performance measures and status words."""
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"DCPPERF2", raw[:8]
+    numsim, nriv, nmeasure, npt = np.frombuffer(raw[8:40], dtype=np.int64).tolist()
+    o = 40
+    n = npt * 7 * numsim
+    mcpar = np.frombuffer(raw[o:o + 8 * n], dtype=np.float64).reshape((npt, 7, numsim), order="F"); o += 8 * n
+    n = nmeasure * nriv * numsim
+    perf = np.frombuffer(raw[o:o + 8 * n], dtype=np.float64).reshape((nmeasure, nriv, numsim), order="F"); o += 8 * n
+    status = np.frombuffer(raw[o:o + 4 * numsim], dtype=np.int32)
+    return dict(mcpar=mcpar, perf=perf, status=status)
+
+
+def read_flow_table(path: str) -> Dict:
+    """<prefix>ensemble_flow.bin (decipher_b200_run -flow-bin): FP64 flow series q(nriv, nstep) of the selected members."""
+    raw = open(path, "rb").read()
+    assert raw[:8] == b"DCPFLOW1", raw[:8]
+    nsel, nriv, nstep = np.frombuffer(raw[8:32], dtype=np.int64).tolist()
+    ids = np.frombuffer(raw[32:32 + 8 * nsel], dtype=np.int64)
+    q = np.frombuffer(raw[32 + 8 * nsel:], dtype=np.float64).reshape((nriv, nstep, nsel), order="F")
+    return dict(members=ids, q=q)

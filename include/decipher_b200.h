@@ -28,13 +28,14 @@
 #ifndef DECIPHER_B200_H
 #define DECIPHER_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
 extern "C" {
 #endif
 
-#define DCP_ABI_VERSION 2   /* 2: DCP_NMEASURE 2 -> 5 (layout of perf_out) and dcp_route_timeseries */
+#define DCP_ABI_VERSION 3   /* 2: DCP_NMEASURE 2 -> 5 (layout of perf_out) and dcp_route_timeseries; 3: dcp_comm_* / dcp_run_ensemble_multi */
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define DCP_OK               0
@@ -216,6 +217,42 @@ int  dcp_route_timeseries(dcp_catchment *c, int64_t n_series, const double *velo
                           double *routed, int32_t *status, int32_t flags);
 
 int  dcp_get_run_stats(const dcp_catchment *c, dcp_run_stats *out);
+
+/* ---- all GPUs of one box (dcp_comm_init / dcp_gather_perf) ----------------------------------------
+ * One process, one host thread per rank.  Rank r owns device devices[r] (NULL: rank r -> device r) and runs the
+ * contiguous member block [r*M/G + min(r, M mod G), ...) of the caller's parameter table, so the results do not
+ * depend on the number of ranks.  The data path has no collective; the only exchange is ONE gather of the per-member
+ * measures, init diagnostics and status words to rank 0 at the end of the run -- NCCL point-to-point over NVLink when
+ * every rank has its own device (libnccl.so.2 is loaded at run time), plain device copies when ranks share a device
+ * (several ranks on one GPU: testing).                                                                           */
+#define DCP_MAX_RANKS 16
+typedef struct dcp_comm dcp_comm;
+typedef struct dcp_multi_stats {
+    int32_t n_ranks;
+    int32_t used_nccl;          /* 1: the gather went through NCCL                                              */
+    int32_t kernel_used;        /* of rank 0                                                                     */
+    int32_t reserved;
+    double ms_wall;             /* host wall clock of the whole call                                             */
+    double ms_gather;           /* the end-of-run gather + copy to the caller's arrays                           */
+    double ms_busy_max;         /* slowest rank, CUDA events (dcp_run_stats.ms_total)                            */
+    double ms_busy_sum;
+    double ms_rank_device[DCP_MAX_RANKS];   /* per rank: CUDA-event time of its dcp_run_ensemble                 */
+    double ms_rank_wall[DCP_MAX_RANKS];     /* per rank: host wall clock incl. catchment upload                  */
+} dcp_multi_stats;
+
+int  dcp_comm_init(int n_ranks, const int *devices, dcp_comm **out);
+int  dcp_comm_destroy(dcp_comm *c);
+int  dcp_comm_size(const dcp_comm *c);
+int  dcp_comm_uses_nccl(const dcp_comm *c);
+/* Replaces the loop `do i_mc = 1, numsim` (RRMODEL/dyna_main.f90:166-206) over every rank of the communicator.
+ * Arguments as dcp_run_ensemble (HOST buffers); when q_out or reach_totals is requested each device writes its
+ * block straight into the caller's arrays and nothing is gathered.                                              */
+int  dcp_run_ensemble_multi(dcp_comm *c, const dcp_catchment_desc *desc, int64_t n_member, double *mcpar,
+                            const dcp_run_opts *opts, double *q_out, double *perf_out, double *reach_totals,
+                            double *init_diag, int32_t *status, dcp_multi_stats *stats);
+/* The collective alone: bytes[r] bytes at send[r] (device memory of rank r) -> back to back, in rank order, in the
+ * communicator's reusable root buffer on rank 0's device (*root_out).                                           */
+int  dcp_gather_bytes(dcp_comm *c, const void *const *send, const size_t *bytes, void **root_out);
 
 /* Standalone FP64 pipe micro-benchmark (dependency-free DFMA chains) used as the roofline
    denominator; returns TFLOP/s (2 flops per DFMA) in *tflops. */

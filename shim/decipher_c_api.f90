@@ -80,5 +80,28 @@ module decipher_c_api
             type(c_ptr), value :: velocity, inflow, routed, status
             integer(c_int32_t), value :: flags
         end function
+        ! ---- every GPU of the box: the MC loop of dyna_main.f90:166-206 over all ranks of a communicator ----
+        ! devices(n_ranks): CUDA device of each rank, or c_null_ptr for rank r -> device r
+        integer(c_int) function dcp_comm_init(n_ranks, devices, comm) bind(C, name="dcp_comm_init")
+            import :: c_int, c_ptr
+            integer(c_int), value :: n_ranks
+            type(c_ptr), value :: devices
+            type(c_ptr), intent(out) :: comm
+        end function
+        integer(c_int) function dcp_comm_destroy(comm) bind(C, name="dcp_comm_destroy")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: comm
+        end function
+        ! arguments as dcp_run_ensemble, over ALL members; stats: c_null_ptr or a dcp_multi_stats (see the C header)
+        integer(c_int) function dcp_run_ensemble_multi(comm, desc, n_member, mcpar, opts, q_out, perf_out, reach_totals, &
+                                                       init_diag, status, stats) bind(C, name="dcp_run_ensemble_multi")
+            import :: c_int, c_int64_t, c_ptr, dcp_catchment_desc, dcp_run_opts
+            type(c_ptr), value :: comm
+            type(dcp_catchment_desc), intent(in) :: desc
+            integer(c_int64_t), value :: n_member
+            type(c_ptr), value :: mcpar
+            type(dcp_run_opts), intent(in) :: opts
+            type(c_ptr), value :: q_out, perf_out, reach_totals, init_diag, status, stats
+        end function
     end interface
 end module decipher_c_api

@@ -37,12 +37,47 @@ def test_cli_matches_oracle(tmp_path):
         assert float(row[12:22]) == pytest.approx(ref["mcpar"][0, 0, m], abs=5.1e-5)
         j = res.index("! ET TOTALS (mm)")
         assert [float(x) for x in res[j + 1].split()] == pytest.approx(list(ref["reach_totals"][2, :, m]), abs=5.1e-3)
-    raw_tab = open(p.out_prefix + "ensemble_perf.bin", "rb").read()
-    hdr = np.frombuffer(raw_tab[:24], dtype=np.int64)
-    from decipher_b200.capi import NMEASURE
     from parity import compare_perf
-    assert hdr.tolist() == [6, 2, NMEASURE]
-    n = NMEASURE * 2 * 6
-    perf = np.frombuffer(raw_tab[24:24 + 8 * n], dtype=np.float64).reshape((NMEASURE, 2, 6), order="F")
-    compare_perf(perf, ref["perf"])
+    tab = formats.read_perf_table(p.out_prefix + "ensemble_perf.bin")
+    compare_perf(tab["perf"], ref["perf"])
+    assert np.array_equal(tab["mcpar"], ref["mcpar"])            # the parameter sets sit next to their measures (after the clip)
+    assert np.array_equal(tab["status"], ref["status"])
+    p.close()
+
+
+def test_cli_selected_members_binary_flows_and_two_ranks(tmp_path):
+    """Ensemble-scale output: text files for the selected members only, their flows as FP64,
+    measures of every member in the table; the same run over two ranks (dcp_run_ensemble_multi; both on device 0 when
+    the box has one GPU is not possible from the CLI, so -gpus 2 is exercised only with two devices)."""
+    import glob
+    root = str(tmp_path)
+    raw = synth.make_raw(nac=40, nriv=3, npt=2, ngp=2, nge=1, nstep=400, kW=4, seed=101, tree=True)
+    ll, ul = synth.example_bounds(2)
+    formats.write_project(raw, root, ll, ul, numsim=40, seeds=(5, 2000))
+    r = subprocess.run([EXE, "-dir", root, "-ids", "1", "1", "1", "-write-members", "3:5,17,40", "-flow-bin", "-fast"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    p = host.Project(root)
+    cat = p.catchment()
+    ref = oracle_run(cat, p.genpar(40).copy(order="F"))
+    want = [3, 4, 5, 17, 40]
+    files = sorted(glob.glob(p.out_prefix + "mc_id_*.flow"))
+    assert [int(f[-13:-5]) for f in files] == want and len(glob.glob(p.out_prefix + "mc_id_*.res")) == 5
+    from parity import compare_flows, compare_perf
+    ft = formats.read_flow_table(p.out_prefix + "ensemble_flow.bin")
+    assert ft["members"].tolist() == want
+    compare_flows(ft["q"], ref["q"][:, :, [m - 1 for m in want]])
+    flow = np.loadtxt(files[3], ndmin=2).T
+    assert np.abs(flow - ft["q"][:, :, 3]).max() <= 0.5e-8 + 1e-12
+    tab = formats.read_perf_table(p.out_prefix + "ensemble_perf.bin")
+    compare_perf(tab["perf"], ref["perf"])
+    assert np.array_equal(tab["mcpar"], ref["mcpar"]) and tab["perf"].shape[2] == 40
+    from decipher_b200.capi import load_library
+    if load_library().dcp_device_count() >= 2:
+        r2 = subprocess.run([EXE, "-dir", root, "-ids", "1", "1", "1", "-no-flow", "-fast", "-gpus", "2"], capture_output=True, text=True, timeout=300)
+        assert r2.returncode == 0, r2.stdout + r2.stderr
+        tab2 = formats.read_perf_table(p.out_prefix + "ensemble_perf.bin")
+        assert np.array_equal(tab2["perf"], tab["perf"], equal_nan=True) and np.array_equal(tab2["status"], tab["status"])
+    bad = subprocess.run([EXE, "-dir", root, "-ids", "1", "1", "1", "-write-members", "0:3"], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 2
     p.close()
