@@ -582,7 +582,7 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
             P.n_threads = CT + 128;
             P.variant = getenv("DCP_RES_VARIANT") ? atoi(getenv("DCP_RES_VARIANT")) : 0;   // 0 = chosen per arithmetic policy
             P.river_team = 1;
-            while (P.river_team < 16 && 2 * P.river_team * n_chains <= 128) P.river_team <<= 1;
+            while (P.river_team < 16 && 2 * P.river_team * n_chains <= 96) P.river_team <<= 1;      // 96 summing lanes (3 warps)
             size_t off = 0;
             auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
             P.off_qbf = take((size_t)2 * P.G * nac_pad * S * 8);

@@ -10,7 +10,7 @@
 #define DCP_RES2_GB 1                // gather batch of the second-generation kernel: W rows are padded to a multiple of it
 #endif
 #define DCP_RES_COMPUTE 512
-#define DCP_RES_MAXPAIRS 256         // (members per CTA) x nriv the river warps can carry (4 warps x 4 passes x 16 pairs)
+#define DCP_RES_MAXPAIRS 192         // (members per CTA) x nriv the river warps can carry (3 summing warps x 4 passes x 16 pairs)
 #define DCP_RES_TT 64                // forcing tile length (timesteps)
 #define DCP_RT_SLACK_STEPS 129        // = DCP_RT_SLACK of dcp_route_fused.cuh: ring length >= histogram span + two hand-over tiles + 1
 #define DCP_FORCING_PAD 64           // forcing arrays are zero-padded to a multiple of this many steps

@@ -32,10 +32,13 @@
 
 #define RES_COLS DCP_RES_COMPUTE      // unit columns per member slot (= HRU positions across the CTA)
 #define RES_RIVER 128                 // one warpgroup of river warps
-#define RES_ROUTE 32                  // H == 1 kernels: one more warp routes finished tiles and adds up the objective terms
-                                      // (dcp_route_fused.cuh); it is not part of the per-step CTA barrier
+#define RES_ROUTE 32                  // H == 1 kernels: the LAST river warp routes finished tiles and adds up the objective terms
+                                      // (dcp_route_fused.cuh) instead of summing; it is not part of the per-step CTA barrier.
+                                      // (No extra warp: setmaxnreg trades registers inside the CTA's launch allocation only,
+                                      // 640 x 96 = 512 x 112 + 128 x 32, so the thread count and the split must stay.)
+#define RES_SUM(H) ((H) == 1 ? RES_RIVER - RES_ROUTE : RES_RIVER)   // lanes that run the summation chains
 // hand-over river warps -> routing warp: once per DCP_RT_TILE steps and per member group
-__device__ __forceinline__ void res_ab_sync() { asm volatile("bar.sync 2, %0;" ::"n"(RES_RIVER + RES_ROUTE) : "memory"); }
+__device__ __forceinline__ void res_ab_sync() { asm volatile("bar.sync 2, %0;" ::"n"(RES_RIVER) : "memory"); }
 #define RES_MAXPASS 4                 // chains per river lane
 #define RES_PARW 6                    // srmax, td, smax, szm, 1/srmax, 1/szm
 
@@ -62,7 +65,7 @@ __device__ __forceinline__ void res_compute_role(const DevCatchment &C, const De
     constexpr bool FAST = MODE != 0;
     constexpr bool LEAN = MODE == 2;
     constexpr int CT = RES_COLS / H;                        // compute threads; each owns H HRU columns x S member slots
-    constexpr int THREADS = CT + RES_RIVER;
+    constexpr int THREADS = CT + RES_SUM(H);               // threads at the per-step CTA barrier
     const int tid = threadIdx.x;
     const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, npt = C.npt;
     const int qbf_stride = P.G * nac_pad * S;              // doubles per qbf time buffer
@@ -296,7 +299,7 @@ template <int S, int H, bool FAST>
 __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevBatch &W, const ResPlan &P,
                                                const ResSmem &M) {
     constexpr int CT = RES_COLS / H;
-    constexpr int THREADS = CT + RES_RIVER;
+    constexpr int THREADS = CT + RES_SUM(H);               // threads at the per-step CTA barrier
     constexpr bool FUSED = H == 1;                          // qout goes to the member slot's ring, a routing warp follows
     const int tid = threadIdx.x;
     const int nac_pad = P.nac_pad, Mc = P.Mc, B = W.B, nriv = C.nriv;
@@ -307,7 +310,7 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
     const uint32_t pet_bytes = (uint32_t)(P.Tt * C.nge * sizeof(double));
     uint32_t tiles_done = 0;
     const int rlane = tid - CT;
-    constexpr int n_rlanes = RES_RIVER;
+    constexpr int n_rlanes = RES_SUM(H);
     const int n_chains = 2 * Mc * nriv;                     // chain id = (pair << 1) | type, pair = member * nriv + river
     // EXACT: one lane per chain, terms added in ascending HRU order (the reference's order).
     // FAST : a team of T lanes per chain (strided partial sums + shuffle tree) -- order is free there.
@@ -420,26 +423,28 @@ __device__ __forceinline__ void res_river_role(const DevCatchment &C, const DevB
 // x 232 registers, 8 (HRU, member) units per thread of which LG run interleaved in one basic block —
 // fewer, fatter threads trade thread-level for instruction-level parallelism on the FP64 pipe.
 template <int H> struct ResRegs;
-template <> struct ResRegs<1> { static constexpr int compute = 112, river = 32, route = 64; };   // launch cap 96: (96-32)*128 == (112-96)*512
+template <> struct ResRegs<1> { static constexpr int compute = 112, river = 32; };   // launch cap 96: (96-32)*128 == (112-96)*512
 template <> struct ResRegs<2> { static constexpr int compute = 232, river = 40; };   // launch cap 168: (168-40)*128 == (232-168)*256
 
 // routing warp of the H == 1 kernels: one tile behind the river warps (dcp_route_fused.cuh)
+template <bool FAST>
 __device__ __forceinline__ void res_route_role(const DevCatchment &C, const DevBatch &W, const ResPlan &P) {
     for (int gi = blockIdx.x; gi < P.n_groups; gi += gridDim.x) {
         res_ab_sync();                                  // group start (pairs with the river warps')
         for (int t0 = 0; t0 < C.nstep; t0 += DCP_RT_TILE) {
             res_ab_sync();                              // qout of [t0, t0 + tile) is in the rings
-            rt_tile(C, W, gi * P.Mc, P.Mc, blockIdx.x * P.Mc, t0, min(C.nstep, t0 + DCP_RT_TILE));
+            rt_tile<FAST>(C, W, gi * P.Mc, P.Mc, blockIdx.x * P.Mc, t0, min(C.nstep, t0 + DCP_RT_TILE));
         }
     }
 }
 
 template <int S, int H, int LG, int MODE, bool AET>
-__global__ void __launch_bounds__(RES_COLS / H + RES_RIVER + (H == 1 ? RES_ROUTE : 0), 1)
+__global__ void __launch_bounds__(RES_COLS / H + RES_RIVER, 1)
 k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
     constexpr bool FAST = MODE != 0;
     constexpr int CT = RES_COLS / H;
-    constexpr int THREADS = CT + RES_RIVER;
+    constexpr int NTHREADS = CT + RES_RIVER;                // threads of the CTA
+    constexpr int THREADS = CT + RES_SUM(H);               // threads at the per-step CTA barrier
     extern __shared__ __align__(128) unsigned char smem[];
     ResSmem M;
     M.qbf_s = (double *)(smem + P.off_qbf);          // [2][G*nac_pad][S]   qbf tuples, time double buffer
@@ -457,16 +462,16 @@ k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
 
     const int tid = threadIdx.x;
     // ---- one-time CTA setup ----
-    for (int e = tid; e < P.nnz; e += THREADS) {
+    for (int e = tid; e < P.nnz; e += NTHREADS) {
         const WEntry we = C.w[e];
         M.w_s[e] = FAST ? we.w * we.ac_src : we.w;
         M.src_s[e] = (uint16_t)P.hru_pos[we.src];
     }
-    for (int i = tid; i < P.nac_pad; i += THREADS) {
+    for (int i = tid; i < P.nac_pad; i += NTHREADS) {
         const int hh = P.thread_hru[i];
         M.ac_s[i] = hh >= 0 ? C.hru[hh].ac : 0.0;
     }
-    for (int i = tid; i < P.nq; i += THREADS) {
+    for (int i = tid; i < P.nq; i += NTHREADS) {
         const RivChain rc = P.rivq[i];
         M.rq_s[i] = (uint16_t)P.hru_pos[rc.ia];
         if (FAST) {
@@ -476,7 +481,7 @@ k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
         }
     }
     if (tid < 3) M.rqc_s[tid * (P.nq + 1) + P.nq] = 1.0;
-    for (int i = tid; i < C.nac; i += THREADS) M.ro_s[i] = (uint16_t)P.hru_pos[P.rivo[i]];
+    for (int i = tid; i < C.nac; i += NTHREADS) M.ro_s[i] = (uint16_t)P.hru_pos[P.rivo[i]];
     if (tid == CT) {
         mbar_init(&M.bars[0], 1);
         mbar_init(&M.bars[1], 1);
@@ -492,8 +497,8 @@ k_physics_resident(DevCatchment C, DevBatch W, ResPlan P) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ResRegs<H>::river));
         res_river_role<S, H, FAST>(C, W, P, M);
     } else if (H == 1) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ResRegs<1>::route));
-        res_route_role(C, W, P);
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ResRegs<H>::river));
+        res_route_role<FAST>(C, W, P);
     }
 }
 #undef gc
@@ -515,7 +520,7 @@ static cudaError_t launch_res(const DevCatchment &C, const DevBatch &W, const Re
     else k = aet ? k_physics_resident<S, H, 1, 0, true> : k_physics_resident<S, H, 1, 0, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
-    k<<<grid, RES_COLS / H + RES_RIVER + (H == 1 ? RES_ROUTE : 0), P.smem_bytes, s>>>(C, W, P);
+    k<<<grid, RES_COLS / H + RES_RIVER, P.smem_bytes, s>>>(C, W, P);
     return cudaGetLastError();
 }
 
@@ -533,7 +538,7 @@ static cudaError_t launch_lean(const DevCatchment &C, const DevBatch &W, const R
     void (*k)(DevCatchment, DevBatch, ResPlan) = aet ? k_physics_resident<S, H, LG, 2, true> : k_physics_resident<S, H, LG, 2, false>;
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
-    k<<<grid, RES_COLS / H + RES_RIVER + (H == 1 ? RES_ROUTE : 0), P.smem_bytes, s>>>(C, W, P);
+    k<<<grid, RES_COLS / H + RES_RIVER, P.smem_bytes, s>>>(C, W, P);
     return cudaGetLastError();
 }
 

@@ -55,15 +55,17 @@
 #define R2_TA 32                      // lanes of warp A
 #define R2_TT (R2_TC + R2_TA)         // threads at a team's per-step barrier (warp B is not part of it)
 #define R2_CT (R2_TEAMS * R2_TC)      // 256 compute threads
-#define R2_THREADS (R2_TEAMS * R2_TT) // 384
+#define R2_THREADS (R2_TEAMS * (R2_TC + R2_TR)) // 384
 #ifndef R2_REG_COMPUTE
-#define R2_REG_COMPUTE 240            // launch cap 168: (168-24)*128 == (240-168)*256
+#define R2_REG_COMPUTE 232            // setmaxnreg moves registers inside the CTA's LAUNCH allocation (384 x 168) only:
+                                      // 256 x 232 + 64 x 24 + 64 x 56 = 64 512 = 384 x 168.  (240 / 24 / 24 is the other split
+                                      // that fits; a request beyond the pool blocks forever.)
 #endif
 #ifndef R2_REG_RIVER
 #define R2_REG_RIVER 24               // warp A
 #endif
 #ifndef R2_REG_ROUTE
-#define R2_REG_ROUTE 40               // warp B; 8 x 240 + 2 x 24 + 2 x 40 = 2048 registers per lane slot = the whole file
+#define R2_REG_ROUTE 56               // warp B
 #endif
 #ifdef DCP_RES2_DEBUG                  // per-warp busy-cycle counters (tuning builds only: two registers and a branch per step)
 #define R2_DBG (P.dbg != nullptr)
@@ -752,7 +754,7 @@ __device__ __forceinline__ void r2_route(const DevCatchment &C, const DevBatch &
         ab_sync(team);                                       // group start (pairs with warp A's)
         for (int t0 = 0; t0 < C.nstep; t0 += DCP_RT_TILE) {
             ab_sync(team);                                   // qout of [t0, t0 + tile) is in the rings
-            rt_tile(C, W, m_base, Mv, sl_base, t0, min(C.nstep, t0 + DCP_RT_TILE));
+            rt_tile<true>(C, W, m_base, Mv, sl_base, t0, min(C.nstep, t0 + DCP_RT_TILE));
         }
     }
 }
@@ -795,6 +797,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     }
     __syncthreads();
 
+    static_assert(R2_CT * R2_REG_COMPUTE + R2_TEAMS * R2_TA * R2_REG_RIVER + R2_TEAMS * (R2_TR - R2_TA) * R2_REG_ROUTE <= R2_THREADS * 168,
+                  "register split exceeds the CTA's launch allocation: setmaxnreg.inc would never return");
     if (is_compute) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R2_REG_COMPUTE));
         if (P.phase_delay < 0 && team == 1) return;          // tuning experiment: one team only (half the members are skipped)

@@ -15,15 +15,18 @@
 //   while the river-sum warps already fill the next tile.  Only the measures (and the flows when requested) leave the chip.
 //
 // Every operation is spelled with round-to-nearest intrinsics (no FMA contraction whatever the TU's -fmad setting), in
-// the order of k_route_conv / k_route_gauge / k_objective_sum (dcp_kernels.cu), so the fused path returns the same bits
-// as the three routing kernels it replaces and as the oracle's shifted flow matrix.
+// the order of k_route_conv / k_route_gauge / k_objective_sum (dcp_kernels.cu), so under the EXACT policy the fused path
+// returns the same bits as the three routing kernels it replaces and as the oracle's shifted flow matrix.  The FAST
+// policy fuses the multiply-add of each histogram tap (half the FP64 instructions of the convolution).
 #pragma once
 #include "dcp_device.cuh"
 
 #define DCP_RT_TILE 64                       // steps between hand-overs A -> B
 #define DCP_RT_SLACK (2 * DCP_RT_TILE + 1)   // a ring holds hist_len + this many steps (A fills tile j+1 while B reads tile j)
 
-// y_n(t) for the member in ring slot `sl` (k_route_conv on rings)
+// y_n(t) for the member in ring slot `sl` (k_route_conv on rings).  FMA = false: multiply and add rounded separately,
+// the reference's arithmetic (EXACT policy); FMA = true: one fused operation per tap (FAST policy, 1e-9 contract).
+template <bool FMA>
 __device__ __forceinline__ double rt_fir(const DevCatchment &C, const DevBatch &W, int m, int sl, int n, int t) {
     const int riv = C.node_input[n];
     const int bins = W.hbins[n * (size_t)W.B + m];
@@ -33,9 +36,29 @@ __device__ __forceinline__ double rt_fir(const DevCatchment &C, const DevBatch &
     int k = bins - 1;
     if (k > t) k = t;                                 // terms before the first timestep do not exist
     double y = 0.0;
-#pragma unroll 4
-    for (; k >= 0; --k) y = __dadd_rn(y, __dmul_rn(dh[k], qi[(t - k) & W.Rmask]));
+#pragma unroll 8
+    for (; k >= 0; --k) {
+        const double h = dh[k], q = qi[(t - k) & W.Rmask];
+        y = FMA ? fma(h, q, y) : __dadd_rn(y, __dmul_rn(h, q));
+    }
     return y;
+}
+
+// Pulls the taps of node n and the window of its inflow ring that the chunk [t0, t0 + 32) convolves into L1 with one
+// request per lane (lane l touches line l of each), so the FIR loop's first touch of every line is not a serial L2 trip.
+__device__ __forceinline__ void rt_prefetch(const DevCatchment &C, const DevBatch &W, int m, int sl, int n, int t0) {
+    const int lane = threadIdx.x & 31;
+    const int riv = C.node_input[n];
+    const int bins = W.hbins[n * (size_t)W.B + m];
+    if (riv < 0 || bins <= 0) return;
+    const double *dh = W.dh + ((size_t)m * C.nnode + n) * W.Lcap;
+    const double *qi = W.qout + ((size_t)sl * C.nriv + riv) * W.R;
+    for (int e = lane * 16; e < bins; e += 512) asm volatile("prefetch.global.L1 [%0];" ::"l"(dh + e));
+    const int first = t0 - (bins - 1);                // oldest step of the window (may be negative: clipped)
+    for (int e = lane * 16; e < bins + 31 + 16; e += 512) {
+        const int tt = first + e;
+        if (tt >= 0 && tt < t0 + 32) asm volatile("prefetch.global.L1 [%0];" ::"l"(qi + (tt & W.Rmask)));
+    }
 }
 
 // flow_matrix(u, col) at step t (node_at_column of dcp_kernels.cu on rings)
@@ -64,13 +87,15 @@ __device__ __forceinline__ double rt_node_at_column(const DevCatchment &C, const
 __device__ __forceinline__ double rt_shfl(double v, int src) { return __shfl_sync(0xffffffffu, v, src); }
 
 // One chunk of up to 32 steps [t0, t0 + nv) of member m (ring slot sl); all 32 lanes of the routing warp call it.
+template <bool FMA>
 __device__ __forceinline__ void rt_chunk(const DevCatchment &C, const DevBatch &W, int m, int sl, int t0, int nv) {
     const int lane = threadIdx.x & 31;
     const int t = t0 + lane;
     const bool in = lane < nv;
     const int B = W.B;
+    for (int n = 0; n < C.nnode; ++n) rt_prefetch(C, W, m, sl, n, t0);
     for (int n = 0; n < C.nnode; ++n) {
-        if (in) W.y[((size_t)sl * C.nnode + n) * W.R + (t & W.Rmask)] = rt_fir(C, W, m, sl, n, t);
+        if (in) W.y[((size_t)sl * C.nnode + n) * W.R + (t & W.Rmask)] = rt_fir<FMA>(C, W, m, sl, n, t);
     }
     __syncwarp();                                     // y of this chunk visible to the lanes that read it with a delay
     const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
@@ -118,9 +143,10 @@ __device__ __forceinline__ void rt_chunk(const DevCatchment &C, const DevBatch &
 }
 
 // steps [t0, t1) (one hand-over tile) of the members m_base .. m_base + n_mem - 1 held in ring slots sl_base ..
+template <bool FMA>
 __device__ __forceinline__ void rt_tile(const DevCatchment &C, const DevBatch &W, int m_base, int n_mem, int sl_base, int t0, int t1) {
     for (int jm = 0; jm < n_mem; ++jm) {
         if (m_base + jm >= W.B) break;
-        for (int c0 = t0; c0 < t1; c0 += 32) rt_chunk(C, W, m_base + jm, sl_base + jm, c0, min(32, t1 - c0));
+        for (int c0 = t0; c0 < t1; c0 += 32) rt_chunk<FMA>(C, W, m_base + jm, sl_base + jm, c0, min(32, t1 - c0));
     }
 }

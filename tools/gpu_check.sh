@@ -3,9 +3,12 @@
 #   tools/gpu_check.sh <tag> [pytest -k expression]
 tag=${1:-x}; sel=${2:-"resident or full_length or small_and_ragged or sharding or fast"}
 out=gpurun_out
-timeout 900 python -m pytest tests -m gpu -x -q -k "$sel" 2>&1 | tail -15 > $out/${tag}_tests.log
+timeout -k 10 240 python tools/gpu_sanity.py > $out/${tag}_sanity.log 2>&1; rc=$?
+tail -8 $out/${tag}_sanity.log
+if [ $rc -ne 0 ]; then echo "SANITY FAILED rc=$rc"; exit 1; fi
+timeout -k 10 900 python -m pytest tests -m gpu -x -q -k "$sel" 2>&1 | tail -15 > $out/${tag}_tests.log
 tail -5 $out/${tag}_tests.log
-timeout 600 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err || { tail -5 $out/${tag}_bench.err; exit 1; }
+timeout -k 10 400 python bench.py --steps 5 --warmup 3 > $out/${tag}_bench.json 2> $out/${tag}_bench.err || { tail -5 $out/${tag}_bench.err; exit 1; }
 python - <<PY
 import json
 d = json.load(open("$out/${tag}_bench.json"))
