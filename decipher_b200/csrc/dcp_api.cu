@@ -99,7 +99,8 @@ namespace {
 // Plan of the second-generation resident kernel: ELL schedule of the weight matrix, column tables, river slots.
 void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vector<HruStatic> &hru,
                  const std::vector<WEntry> &w, const std::vector<int32_t> &thread_hru, const std::vector<int32_t> &hru_pos,
-                 int nac_pad, const std::vector<double> &pet, cudaError_t &e) {
+                 int nac_pad, const std::vector<double> &pet, const std::vector<double> &frac, const std::vector<double> &qobs,
+                 const std::vector<ObsStat> &obs, cudaError_t &e) {
     const int nac = d->nac, nriv = d->nriv, npt = d->npt, S = 2, COLS = DCP_RES_COMPUTE, TC = 128, H = 4;
     const DevCatchment &C = c->C;
     Res2Plan &Q = c->plan2;
@@ -301,10 +302,27 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     if (Q.ell_len >= (1 << 20)) return;
 
     Q.n_teams = G * nriv;
-    Q.team = 32;                                            // the 32 lanes of a team's river-sum warp
-    while (Q.team > 1 && Q.team * Q.n_teams > 32) Q.team >>= 1;
-    Q.n_pass = (Q.n_teams * Q.team + 31) / 32;
+    Q.team = 32;
+    while (Q.team > 1 && Q.team * Q.n_teams > 64) Q.team >>= 1;
+    Q.n_pass = (Q.n_teams * Q.team + 63) / 64;
     if (Q.n_pass > 16) return;
+    // routing jobs of one member: gauge i x node u in {i} + upstream tree of i (order of route_process_run_step's sum,
+    // DTA/dta_route_processing.f90:685-714)
+    std::vector<int32_t> job_node, job_gauge, gauge_job_beg(nriv + 1, 0);
+    {
+        std::vector<int32_t> up_beg(d->nnode + 1, 0);
+        for (int n = 0; n < d->nnode; ++n) up_beg[n + 1] = up_beg[n] + d->uptree_count[n];
+        for (int i = 0; i < nriv; ++i) {                     // river / output index i == node i (flow_output_indexes)
+            job_node.push_back(i); job_gauge.push_back(i);
+            for (int e2 = up_beg[i]; e2 < up_beg[i + 1]; ++e2) { job_node.push_back(d->uptree_index[e2] - 1); job_gauge.push_back(i); }
+            gauge_job_beg[i + 1] = (int)job_node.size();
+        }
+    }
+    Q.jobs_per_member = (int)job_node.size();
+    const int n_jobs = G * S * Q.jobs_per_member;
+    if (n_jobs > 4096) return;
+    Q.fir_team = 32;
+    while (Q.fir_team > 1 && Q.fir_team * n_jobs > 64) Q.fir_team >>= 1;
     // shared memory: [shared tables][team 0][team 1]
     size_t off = 0;
     auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
@@ -319,8 +337,10 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     Q.off_cst = take((size_t)S * COLS * 16);
     Q.off_par = take((size_t)G * S * npt * 3 * 16);
     Q.off_forc = take((size_t)2 * Q.Tt * (d->ngp + d->nge) * 8);
-    Q.off_bar = take(32);
-    Q.off_sz = take((size_t)S * COLS * 16);                  // parked {srz, suz} of the split-barrier step
+    Q.off_bar = take(16);
+    Q.off_job = take((size_t)n_jobs * 16);
+    Q.off_jres = take((size_t)n_jobs * 8);
+    Q.off_acc = take((size_t)G * S * nriv * 6 * 8);
     Q.team_bytes = (int)((off + 8191) & ~(size_t)8191);     // team blocks (tuple buffers first) sit on 8 KB boundaries
     Q.smem_bytes = Q.off_team + 8192 + 2 * Q.team_bytes;    // + the kernel's alignment slack
     if ((size_t)Q.smem_bytes > c->smem_optin) return;
@@ -329,6 +349,15 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     auto up = [&](auto &vec, auto **dst) { if (e == cudaSuccess) e = upload(vec, dst, c->owned); };
     up(ent, &Q.ell_w); up(col_i, &Q.col_i); up(col_d, &Q.col_d); up(col_ia, &Q.col_ia);
     up(rbeg, &Q.rbeg); up(pet_pos, &Q.pet_pos);
+    up(job_node, &Q.job_node); up(job_gauge, &Q.job_gauge); up(gauge_job_beg, &Q.gauge_job_beg);
+    std::vector<double> inv_frac(nriv), log_obs(qobs.size(), 0.0);
+    for (int r = 0; r < nriv; ++r) inv_frac[r] = 1.0 / frac[r];
+    for (size_t x = 0; x < qobs.size(); ++x) {
+        const int g = (int)(x % nriv);
+        if (qobs[x] != d->flow_err) log_obs[x] = std::log(qobs[x] > obs[g].eps ? qobs[x] : obs[g].eps);
+    }
+    up(inv_frac, &Q.inv_frac);
+    if (!qobs.empty()) up(log_obs, &Q.log_obs); else Q.log_obs = nullptr;
     Q.feasible = 1;
 }
 
@@ -620,7 +649,7 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
                 // ---- second-generation plan (dcp_resident_v2.cu) ----
                 c->plan2 = Res2Plan{};
                 if (P.lean_ok && !getenv("DCP_RES_NO_V2"))
-                    build_plan2(c, d, hru, w, thread_hru, hru_pos, nac_pad, pet, e);
+                    build_plan2(c, d, hru, w, thread_hru, hru_pos, nac_pad, pet, frac, qobs, obs, e);
             }
         }
     }

@@ -2,6 +2,7 @@
 // (cp.async.bulk; SASS UBLKCP / SYNCS) and the named CTA barrier used inside role-specialised code.
 #pragma once
 #include <cstdint>
+#include <cstdio>
 
 // ---------------------------------------------------------------------------------------------
 // mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: UBLKCP, SYNCS)
@@ -15,6 +16,18 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+#ifdef DCP_WATCHDOG                  // debugging builds: a wait that never completes reports itself and kills the kernel
+    for (long long spins = 0;; ++spins) {
+        uint32_t ok;
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) return;
+        if (spins > (1ll << 22)) {
+            printf("[dcp watchdog] mbarrier wait stuck: block %d thread %d bar smem 0x%x parity %u\n", blockIdx.x, threadIdx.x, smem_u32(bar), parity);
+            __trap();
+        }
+    }
+#endif
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "WAIT_%=:\n\t"

@@ -43,29 +43,24 @@
 #include "dcp_physics.cuh"
 #include "dcp_kernels.h"
 #include "dcp_resident_common.cuh"
-#include "dcp_route_fused.cuh"
 
 #include <cstdint>
 
 #define R2_COLS DCP_RES_COMPUTE       // 512 unit columns per member slot
 #define R2_TEAMS 2
 #define R2_TC 128                     // compute threads per team (4 columns each)
-#define R2_TR 64                      // river threads per team: warp A sums the river contributions of every step (and drives
-                                      // the forcing TMA), warp B routes finished tiles and accumulates the objective sums
-#define R2_TA 32                      // lanes of warp A
-#define R2_TT (R2_TC + R2_TA)         // threads at a team's per-step barrier (warp B is not part of it)
+#define R2_TR 64                      // river threads per team: contribution sums, routing convolution and objective terms of every
+                                      // step, one step behind the compute warps; lane 0 also drives the forcing TMA
+#define R2_TT (R2_TC + R2_TR)         // threads at a team's per-step barrier
 #define R2_CT (R2_TEAMS * R2_TC)      // 256 compute threads
 #define R2_THREADS (R2_TEAMS * (R2_TC + R2_TR)) // 384
 #ifndef R2_REG_COMPUTE
-#define R2_REG_COMPUTE 232            // setmaxnreg moves registers inside the CTA's LAUNCH allocation (384 x 168) only:
-                                      // 256 x 232 + 64 x 24 + 64 x 56 = 64 512 = 384 x 168.  (240 / 24 / 24 is the other split
-                                      // that fits; a request beyond the pool blocks forever.)
+#define R2_REG_COMPUTE 240            // setmaxnreg (a) moves registers inside the CTA's LAUNCH allocation (384 x 168) only -- a request
+                                      // beyond that pool blocks forever -- and (b) must be the SAME instruction for the four warps of a
+                                      // warpgroup (warps 8-11 are the river warps): 256 x 240 + 128 x 24 = 64 512 = 384 x 168
 #endif
 #ifndef R2_REG_RIVER
-#define R2_REG_RIVER 24               // warp A
-#endif
-#ifndef R2_REG_ROUTE
-#define R2_REG_ROUTE 56               // warp B
+#define R2_REG_RIVER 24
 #endif
 #ifdef DCP_RES2_DEBUG                  // per-warp busy-cycle counters (tuning builds only: two registers and a branch per step)
 #define R2_DBG (P.dbg != nullptr)
@@ -100,9 +95,10 @@ struct R2Smem {                       // team-private views unless noted
                           //                 two DMULs instead of an LDS.128 per unit and step, and 32 KB less shared memory
     double2 *par_s;       // [Mv][npt][3]    {srmax, 1/srmax}, {td/dt, smax}, {szm, dtt/szm}
     double *forc_s;       // [2][Tt*(ngp+nge)]
-    uint64_t *bars;       // [2] forcing tiles (TMA) + [1] the split per-step barrier (R2_SPLIT)
-    double2 *sz_s;        // [2][4][128]     {srz, suz} per (member slot, column slot j, team thread), own-column: the two upper stores
-                          //                 are parked here while the thread gathers and solves the saturated zone (R2_SPLIT)
+    uint64_t *bars;       // [2] forcing tiles (TMA)
+    int4 *job_s;          // [Mv * jobs_per_member]  routing jobs of the group: {ring offset, delay, taps, histogram offset}
+    double *jres_s;       // [Mv * jobs_per_member]  this step's result of every job
+    double *acc_s;        // [Mv * nriv][6]          objective sums sse, lsse, sq, sqq, sqo and the non-finite flag
     // shared by both teams (read-only after setup)
     double *ellw_s;       // [ell_len]       packed gather list (weight | source tuple index)
     int4 *coli_s;         // [4][128]        per (column slot j, team thread): packed indices
@@ -122,18 +118,8 @@ __device__ __forceinline__ double2 lds_tuple(int lo, uint32_t buf_u32) {
 }
 
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(R2_TT) : "memory"); }
-// hand-over between a team's river-sum warp (A) and its routing warp (B): once per DCP_RT_TILE steps and per member group
-__device__ __forceinline__ void ab_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 3), "n"(R2_TR) : "memory"); }
-
-// Split per-step barrier (R2_SPLIT): mbarrier with one arrival per compute thread and per lane of warp A.  A thread ARRIVES as
-// soon as it has published its step and waits for the phase only when it needs the other warps' results, so the work
-// that depends on nothing but the thread's own stores (root zone + unsaturated zone of the NEXT step) fills the wait.
-__device__ __forceinline__ void step_arrive(uint64_t *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-#ifndef R2_SPLIT
-#define R2_SPLIT 1
-#endif
+// the two river warps of a team among themselves (sums -> convolution jobs -> gauges inside one step)
+__device__ __forceinline__ void river_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 3), "n"(R2_TR) : "memory"); }
 
 #define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})
 
@@ -419,243 +405,18 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 }
 
 // ---------------------------------------------------------------------------------------------
-// compute role with the SPLIT per-step barrier (R2_SPLIT): per step
-//     wait(step t-1 published by everyone) -> gather -> saturated zone -> publish -> ARRIVE(t) -> root + unsat zone of t+1
-// The unit's srz / suz are only touched by the upper zones, so they live in an own-column shared slot while the thread
-// gathers and solves (registers: sd, exp(sd/m2), uz, exus per unit -- the same 4 doubles per unit as the fused step).
-// ---------------------------------------------------------------------------------------------
-template <bool AET, bool ONEPAR>
-__device__ __forceinline__ void r2_compute_split(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
-                                                 const int team, const int tt_id) {
-    constexpr int H = R2_H, S = R2_S;
-    const int B = W.B, npt = C.npt;
-    const int forc_stride = P.Tt * (C.ngp + C.nge);
-    const int par_kstride = npt * 3;
-    const int Mv = P.G * S;
-    uint32_t tiles_done = 0, steps_done = 0;
-    uint64_t *sbar = &M.bars[2];
-
-    for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
-        const int m_base = vg * Mv;
-        team_sync(team);                                     // previous group fully done with shared memory
-
-        double sd[H][S], e1s[H][S], uzv[H][S], exv[H][S], aet[H][S];
-#pragma unroll
-        for (int j = 0; j < H; ++j) {
-            const int4 ci = M.coli_s[j * R2_TC + tt_id];
-            const int tup = ci.z & 0xffff, g = (ci.y >> 16) & 0x7fff;
-            const int ia = P.col_ia[j * R2_TC + tt_id];
-            const double cosm = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id].y;
-            const int ipar = ia >= 0 ? C.hru[ia].ipar : 0;
-#pragma unroll
-            for (int k = 0; k < S; ++k) {
-                const int m = m_base + g * S + k;
-                sd[j][k] = 1.0; aet[j][k] = 0.0;
-                double suz0 = 0.0, srz0 = 0.0, qb0 = 0.0, c_q0 = 1.0, c_q2 = 1.0, c_im2 = 1.0;
-                if (ia >= 0 && m < B) {
-                    const size_t o = (size_t)ia * B + m;
-                    sd[j][k] = W.sd[o]; suz0 = W.suz[o]; srz0 = W.srz[o];
-                    c_q0 = W.q0[o]; c_q2 = W.q2[o];
-                    const double szm = W.par[(0 * npt + ipar) * (size_t)B + m];
-                    c_im2 = cosm * (1.0 / szm);
-                    qb0 = W.qbf0[o];
-                }
-                e1s[j][k] = exp(sd[j][k] * c_im2);
-                reinterpret_cast<double *>(M.qbf_s + tup)[k] = qb0;
-                reinterpret_cast<double *>(M.qbf_s + R2_COLS + tup)[k] = 0.0;
-                M.cst_s[(k * H + j) * R2_TC + tt_id] = make_double2(c_q0, c_q2);
-                M.sz_s[(k * H + j) * R2_TC + tt_id] = make_double2(srz0, suz0);
-            }
-        }
-        for (int i = tt_id; i < Mv * npt; i += R2_TC) {      // member parameters -> shared
-            const int jm = i / npt, l = i % npt;
-            const int m = m_base + jm;
-            double srmax = 1.0, td = 1.0, smax = 1.0, szm = 1.0;
-            if (m < B) {
-                szm = W.par[(0 * npt + l) * (size_t)B + m];
-                srmax = W.par[(2 * npt + l) * (size_t)B + m];
-                td = W.par[(5 * npt + l) * (size_t)B + m];
-                smax = W.par[(6 * npt + l) * (size_t)B + m];
-            }
-            M.par_s[i * 3 + 0] = make_double2(srmax, 1.0 / srmax);
-            M.par_s[i * 3 + 1] = make_double2(td / C.dt, smax);
-            M.par_s[i * 3 + 2] = make_double2(szm, C.dtt / szm);
-        }
-        team_sync(team);
-
-        // root zone + unsaturated zone of step `tn` for all of the thread's units (own state + forcing only)
-        auto upper = [&](const double *forc_t, int tt) {
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-                const int4 ci = M.coli_s[j * R2_TC + tt_id];
-                const double p = forc_t[tt * C.ngp + (ci.y & 0xff)];
-                const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci.y >> 8) & 0xff)];     // already max(ep, 0)
-#pragma unroll
-                for (int k = 0; k < S; ++k) {
-                    const double2 p0 = M.par_s[(ONEPAR ? 0 : (ci.w & 0xffff)) + k * par_kstride];
-                    const double2 p1 = M.par_s[(ONEPAR ? 0 : (ci.w & 0xffff)) + k * par_kstride + 1];
-                    double2 *slot = M.sz_s + (k * H + j) * R2_TC + tt_id;
-                    double2 z = *slot;
-                    double ea;
-                    hru_lean_upper(LeanUpperConst{p0.x, p0.y, p1.x}, C.inv_dtt, p, epp, sd[j][k], z.x, z.y, uzv[j][k], exv[j][k], ea);
-                    *slot = z;
-                    if (AET) aet[j][k] = aet[j][k] + ea;
-                }
-            }
-        };
-
-        const double *ent0 = M.ellw_s + (M.coli_s[tt_id].x & 0xfffff);
-        double wv0 = ent0[0];
-
-        int t = 0;
-        const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
-        mbar_wait(&M.bars[tiles_done & 1], (tiles_done >> 1) & 1);                   // forcing tile 0
-        upper(M.forc_s + (tiles_done & 1) * forc_stride, 0);
-        for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
-            const int t_end = min(C.nstep, t + P.Tt);
-            for (int tt = 0; t < t_end; ++t, ++tt, ++steps_done) {
-                const double2 *qbf_cur = M.qbf_s + (t & 1) * R2_COLS;
-                const uint32_t qcur_u32 = smem_u32(qbf_cur);
-                double2 *qbf_nxt = M.qbf_s + ((t & 1) ^ 1) * R2_COLS;
-                double2 *con = M.con_s + (t & 1) * R2_COLS;
-                // everyone has published step t-1 (and warp A is done with the contribution buffer this step overwrites)
-                if (t > 0) mbar_wait(sbar, (steps_done - 1) & 1);
-                const double *ep = ent0;
-#pragma unroll
-                for (int jp = 0; jp < H; jp += 2) {
-                    int4 ci[H];
-                    double qin[H][S];
-#pragma unroll
-                    for (int j = jp; j < jp + 2; ++j) {
-                        ci[j] = M.coli_s[j * R2_TC + tt_id];
-                        const int nb = ci[j].x >> 20;
-                        double qa[R2_NACC][2];
-#pragma unroll
-                        for (int u = 0; u < R2_NACC; ++u) { qa[u][0] = 0.0; qa[u][1] = 0.0; }
-                        int bb = 0;
-#if R2_LONG > 1
-                        if (j == 0) {
-#pragma unroll 1
-                            for (; bb + R2_LONG * R2_NACC <= nb; bb += R2_LONG * R2_NACC) {
-#pragma unroll
-                                for (int u = 0; u < R2_LONG * R2_NACC; ++u) {
-                                    const double wc = wv0;
-                                    const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
-                                    ep += 32;
-                                    wv0 = ep[0];
-                                    qa[u % R2_NACC][0] = fma(qv.x, wc, qa[u % R2_NACC][0]);
-                                    qa[u % R2_NACC][1] = fma(qv.y, wc, qa[u % R2_NACC][1]);
-                                }
-                            }
-                        }
-#endif
-#pragma unroll 1
-                        for (; bb + R2_NACC <= nb; bb += R2_NACC) {
-#pragma unroll
-                            for (int u = 0; u < R2_NACC; ++u) {
-                                const double wc = wv0;
-                                const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
-                                ep += 32;
-                                wv0 = ep[0];
-                                qa[u][0] = fma(qv.x, wc, qa[u][0]); qa[u][1] = fma(qv.y, wc, qa[u][1]);
-                            }
-                        }
-#pragma unroll 1
-                        for (; bb < nb; ++bb) {
-                            const double wc = wv0;
-                            const double2 qv = lds_tuple(__double2loint(wc), qcur_u32);
-                            ep += 32;
-                            wv0 = ep[0];
-                            qa[0][0] = fma(qv.x, wc, qa[0][0]); qa[0][1] = fma(qv.y, wc, qa[0][1]);
-                        }
-                        double q0 = qa[0][0], q1 = qa[0][1];
-#pragma unroll
-                        for (int u = 1; u < R2_NACC; ++u) { q0 += qa[u][0]; q1 += qa[u][1]; }
-                        qin[j][0] = q0; qin[j][1] = q1;
-                    }
-                    // ---- saturated zone: 4 interleaved dependency chains ----
-                    double qbn[2][S], exac[2][S], sd0[2][S], cq[2];
-                    bool slow[2][S], any_slow = false;
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const int j = jp + jj;
-                        const double2 d0 = M.cold_s[j * R2_TC + tt_id];                          // {ac, 1/ac}
-                        const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];           // {cq, cos}
-                        const double icos = M.cold_s[2 * R2_H * R2_TC + j * R2_TC + tt_id].x;
-                        cq[jj] = d1.x;
-#pragma unroll
-                        for (int k = 0; k < S; ++k) {
-                            const double2 c0v = M.cst_s[(k * H + j) * R2_TC + tt_id];
-                            const double2 p1 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 1];
-                            const double2 p2 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 2];
-                            LeanSatConst c;
-                            c.ac = d0.x; c.inv_ac = d0.y; c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.dtt_inv_m2 = d1.y * p2.y;
-                            c.q1 = c.q0 * d1.y; c.smax = p1.y;
-                            sd0[jj][k] = sd[j][k];
-                            slow[jj][k] = hru_lean_sat(c, C.dtt, C.inv_dtt, qin[j][k], uzv[j][k], exv[j][k], sd[j][k], e1s[j][k], qbn[jj][k], exac[jj][k]);
-                            any_slow |= slow[jj][k];
-                        }
-                    }
-                    if (__builtin_expect(any_slow, 0)) {                                         // rare: sd > smax, out-of-range exponent
-#pragma unroll
-                        for (int jj = 0; jj < 2; ++jj)
-#pragma unroll
-                            for (int k = 0; k < S; ++k)
-                                if (slow[jj][k]) {
-                                    const int j = jp + jj;
-                                    const R2Fix f = r2_fix_unit(smem_u32(M.cst_s + (k * H + j) * R2_TC + tt_id),
-                                                                smem_u32(M.par_s + (ci[j].w & 0xffff) + k * par_kstride),
-                                                                smem_u32(M.cold_s + j * R2_TC + tt_id), C.dtt, C.inv_dtt, C.ntt,
-                                                                qin[j][k], uzv[j][k], exv[j][k], sd0[jj][k]);
-                                    sd[j][k] = f.sd; qbn[jj][k] = f.qbf; exac[jj][k] = f.exac; e1s[j][k] = f.e1;
-                                }
-                    }
-                    double2 qold[2];
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) qold[jj] = qbf_cur[ci[jp + jj].z & 0xffff];
-#pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
-                        const int j = jp + jj;
-                        const int tup = ci[j].z & 0xffff, ctup = (int)((uint32_t)ci[j].w >> 16);
-                        if (ci[j].y >= 0) qbf_nxt[tup] = make_double2(qbn[jj][0], qbn[jj][1]);
-                        con[ctup] = make_double2(fma(cq[jj], qold[jj].x, exac[jj][0]), fma(cq[jj], qold[jj].y, exac[jj][1]));
-                    }
-                }
-                step_arrive(sbar);                                                               // step t published
-                wv0 = ent0[0];                                                                   // next step's first gather entry
-                // ---- root zone + unsaturated zone of step t+1 while the other warps finish step t ----
-                if (t + 1 < C.nstep) {
-                    uint32_t td = tiles_done;
-                    int ttn = tt + 1;
-                    if (ttn == P.Tt) {                                                           // first step of the next forcing tile
-                        ++td; ttn = 0;
-                        mbar_wait(&M.bars[td & 1], (td >> 1) & 1);
-                    }
-                    upper(M.forc_s + (td & 1) * forc_stride, ttn);
-                }
-            }
-        }
-        // the last step's phase: nobody waits for it inside the loop, so consume it here (keeps the parity count in step)
-        mbar_wait(sbar, (steps_done - 1) & 1);
-        if (AET) {
-#pragma unroll
-            for (int j = 0; j < H; ++j) {
-                const int ia = P.col_ia[j * R2_TC + tt_id];
-                const int g = (M.coli_s[j * R2_TC + tt_id].y >> 16) & 0x7fff;
-#pragma unroll
-                for (int k = 0; k < S; ++k) {
-                    const int m = m_base + g * S + k;
-                    if (ia >= 0 && m < B) W.aet[(size_t)ia * B + m] = aet[j][k];
-                }
-            }
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// river role, warp A of a team.  A group of T lanes adds up one (member sub-group, river) range of
-// contribution tuples, one step behind the compute warps, and stores qout(t) into the q RING of the member's
-// slot (dcp_route_fused.cuh); lane 0 also drives the team's forcing TMA.
+// river role: 2 warps per team, one step behind the compute warps.  Per finished step tp:
+//   (1) SUMS      a group of T lanes adds up one (member sub-group, river) range of contribution tuples: qout_r(tp)
+//                 (dyna_river.f90:43), stored into the member slot's inflow RING (the last `hist_len` values per river are
+//                 all the routing ever needs -- no series of length nstep exists unless the caller asks for the flows);
+//   (2) ROUTING   the time-delay-histogram convolution of route_process_run_step (DTA/dta_route_processing.f90:671-727)
+//                 as warp-shuffle FIRs: one JOB per (member, gauge i, node u in {i} + upstream tree of i),
+//                     job(tp) = sum_k delay_hist_u(k + o) * qout_u(tp - d - k),   d = delay of u's histogram start past i's column,
+//                 L lanes split the taps of a job and meet in a shuffle tree (the FAST policy has no summation-order
+//                 contract; the EXACT policy lives in the first-generation kernel, dcp_route_fused.cuh);
+//   (3) GAUGES    one lane per (member, gauge): q_i(tp) = (sum of its jobs) / frac_sub_area (dyna_river.f90:57-59), the flow
+//                 output when requested, and the objective terms added to sums kept in shared memory.
+// Lane 0 also drives the team's forcing TMA.  Only the measures (and the flows when requested) leave the chip.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
                                          const int team, const int rl) {
@@ -668,14 +429,16 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
     const int Mv = P.G * S;
     uint32_t tiles_done = 0;
     const int T = P.team, sub = rl & (T - 1);
-    const int sums_per_pass = R2_TA / T;
+    const int sums_per_pass = R2_TR / T;
     const int sl_base = (blockIdx.x * R2_TEAMS + team) * Mv; // ring slots of this team (one per member in flight)
-    uint32_t steps_done = 0;
+    const int njm = P.jobs_per_member, n_jobs = Mv * njm;
+    const int L = P.fir_team, fsub = rl & (L - 1);
+    const int jobs_per_pass = R2_TR / L;
+    const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
     long long busy = 0;
 
     for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
         const int m_base = vg * Mv;
-        ab_sync(team);                                       // warp B is done with the rings of the previous group
         team_sync(team);
         if (rl == 0) {                                       // forcing tile 0 of this group
             const uint32_t b = tiles_done & 1;
@@ -684,11 +447,33 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
             tma_load_1d(M.forc_s + b * forc_stride, C.rain, rain_bytes, &M.bars[b]);
             tma_load_1d(M.forc_s + b * forc_stride + P.Tt * C.ngp, P.pet_pos, pet_bytes, &M.bars[b]);
         }
+        // routing jobs of this group's members: the histogram geometry depends on the member's channel velocity
+        for (int j = rl; j < n_jobs; j += R2_TR) {
+            const int jm = j / njm, jj = j - jm * njm;
+            const int m = m_base + jm;
+            int4 e = make_int4(0, 0, 0, 0);
+            if (m < B) {
+                const int u = P.job_node[jj], i = P.job_gauge[jj];
+                const int riv = C.node_input[u];
+                const int bins = W.hbins[u * (size_t)B + m];
+                const int d = W.hstart[u * (size_t)B + m] - W.hstart[i * (size_t)B + m];    // hist start of u past the gauge's sum_index
+                const int o = d < 0 ? -d : 0;                // column inside u's histogram: partial sum from tap o on
+                if (riv >= 0 && bins - o > 0) {
+                    e.x = ((sl_base + jm) * nriv + riv) * W.R;
+                    e.y = d < 0 ? 0 : d;
+                    e.z = bins - o;
+                    e.w = (int)(((size_t)m * C.nnode + u) * W.Lcap) + o;
+                }
+            }
+            M.job_s[j] = e;
+        }
+        for (int a = rl; a < Mv * nriv * 6; a += R2_TR) M.acc_s[a] = 0.0;
         team_sync(team);
 
-        // sums the contributions of step tp and streams qout(tp) to global memory (dyna_river.f90:43)
+        // river sums, routing and objective terms of step tp
         auto flush_step = [&](int tp) {
             const double2 *con = M.con_s + (tp & 1) * R2_COLS;
+#pragma unroll 1
             for (int pass = 0; pass < P.n_pass; ++pass) {
                 const int sum_id = pass * sums_per_pass + rl / T;
                 const bool live = sum_id < P.n_teams;
@@ -696,66 +481,91 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
                 const int beg = M.rbeg_s[r], end = live ? M.rbeg_s[r + 1] : beg;
                 const double2 *cg = con + g * nac_pad;
                 double a0 = 0.0, a1 = 0.0;
-#pragma unroll 4
+#pragma unroll 2
                 for (int p = beg + sub; p < end; p += T) { const double2 x = cg[p]; a0 += x.x; a1 += x.y; }
                 for (int o = T >> 1; o > 0; o >>= 1) {
                     a0 += __shfl_xor_sync(0xffffffffu, a0, o);
                     a1 += __shfl_xor_sync(0xffffffffu, a1, o);
                 }
                 if (live && sub == 0) {
-                    const int m0 = m_base + g * S;
                     const size_t tq = (size_t)(tp & W.Rmask);
-                    if (m0 + 0 < B) W.qout[((size_t)(sl_base + g * S + 0) * nriv + r) * W.R + tq] = a0;
-                    if (m0 + 1 < B) W.qout[((size_t)(sl_base + g * S + 1) * nriv + r) * W.R + tq] = a1;
+                    W.qout[((size_t)(sl_base + g * S + 0) * nriv + r) * W.R + tq] = a0;
+                    W.qout[((size_t)(sl_base + g * S + 1) * nriv + r) * W.R + tq] = a1;
                 }
             }
-            if ((tp & (DCP_RT_TILE - 1)) == DCP_RT_TILE - 1 || tp == C.nstep - 1) ab_sync(team);   // tile complete: hand over to warp B
+            river_sync(team);                                // every qout(tp) of the group is in the rings
+#pragma unroll 1
+            for (int j0 = 0; j0 < n_jobs; j0 += jobs_per_pass) {
+                const int j = j0 + rl / L;
+                const int4 e = M.job_s[j < n_jobs ? j : 0];
+                int nt = j < n_jobs ? min(e.z, tp - e.y + 1) : 0;                    // terms before the first timestep do not exist
+                const double *__restrict__ dh = W.dh + e.w;
+                const double *qi = W.qout + e.x;
+                const int tb = tp - e.y;
+                double y = 0.0;
+#pragma unroll 2
+                for (int k = fsub; k < nt; k += L) y = fma(dh[k], qi[(tb - k) & W.Rmask], y);
+                for (int o = L >> 1; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
+                if (fsub == 0 && j < n_jobs) M.jres_s[j] = y;
+            }
+            river_sync(team);
+#pragma unroll 1
+            for (int pg = rl; pg < Mv * nriv; pg += R2_TR) {
+                const int jm = pg / nriv, i = pg - jm * nriv;
+                const int m = m_base + jm;
+                if (m >= B) continue;
+                double q_sum = 0.0;
+                for (int jj = P.gauge_job_beg[i]; jj < P.gauge_job_beg[i + 1]; ++jj) q_sum += M.jres_s[jm * njm + jj];
+                const double q = q_sum * P.inv_frac[i];      // FAST policy: hoisted reciprocal of frac_sub_area (dyna_river.f90:57-59)
+                if (W.q_user) W.q_user[((size_t)m * C.nstep + tp) * nriv + i] = q;
+                double *acc = M.acc_s + pg * 6;
+                if (!isfinite(q)) acc[5] = 1.0;
+                if (C.qobs != nullptr && tp >= C.t_warm && tp < n_t) {
+                    const double o = C.qobs[(size_t)tp * nriv + i];
+                    if (o != C.flow_err && isfinite(q)) {
+                        const double eps = C.obs[i].eps;
+                        const double d = q - o;
+                        const double dl = LEAN_LOG(q > eps ? q : eps) - P.log_obs[(size_t)tp * nriv + i];   // ln(max(obs, eps)) is member independent
+                        acc[0] += d * d; acc[1] += dl * dl;
+                        acc[2] += q; acc[3] = fma(q, q, acc[3]); acc[4] = fma(q, o, acc[4]);
+                    }
+                }
+            }
         };
 
-        int t = 0;
-        for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
-            if (rl == 0 && tile + 1 < ntiles) {
-                // prefetch the next tile into the other buffer (the team left it at the last barrier)
-                const uint32_t nb = (tiles_done & 1) ^ 1;
-                const size_t t_next = (size_t)(tile + 1) * P.Tt;
-                fence_proxy_async();
-                mbar_expect_tx(&M.bars[nb], rain_bytes + pet_bytes);
-                tma_load_1d(M.forc_s + nb * forc_stride, C.rain + t_next * C.ngp, rain_bytes, &M.bars[nb]);
-                tma_load_1d(M.forc_s + nb * forc_stride + P.Tt * C.ngp, P.pet_pos + t_next * C.nge, pet_bytes, &M.bars[nb]);
+        // one loop, one copy of flush_step in the instruction stream (the river code shares the SM's instruction cache with
+        // the compute warps' 30 KB loop body): iteration t sums / routes step t-1 while the compute warps run step t
+#pragma unroll 1
+        for (int t = 0; t <= C.nstep; ++t) {
+            if (t < C.nstep && (t & (P.Tt - 1)) == 0) {      // first step of a forcing tile (Tt is a power of two)
+                if (t > 0) ++tiles_done;
+                if (rl == 0 && t + P.Tt < C.nstep) {
+                    // prefetch the next tile into the other buffer (the team left it at the last barrier)
+                    const uint32_t nb = (tiles_done & 1) ^ 1;
+                    const size_t t_next = (size_t)t + P.Tt;
+                    fence_proxy_async();
+                    mbar_expect_tx(&M.bars[nb], rain_bytes + pet_bytes);
+                    tma_load_1d(M.forc_s + nb * forc_stride, C.rain + t_next * C.ngp, rain_bytes, &M.bars[nb]);
+                    tma_load_1d(M.forc_s + nb * forc_stride + P.Tt * C.ngp, P.pet_pos + t_next * C.nge, pet_bytes, &M.bars[nb]);
+                }
             }
-            const int t_end = min(C.nstep, t + P.Tt);
-            for (; t < t_end; ++t) {
-                const long long c0 = R2_DBG ? clock64() : 0;
-                if (t > 0) flush_step(t - 1);                // while the compute warps run step t
-                if (R2_DBG) busy += clock64() - c0;
-#if R2_SPLIT
-                step_arrive(&M.bars[2]);                     // done with the contribution buffer of step t-1 ...
-                mbar_wait(&M.bars[2], steps_done & 1);       // ... and step t is published
-                ++steps_done;
-#else
-                team_sync(team);
-#endif
-            }
+            const long long c0 = R2_DBG ? clock64() : 0;
+            if (t > 0) flush_step(t - 1);
+            if (R2_DBG) busy += clock64() - c0;
+            if (t < C.nstep) team_sync(team);
         }
-        flush_step(C.nstep - 1);
+        ++tiles_done;
+        // the group's objective sums -> the finalize kernel's accumulators
+        for (int pg = rl; pg < Mv * nriv; pg += R2_TR) {
+            const int jm = pg / nriv, i = pg - jm * nriv;
+            const int m = m_base + jm;
+            if (m >= B) continue;
+            const double *acc = M.acc_s + pg * 6;
+            const size_t a = i * (size_t)B + m;
+            W.sse[a] = acc[0]; W.lsse[a] = acc[1]; W.sq[a] = acc[2]; W.sqq[a] = acc[3]; W.sqo[a] = acc[4];
+            if (acc[5] != 0.0) W.bad[a] = 1;
+        }
         if (R2_DBG && (rl & 31) == 0) P.dbg[blockIdx.x * 12 + 8 + team * 2 + (rl >> 5)] = busy;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------
-// routing role, warp B of a team: route_process_run_step + river's division by frac_sub_area + the objective sums
-// for every finished tile of DCP_RT_TILE steps (dcp_route_fused.cuh), one tile behind warp A.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void r2_route(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const int team) {
-    const int Mv = P.G * R2_S;
-    const int sl_base = (blockIdx.x * R2_TEAMS + team) * Mv;
-    for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
-        const int m_base = vg * Mv;
-        ab_sync(team);                                       // group start (pairs with warp A's)
-        for (int t0 = 0; t0 < C.nstep; t0 += DCP_RT_TILE) {
-            ab_sync(team);                                   // qout of [t0, t0 + tile) is in the rings
-            rt_tile<true>(C, W, m_base, Mv, sl_base, t0, min(C.nstep, t0 + DCP_RT_TILE));
-        }
     }
 }
 
@@ -763,7 +573,7 @@ template <bool AET, bool ONEPAR>
 __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchment C, DevBatch W, Res2Plan P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
-    // warps 0-3: team 0 compute, 4-7: team 1 compute, 8: team 0 river sums (A), 9: team 0 routing (B), 10-11: the same for team 1
+    // warps 0-3: team 0 compute, 4-7: team 1 compute, 8-9: team 0 river, 10-11: team 1 river
     const bool is_compute = tid < R2_CT;
     const int team = is_compute ? tid / R2_TC : (tid - R2_CT) / R2_TR;
     R2Smem M;
@@ -777,7 +587,9 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     M.par_s = (double2 *)(tb + P.off_par);
     M.forc_s = (double *)(tb + P.off_forc);
     M.bars = (uint64_t *)(tb + P.off_bar);
-    M.sz_s = (double2 *)(tb + P.off_sz);
+    M.job_s = (int4 *)(tb + P.off_job);
+    M.jres_s = (double *)(tb + P.off_jres);
+    M.acc_s = (double *)(tb + P.off_acc);
     M.ellw_s = (double *)(smem + P.off_ellw);
     M.coli_s = (int4 *)(smem + P.off_coli);
     M.cold_s = (double2 *)(smem + P.off_cold);
@@ -792,12 +604,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     if (!is_compute && (tid - R2_CT) % R2_TR == 0) {
         mbar_init(&M.bars[0], 1);
         mbar_init(&M.bars[1], 1);
-        mbar_init(&M.bars[2], R2_TT);                        // split per-step barrier: 128 compute threads + warp A
         fence_mbar_init();
     }
     __syncthreads();
 
-    static_assert(R2_CT * R2_REG_COMPUTE + R2_TEAMS * R2_TA * R2_REG_RIVER + R2_TEAMS * (R2_TR - R2_TA) * R2_REG_ROUTE <= R2_THREADS * 168,
+    static_assert(R2_CT * R2_REG_COMPUTE + R2_TEAMS * R2_TR * R2_REG_RIVER <= R2_THREADS * 168,
                   "register split exceeds the CTA's launch allocation: setmaxnreg.inc would never return");
     if (is_compute) {
         asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(R2_REG_COMPUTE));
@@ -806,19 +617,11 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
             const long long t0 = clock64();
             while (clock64() - t0 < P.phase_delay) {}
         }
-#if R2_SPLIT
-        r2_compute_split<AET, ONEPAR>(C, W, P, M, team, tid % R2_TC);
-#else
         r2_compute<AET, ONEPAR>(C, W, P, M, team, tid % R2_TC);
-#endif
-    } else if ((tid - R2_CT) % R2_TR < R2_TA) {
+    } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_RIVER));
         if (P.phase_delay < 0 && team == 1) return;
         r2_river(C, W, P, M, team, (tid - R2_CT) % R2_TR);
-    } else {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(R2_REG_ROUTE));
-        if (P.phase_delay < 0 && team == 1) return;
-        r2_route(C, W, P, team);
     }
 }
 #undef gc
