@@ -199,6 +199,9 @@ def load_library(path: str = LIB_PATH):
     lib.dcp_get_run_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
     lib.dcp_route_timeseries.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     lib.dcp_measure_fp64_peak.argtypes = [c_double_p, c_double_p]
+    if not hasattr(lib, "dcp_comm_init"):        # a kernel-tuning build of an older ABI (DCP_B200_LIB): single-GPU entry points only
+        _lib = lib
+        return lib
     lib.dcp_comm_init.argtypes = [C.c_int, c_int32_p, C.POINTER(C.c_void_p)]
     lib.dcp_comm_destroy.argtypes = [C.c_void_p]
     lib.dcp_comm_size.argtypes = [C.c_void_p]

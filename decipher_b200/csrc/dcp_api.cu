@@ -321,8 +321,6 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     Q.jobs_per_member = (int)job_node.size();
     const int n_jobs = G * S * Q.jobs_per_member;
     if (n_jobs > 4096) return;
-    Q.fir_team = 32;
-    while (Q.fir_team > 1 && Q.fir_team * n_jobs > 64) Q.fir_team >>= 1;
     // shared memory: [shared tables][team 0][team 1]
     size_t off = 0;
     auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
@@ -339,7 +337,6 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     Q.off_forc = take((size_t)2 * Q.Tt * (d->ngp + d->nge) * 8);
     Q.off_bar = take(16);
     Q.off_job = take((size_t)n_jobs * 16);
-    Q.off_jres = take((size_t)n_jobs * 8);
     Q.off_acc = take((size_t)G * S * nriv * 6 * 8);
     Q.team_bytes = (int)((off + 8191) & ~(size_t)8191);     // team blocks (tuple buffers first) sit on 8 KB boundaries
     Q.smem_bytes = Q.off_team + 8192 + 2 * Q.team_bytes;    // + the kernel's alignment slack
@@ -350,13 +347,13 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     up(ent, &Q.ell_w); up(col_i, &Q.col_i); up(col_d, &Q.col_d); up(col_ia, &Q.col_ia);
     up(rbeg, &Q.rbeg); up(pet_pos, &Q.pet_pos);
     up(job_node, &Q.job_node); up(job_gauge, &Q.job_gauge); up(gauge_job_beg, &Q.gauge_job_beg);
-    std::vector<double> inv_frac(nriv), log_obs(qobs.size(), 0.0);
-    for (int r = 0; r < nriv; ++r) inv_frac[r] = 1.0 / frac[r];
+    std::vector<double> inv_frac(nriv), obs_eps(nriv), log_obs(qobs.size(), 0.0);
+    for (int r = 0; r < nriv; ++r) { inv_frac[r] = 1.0 / frac[r]; obs_eps[r] = obs[r].eps; }
     for (size_t x = 0; x < qobs.size(); ++x) {
         const int g = (int)(x % nriv);
         if (qobs[x] != d->flow_err) log_obs[x] = std::log(qobs[x] > obs[g].eps ? qobs[x] : obs[g].eps);
     }
-    up(inv_frac, &Q.inv_frac);
+    up(inv_frac, &Q.inv_frac); up(obs_eps, &Q.obs_eps);
     if (!qobs.empty()) up(log_obs, &Q.log_obs); else Q.log_obs = nullptr;
     Q.feasible = 1;
 }

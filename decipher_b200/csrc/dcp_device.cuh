@@ -183,7 +183,7 @@ struct Res2Plan {
     int32_t phase_delay;            // cycles the second team waits at kernel start (0: none)
     int32_t smem_bytes, team_bytes;
     int32_t off_team;               // start of the team-private region; offsets below off_forc.. are relative to a team's base
-    int32_t off_qbf, off_con, off_cst, off_par, off_forc, off_bar, off_job, off_jres, off_acc;
+    int32_t off_qbf, off_con, off_cst, off_par, off_forc, off_bar, off_job, off_acc;
     int32_t off_ellw, off_coli, off_cold, off_rbeg;                // shared, absolute
     const double *ell_w;            // [ell_len] w * ac(src)   (dyna_dynamic_dist.f90:50-51), 0 in padding; the low 9
                                     //           mantissa bits hold the source's tuple index (0..511)
@@ -194,11 +194,11 @@ struct Res2Plan {
     const int32_t *rbeg;            // [nriv+1] contribution-slot ranges per river
     // routing inside the kernel: jobs of ONE member (gauge i x node u in {i} + upstream tree of i, gauge-major, own node first)
     int32_t jobs_per_member;
-    int32_t fir_team;               // lanes per job (power of two <= 32)
     const int32_t *job_node;        // [jobs_per_member] node u of the job
     const int32_t *job_gauge;       // [jobs_per_member] gauge i of the job
     const int32_t *gauge_job_beg;   // [nriv+1] jobs of gauge i
     const double *inv_frac;         // [nriv] 1 / frac_sub_area of the gauge's node
+    const double *obs_eps;          // [nriv] floor of the logarithmic measure (mean observed flow / 100)
     const double *log_obs;          // [nriv x nstep_obs] ln(max(qobs, eps)) (0 where the observation is missing), or null
     const double *pet_pos;          // [nge x nstep_pad] max(pe_step, 0): the root zone only acts on ep > 0 (dyna_root_zone1.f90:55)
     long long *dbg;                 // optional busy-cycle counters [grid][12 warps]

@@ -97,7 +97,6 @@ struct R2Smem {                       // team-private views unless noted
     double *forc_s;       // [2][Tt*(ngp+nge)]
     uint64_t *bars;       // [2] forcing tiles (TMA)
     int4 *job_s;          // [Mv * jobs_per_member]  routing jobs of the group: {ring offset, delay, taps, histogram offset}
-    double *jres_s;       // [Mv * jobs_per_member]  this step's result of every job
     double *acc_s;        // [Mv * nriv][6]          objective sums sse, lsse, sq, sqq, sqo and the non-finite flag
     // shared by both teams (read-only after setup)
     double *ellw_s;       // [ell_len]       packed gather list (weight | source tuple index)
@@ -118,8 +117,6 @@ __device__ __forceinline__ double2 lds_tuple(int lo, uint32_t buf_u32) {
 }
 
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(R2_TT) : "memory"); }
-// the two river warps of a team among themselves (sums -> convolution jobs -> gauges inside one step)
-__device__ __forceinline__ void river_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 3), "n"(R2_TR) : "memory"); }
 
 #define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})
 
@@ -154,6 +151,88 @@ static __device__ __noinline__ R2Fix r2_fix_unit(uint32_t cst_a, uint32_t par_a,
 }
 
 // ---------------------------------------------------------------------------------------------
+// Routing + objective terms of a finished TILE of steps [t0, t1) (t1 - t0 <= R2_RT), run by the team's four compute warps
+// once per R2_RT steps -- NOT by the river warps every step: measured on C2 (profiles/r2_ab_routing_designs.txt), the
+// convolution in the river warps costs 8 % for the per-step FIR, 8 % for the per-step gauge terms and 27 % for both (their
+// latency chain then exceeds a compute step), a dedicated routing warp 16 %; here the lanes of a warp are 32 consecutive
+// TIMESTEPS of one (member, gauge) pair, every lane busy, no barrier, ~2 % of the compute warps' instructions.
+//     job(t)  = sum_k delay_hist_u(k + o) * qout_u(t - d - k)       one job per node u in {i} + upstream tree of gauge i
+//     q_i(t)  = (sum of the gauge's jobs) / frac_sub_area             (DTA/dta_route_processing.f90:671-714, dyna_river.f90:57-59)
+// The inflows come from the member slot's RING (the river warps store qout(t) there one step behind the compute warps),
+// the per-(member, gauge) objective sums live in shared memory: a warp shuffle tree per tile, then one lane adds the tile's
+// partial sums (deterministic order: tiles ascending).  Only measures -- and the flows when requested -- leave the chip.
+// FAST policy only (no summation-order contract); the EXACT policy routes in dcp_route_fused.cuh.
+// ---------------------------------------------------------------------------------------------
+#define R2_RT 64                      // == the forcing tile DCP_RES_TT: routing happens between two tiles (ring slack: dcp_api.cu)
+struct R2RouteArgs {
+    const double *dh, *ring, *qobs, *log_obs, *inv_frac, *obs_eps;
+    double *q_user;
+    const int32_t *gauge_job_beg;
+    uint32_t job_s, acc_s;            // shared-memory addresses
+    int Rmask, nriv, njm, n_pairs, m_base, B, nstep, n_t, t_warm;
+    double flow_err;
+};
+static __device__ __noinline__ void r2_route_tile(const R2RouteArgs a, const int t0, const int t1, const int warp, const int lane) {
+    for (int pg = warp; pg < a.n_pairs; pg += R2_TC / 32) {                  // (member slot, gauge) pairs over the 4 warps
+        const int jm = pg / a.nriv, i = pg - jm * a.nriv;
+        const int m = a.m_base + jm;
+        if (m >= a.B) continue;                                              // warp-uniform
+        const int jb = a.gauge_job_beg[i], je = a.gauge_job_beg[i + 1];
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0, s4 = 0.0;
+        bool bad = false;
+        for (int tb = t0; tb < t1; tb += 32) {
+            const int t = tb + lane;
+            if (t < t1) {
+                double q_sum = 0.0;
+                for (int jj = jb; jj < je; ++jj) {
+                    int4 e;
+                    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(e.x), "=r"(e.y), "=r"(e.z), "=r"(e.w) : "r"(a.job_s + (jm * a.njm + jj) * 16));
+                    const int tq = t - e.y;
+                    const int nt = min(e.z, tq + 1);                         // terms before the first timestep do not exist
+                    const double *__restrict__ dh = a.dh + e.w;
+                    const double *qi = a.ring + e.x;
+                    double y = 0.0;
+#pragma unroll 4
+                    for (int k = 0; k < nt; ++k) y = fma(dh[k], qi[(tq - k) & a.Rmask], y);
+                    q_sum += y;
+                }
+                const double q = q_sum * a.inv_frac[i];
+                if (a.q_user) a.q_user[((size_t)m * a.nstep + t) * a.nriv + i] = q;
+                const bool fin = isfinite(q);
+                bad |= !fin;
+                if (a.qobs != nullptr && t >= a.t_warm && t < a.n_t) {
+                    const double o = a.qobs[(size_t)t * a.nriv + i];
+                    if (o != a.flow_err && fin) {
+                        const double eps = a.obs_eps[i];
+                        const double d = q - o;
+                        const double dl = LEAN_LOG(q > eps ? q : eps) - a.log_obs[(size_t)t * a.nriv + i];   // ln(max(obs, eps)): member independent
+                        s0 = fma(d, d, s0); s1 = fma(dl, dl, s1); s2 += q; s3 = fma(q, q, s3); s4 = fma(q, o, s4);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s0 += __shfl_xor_sync(0xffffffffu, s0, o); s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o); s3 += __shfl_xor_sync(0xffffffffu, s3, o);
+            s4 += __shfl_xor_sync(0xffffffffu, s4, o);
+        }
+        const bool any_bad = __any_sync(0xffffffffu, bad);
+        if (lane == 0) {
+            const uint32_t ad = a.acc_s + pg * 48;
+            double c0, c1, c2, c3, c4;
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c0), "=d"(c1) : "r"(ad));
+            asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(c2), "=d"(c3) : "r"(ad + 16));
+            asm volatile("ld.shared.f64 %0, [%1];" : "=d"(c4) : "r"(ad + 32));
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad), "d"(c0 + s0), "d"(c1 + s1) : "memory");
+            asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(ad + 16), "d"(c2 + s2), "d"(c3 + s3) : "memory");
+            asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad + 32), "d"(c4 + s4) : "memory");
+            if (any_bad) asm volatile("st.shared.f64 [%0], %1;" ::"r"(ad + 40), "d"(1.0) : "memory");
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // compute role: 4 warps per team, thread = 4 HRU columns x 2 member slots
 // ---------------------------------------------------------------------------------------------
 // ONEPAR: one parameter layer and one member sub-group per team (C2): the member-parameter words sit at fixed
@@ -173,6 +252,15 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
     for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
         const int m_base = vg * Mv;
         team_sync(team);                                     // previous group fully done with shared memory
+        auto route_args = [&]() {
+            R2RouteArgs a;
+            a.dh = W.dh; a.ring = W.qout; a.qobs = C.qobs; a.log_obs = P.log_obs; a.inv_frac = P.inv_frac; a.obs_eps = P.obs_eps;
+            a.q_user = W.q_user; a.gauge_job_beg = P.gauge_job_beg;
+            a.job_s = smem_u32(M.job_s); a.acc_s = smem_u32(M.acc_s);
+            a.Rmask = W.Rmask; a.nriv = C.nriv; a.njm = P.jobs_per_member; a.n_pairs = Mv * C.nriv; a.m_base = m_base; a.B = B;
+            a.nstep = C.nstep; a.n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs; a.t_warm = C.t_warm; a.flow_err = C.flow_err;
+            return a;
+        };
 
         // ---- load the group's initial state (written by k_init_members) ----
         double sd[H][S], suz[H][S], srz[H][S], aet[H][S];
@@ -231,8 +319,15 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #pragma unroll
         for (int u = 0; u < GB; ++u) wv[u] = ent0[u * 32];
 
-        int t = 0;
-        for (int tile = 0; tile < ntiles; ++tile, ++tiles_done) {
+        int t = 0, routed = 0;
+        // one pass per forcing tile + a last pass without steps: every pass ends by routing the steps whose river inflows are
+        // complete (the river warps run one step behind), OUTSIDE the step loop -- a call inside it costs 6 % (register
+        // allocation of the hot basic blocks), between two tiles nothing measurable
+#pragma unroll 1
+        for (int tile = 0; tile <= ntiles; ++tile) {
+            int r_hi = C.nstep;
+            if (tile == ntiles) team_sync(team);             // the river warps have stored qout(nstep - 1)
+            else {
             const uint32_t b = tiles_done & 1;
             mbar_wait(&M.bars[b], (tiles_done >> 1) & 1);    // forcing tile landed (TMA, issued by the team's river warp)
             const double *forc_t = M.forc_s + b * forc_stride;
@@ -387,6 +482,22 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                 if (R2_DBG) busy += clock64() - c0;
                 team_sync(team);
             }
+            ++tiles_done;
+            r_hi = t - 1;                                    // qout of every step < t - 1 ... t - 2 is in the rings; step t - 1 follows next pass
+            }
+            if (r_hi > routed) r2_route_tile(route_args(), routed, r_hi, tt_id >> 5, tt_id & 31);
+            routed = r_hi > routed ? r_hi : routed;
+        }
+        __syncwarp();
+        for (int pg = (tt_id >> 5); pg < Mv * C.nriv; pg += R2_TC / 32) {               // the pair's warp wrote its sums: lane 0 hands them over
+            const int jm = pg / C.nriv, i = pg - jm * C.nriv;
+            const int m = m_base + jm;
+            if ((tt_id & 31) == 0 && m < B) {
+                const double *acc = M.acc_s + pg * 6;
+                const size_t a = i * (size_t)B + m;
+                W.sse[a] = acc[0]; W.lsse[a] = acc[1]; W.sq[a] = acc[2]; W.sqq[a] = acc[3]; W.sqo[a] = acc[4];
+                if (acc[5] != 0.0) W.bad[a] = 1;
+            }
         }
         if (R2_DBG && (tt_id & 31) == 0) P.dbg[blockIdx.x * 12 + team * 4 + (tt_id >> 5)] = busy;
         if (AET) {
@@ -405,18 +516,12 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 }
 
 // ---------------------------------------------------------------------------------------------
-// river role: 2 warps per team, one step behind the compute warps.  Per finished step tp:
-//   (1) SUMS      a group of T lanes adds up one (member sub-group, river) range of contribution tuples: qout_r(tp)
-//                 (dyna_river.f90:43), stored into the member slot's inflow RING (the last `hist_len` values per river are
-//                 all the routing ever needs -- no series of length nstep exists unless the caller asks for the flows);
-//   (2) ROUTING   the time-delay-histogram convolution of route_process_run_step (DTA/dta_route_processing.f90:671-727)
-//                 as warp-shuffle FIRs: one JOB per (member, gauge i, node u in {i} + upstream tree of i),
-//                     job(tp) = sum_k delay_hist_u(k + o) * qout_u(tp - d - k),   d = delay of u's histogram start past i's column,
-//                 L lanes split the taps of a job and meet in a shuffle tree (the FAST policy has no summation-order
-//                 contract; the EXACT policy lives in the first-generation kernel, dcp_route_fused.cuh);
-//   (3) GAUGES    one lane per (member, gauge): q_i(tp) = (sum of its jobs) / frac_sub_area (dyna_river.f90:57-59), the flow
-//                 output when requested, and the objective terms added to sums kept in shared memory.
-// Lane 0 also drives the team's forcing TMA.  Only the measures (and the flows when requested) leave the chip.
+// river role: 2 warps per team, one step behind the compute warps.  A group of T lanes adds up one (member sub-group,
+// river) range of contribution tuples: qout_r(tp) (dyna_river.f90:43), stored into the member slot's inflow RING -- the last
+// `hist_len` (+ one routing tile) values per river are all the routing ever needs, so no series of length nstep exists
+// unless the caller asks for the flows.  At the start of a group the river lanes also lay out the group's routing jobs
+// (the histogram geometry depends on each member's channel velocity) and clear its objective sums; lane 0 drives the
+// team's forcing TMA.
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, const R2Smem &M,
                                          const int team, const int rl) {
@@ -432,9 +537,6 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
     const int sums_per_pass = R2_TR / T;
     const int sl_base = (blockIdx.x * R2_TEAMS + team) * Mv; // ring slots of this team (one per member in flight)
     const int njm = P.jobs_per_member, n_jobs = Mv * njm;
-    const int L = P.fir_team, fsub = rl & (L - 1);
-    const int jobs_per_pass = R2_TR / L;
-    const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
     long long busy = 0;
 
     for (int vg = blockIdx.x * R2_TEAMS + team; vg < P.n_groups; vg += gridDim.x * R2_TEAMS) {
@@ -481,7 +583,7 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
                 const int beg = M.rbeg_s[r], end = live ? M.rbeg_s[r + 1] : beg;
                 const double2 *cg = con + g * nac_pad;
                 double a0 = 0.0, a1 = 0.0;
-#pragma unroll 2
+#pragma unroll 4
                 for (int p = beg + sub; p < end; p += T) { const double2 x = cg[p]; a0 += x.x; a1 += x.y; }
                 for (int o = T >> 1; o > 0; o >>= 1) {
                     a0 += __shfl_xor_sync(0xffffffffu, a0, o);
@@ -491,44 +593,6 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
                     const size_t tq = (size_t)(tp & W.Rmask);
                     W.qout[((size_t)(sl_base + g * S + 0) * nriv + r) * W.R + tq] = a0;
                     W.qout[((size_t)(sl_base + g * S + 1) * nriv + r) * W.R + tq] = a1;
-                }
-            }
-            river_sync(team);                                // every qout(tp) of the group is in the rings
-#pragma unroll 1
-            for (int j0 = 0; j0 < n_jobs; j0 += jobs_per_pass) {
-                const int j = j0 + rl / L;
-                const int4 e = M.job_s[j < n_jobs ? j : 0];
-                int nt = j < n_jobs ? min(e.z, tp - e.y + 1) : 0;                    // terms before the first timestep do not exist
-                const double *__restrict__ dh = W.dh + e.w;
-                const double *qi = W.qout + e.x;
-                const int tb = tp - e.y;
-                double y = 0.0;
-#pragma unroll 2
-                for (int k = fsub; k < nt; k += L) y = fma(dh[k], qi[(tb - k) & W.Rmask], y);
-                for (int o = L >> 1; o > 0; o >>= 1) y += __shfl_xor_sync(0xffffffffu, y, o);
-                if (fsub == 0 && j < n_jobs) M.jres_s[j] = y;
-            }
-            river_sync(team);
-#pragma unroll 1
-            for (int pg = rl; pg < Mv * nriv; pg += R2_TR) {
-                const int jm = pg / nriv, i = pg - jm * nriv;
-                const int m = m_base + jm;
-                if (m >= B) continue;
-                double q_sum = 0.0;
-                for (int jj = P.gauge_job_beg[i]; jj < P.gauge_job_beg[i + 1]; ++jj) q_sum += M.jres_s[jm * njm + jj];
-                const double q = q_sum * P.inv_frac[i];      // FAST policy: hoisted reciprocal of frac_sub_area (dyna_river.f90:57-59)
-                if (W.q_user) W.q_user[((size_t)m * C.nstep + tp) * nriv + i] = q;
-                double *acc = M.acc_s + pg * 6;
-                if (!isfinite(q)) acc[5] = 1.0;
-                if (C.qobs != nullptr && tp >= C.t_warm && tp < n_t) {
-                    const double o = C.qobs[(size_t)tp * nriv + i];
-                    if (o != C.flow_err && isfinite(q)) {
-                        const double eps = C.obs[i].eps;
-                        const double d = q - o;
-                        const double dl = LEAN_LOG(q > eps ? q : eps) - P.log_obs[(size_t)tp * nriv + i];   // ln(max(obs, eps)) is member independent
-                        acc[0] += d * d; acc[1] += dl * dl;
-                        acc[2] += q; acc[3] = fma(q, q, acc[3]); acc[4] = fma(q, o, acc[4]);
-                    }
                 }
             }
         };
@@ -555,16 +619,7 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
             if (t < C.nstep) team_sync(team);
         }
         ++tiles_done;
-        // the group's objective sums -> the finalize kernel's accumulators
-        for (int pg = rl; pg < Mv * nriv; pg += R2_TR) {
-            const int jm = pg / nriv, i = pg - jm * nriv;
-            const int m = m_base + jm;
-            if (m >= B) continue;
-            const double *acc = M.acc_s + pg * 6;
-            const size_t a = i * (size_t)B + m;
-            W.sse[a] = acc[0]; W.lsse[a] = acc[1]; W.sq[a] = acc[2]; W.sqq[a] = acc[3]; W.sqo[a] = acc[4];
-            if (acc[5] != 0.0) W.bad[a] = 1;
-        }
+        team_sync(team);                                     // qout of the last step is in the rings: the compute warps route the tail
         if (R2_DBG && (rl & 31) == 0) P.dbg[blockIdx.x * 12 + 8 + team * 2 + (rl >> 5)] = busy;
     }
 }
@@ -588,7 +643,6 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     M.forc_s = (double *)(tb + P.off_forc);
     M.bars = (uint64_t *)(tb + P.off_bar);
     M.job_s = (int4 *)(tb + P.off_job);
-    M.jres_s = (double *)(tb + P.off_jres);
     M.acc_s = (double *)(tb + P.off_acc);
     M.ellw_s = (double *)(smem + P.off_ellw);
     M.coli_s = (int4 *)(smem + P.off_coli);
