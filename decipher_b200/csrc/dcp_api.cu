@@ -87,6 +87,7 @@ struct dcp_catchment {
     bool has_qobs = false;
     ResPlan plan{};                     // resident-kernel plan (plan.feasible == 0: streamed kernel only)
     Res2Plan plan2{};                   // second-generation resident kernel (lean arithmetic, own-river catchments)
+    Res2Plan plan2w{};                  // its wide build: 513 .. 1024 HRUs (FAST policy only)
     DensePlan dplan{};                  // stepwise path: ordered river lists, dense W when it pays
     int n_sm = 148;
     size_t smem_optin = 0;
@@ -100,10 +101,14 @@ namespace {
 void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vector<HruStatic> &hru,
                  const std::vector<WEntry> &w, const std::vector<int32_t> &thread_hru, const std::vector<int32_t> &hru_pos,
                  int nac_pad, const std::vector<double> &pet, const std::vector<double> &frac, const std::vector<double> &qobs,
-                 const std::vector<ObsStat> &obs, cudaError_t &e) {
-    const int nac = d->nac, nriv = d->nriv, npt = d->npt, S = 2, COLS = DCP_RES_COMPUTE, TC = 128, H = 4;
+                 const std::vector<ObsStat> &obs, bool wide, cudaError_t &e) {
+    // narrow build: 2 teams x 128 compute threads x 4 columns = 512 columns per member slot; wide build (dcp_resident_v2w.cu):
+    // 1 team x 256 compute threads = 1024 columns
+    const int nac = d->nac, nriv = d->nriv, npt = d->npt, S = 2, TEAMS = wide ? 1 : 2, TC = 256 / TEAMS, H = 4, COLS = H * TC;
+    const int TR = 128 / TEAMS, NW = TC / 32, PARW = wide ? 4 : 3, COLW = wide ? 2 : 3;
     const DevCatchment &C = c->C;
-    Res2Plan &Q = c->plan2;
+    Res2Plan &Q = wide ? c->plan2w : c->plan2;
+    Q.wide = wide ? 1 : 0;
     // every river share of an HRU must sit on its own river ipriv (contribution sums)
     std::vector<double> cq(nac, 0.0);
     for (int ia = 0; ia < nac; ++ia)
@@ -114,7 +119,7 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
             cq[ia] = C.dtt * hru[ia].w_riv * sh * hru[ia].ac;
         }
     const int G = COLS / nac_pad, npb = nac_pad / 32;
-    if (d->ngp > 255 || d->nge > 255 || G * S * npt * 3 + npt * 3 > 65535) return;
+    if (d->ngp > 255 || d->nge > 255 || G * S * npt * PARW + npt * PARW > 65535) return;
     Q.nac_pad = nac_pad; Q.G = G; Q.Tt = DCP_RES_TT;
     Q.phase_delay = getenv("DCP_RES_PHASE") ? atoi(getenv("DCP_RES_PHASE")) : 0;
 
@@ -194,7 +199,9 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
                         size_t pick = 0;
                         while ((hru_pos[w[rem[l][pick]].src] & 7) != cls_of[l]) ++pick;
                         const WEntry &we = w[rem[l][pick]];
-                        ell_w[o] = we.w * we.ac_src; ell_src[o] = (uint16_t)hru_pos[we.src];
+                        // wide build: 1/ac of the DESTINATION is folded in too (qin is only ever used as qin / ac)
+                        ell_w[o] = wide ? (we.w * we.ac_src) / hru[thread_hru[pos]].ac : we.w * we.ac_src;
+                        ell_src[o] = (uint16_t)hru_pos[we.src];
                         rem[l].erase(rem[l].begin() + pick);
                     } else {
                         // zero weight on an idle position's tuple (always 0.0, so nothing non-finite can leak from another
@@ -242,32 +249,35 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
         }
     }
 
-    // ---- the 16 blocks of 32 columns are dealt to the 4 compute warps of a team longest-first ----
-    std::vector<int> blocks(16), load(4, 0), cnt(4, 0);
-    for (int i = 0; i < 16; ++i) blocks[i] = i;
+    // ---- the COLS/32 blocks of 32 columns are dealt to the compute warps of a team longest-first ----
+    const int NBLK = COLS / 32;
+    std::vector<int> blocks(NBLK), load(NW, 0), cnt(NW, 0);
+    for (int i = 0; i < NBLK; ++i) blocks[i] = i;
     std::stable_sort(blocks.begin(), blocks.end(), [&](int a, int b) { return ell_K[a % npb] > ell_K[b % npb]; });
-    int slot_blk[4][4];
-    for (int bi = 0; bi < 16; ++bi) {
+    std::vector<std::vector<int>> slot_blk(NW, std::vector<int>(H, 0));
+    for (int bi = 0; bi < NBLK; ++bi) {
         const int blk = blocks[bi];
         int wsel = -1;
-        for (int wi = 0; wi < 4; ++wi) if (cnt[wi] < H && (wsel < 0 || load[wi] < load[wsel])) wsel = wi;
+        for (int wi = 0; wi < NW; ++wi) if (cnt[wi] < H && (wsel < 0 || load[wi] < load[wsel])) wsel = wi;
         slot_blk[wsel][cnt[wsel]++] = blk;
         load[wsel] += ell_K[blk % npb];
     }
     // ---- flat gather list per compute warp: the four columns of a thread one after the other, step-major over the
-    // lanes, one 8-byte word per entry = the weight with the byte offset of the source tuple (index << 4, index < 512)
-    // in mantissa bits 4..12 (weight rounded to the nearest multiple of 2^13 ulp: relative change <= 2^-40).  One spare batch of four
-    // steps follows each warp's list (the kernel prefetches one batch ahead). ----
-    auto pack = [](double wv, int idx) {
+    // lanes, one 8-byte word per entry = the weight with the byte offset of the source tuple (index << 4, index < COLS)
+    // in mantissa bits 4..12 (4..13 in the wide build; weight rounded to the nearest multiple of 2^13 / 2^14 ulp: relative
+    // change <= 2^-40 / 2^-39).  One spare batch of four steps follows each warp's list (the kernel prefetches one batch ahead). ----
+    const uint64_t half = (uint64_t)COLS * 8, keep = ~((uint64_t)COLS * 16 - 1);
+    auto pack = [half, keep](double wv, int idx) {
         uint64_t b; std::memcpy(&b, &wv, 8);
-        b = ((b + 4096) & ~(uint64_t)8191) | ((uint64_t)idx << 4);
+        b = ((b + half) & keep) | ((uint64_t)idx << 4);
         double r; std::memcpy(&r, &b, 8); return r;
     };
     std::vector<double> ent;
     std::vector<int4> col_i((size_t)H * TC);
-    std::vector<double2> col_d((size_t)H * TC * 3);
+    std::vector<double2> col_d((size_t)H * TC * COLW);
+    std::vector<double> eq0((size_t)H * TC, 1.0);
     std::vector<int32_t> col_ia((size_t)H * TC, -1);
-    for (int wi = 0; wi < 4; ++wi)
+    for (int wi = 0; wi < NW; ++wi)
         for (int j = 0; j <= H; ++j) {
             const size_t fbase = ent.size();
             if (j == H) { ent.resize(fbase + DCP_RES2_GB * 32, 0.0); break; }
@@ -286,25 +296,31 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
                 ci.x = (int)(fbase + l) | (K << 20);
                 ci.y = (h ? h->ippt : 0) | ((h ? h->ipet : 0) << 8) | (g << 16) | (h ? 0 : (int)0x80000000u);
                 ci.z = (g * nac_pad + pos) | ((g * nac_pad) << 16);
-                ci.w = ((g * S * npt + (h ? h->ipar : 0)) * 3) | ((g * nac_pad + rank[pos]) << 16);
+                ci.w = ((g * S * npt + (h ? h->ipar : 0)) * PARW) | ((g * nac_pad + rank[pos]) << 16);
                 col_i[o] = ci;
-                col_d[o] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);                 // word-major: a warp's
-                col_d[(size_t)H * TC + o] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);     // LDS.128 spans 512 B
-                col_d[(size_t)2 * H * TC + o] = make_double2(h ? 1.0 / h->cosm : 1.0, 0.0);
+                if (wide) {                                                                          // word-major: a warp's
+                    col_d[o] = make_double2(h ? h->ac : 1.0, h ? cq[ia] : 0.0);                      // LDS.128 spans 512 B
+                    col_d[(size_t)H * TC + o] = make_double2(h ? h->cosm : 1.0, h ? 1.0 / h->cosm : 1.0);
+                    eq0[o] = h ? std::exp(-h->st) : 1.0;
+                } else {
+                    col_d[o] = make_double2(h ? h->ac : 1.0, h ? 1.0 / h->ac : 1.0);
+                    col_d[(size_t)H * TC + o] = make_double2(h ? cq[ia] : 0.0, h ? h->cosm : 1.0);
+                    col_d[(size_t)2 * H * TC + o] = make_double2(h ? 1.0 / h->cosm : 1.0, 0.0);
+                }
                 col_ia[o] = ia;
             }
         }
     if (getenv("DCP_RES_DEBUG"))
-        fprintf(stderr, "[dcp plan2] gather list %zu entries (nnz %zu), K per block:%s; gather steps per warp: %d %d %d %d\n", ent.size(),
+        fprintf(stderr, "[dcp plan2%s] gather list %zu entries (nnz %zu), K per block:%s; gather steps per warp:%s\n", wide ? "w" : "", ent.size(),
                 w.size(), [&] { static std::string s2; s2.clear(); for (int pb = 0; pb < npb; ++pb) s2 += " " + std::to_string(ell_K[pb]); return s2.c_str(); }(),
-                load[0], load[1], load[2], load[3]);
+                [&] { static std::string s3; s3.clear(); for (int wi = 0; wi < NW; ++wi) s3 += " " + std::to_string(load[wi]); return s3.c_str(); }());
     Q.ell_len = (int)ent.size();
     if (Q.ell_len >= (1 << 20)) return;
 
     Q.n_teams = G * nriv;
     Q.team = 32;
-    while (Q.team > 1 && Q.team * Q.n_teams > 64) Q.team >>= 1;
-    Q.n_pass = (Q.n_teams * Q.team + 63) / 64;
+    while (Q.team > 1 && Q.team * Q.n_teams > TR) Q.team >>= 1;
+    Q.n_pass = (Q.n_teams * Q.team + TR - 1) / TR;
     if (Q.n_pass > 16) return;
     // routing jobs of one member: gauge i x node u in {i} + upstream tree of i (order of route_process_run_step's sum,
     // DTA/dta_route_processing.f90:685-714)
@@ -326,25 +342,31 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     auto take = [&](size_t bytes) { off = (off + 127) & ~(size_t)127; const size_t o = off; off += bytes; return (int)o; };
     Q.off_ellw = take((size_t)Q.ell_len * 8);
     Q.off_coli = take((size_t)H * TC * 16);
-    Q.off_cold = take((size_t)H * TC * 48);
+    Q.off_cold = take((size_t)H * TC * 16 * COLW);
     Q.off_rbeg = take((size_t)(nriv + 1) * 4);
+    Q.off_eq0 = take(wide ? (size_t)H * TC * 8 : 0);
     Q.off_team = (int)((off + 127) & ~(size_t)127);
     off = 0;
     Q.off_qbf = take((size_t)2 * COLS * 16);
     Q.off_con = take((size_t)2 * COLS * 16);
-    Q.off_cst = take((size_t)S * COLS * 16);
-    Q.off_par = take((size_t)G * S * npt * 3 * 16);
+    Q.off_cst = take((size_t)S * COLS * (wide ? 8 : 16));
+    Q.off_par = take((size_t)G * S * npt * PARW * 16);
     Q.off_forc = take((size_t)2 * Q.Tt * (d->ngp + d->nge) * 8);
     Q.off_bar = take(16);
     Q.off_job = take((size_t)n_jobs * 16);
     Q.off_acc = take((size_t)G * S * nriv * 6 * 8);
-    Q.team_bytes = (int)((off + 8191) & ~(size_t)8191);     // team blocks (tuple buffers first) sit on 8 KB boundaries
-    Q.smem_bytes = Q.off_team + 8192 + 2 * Q.team_bytes;    // + the kernel's alignment slack
+    // narrow build: team blocks (tuple buffers first) sit on boundaries of one tuple buffer (the kernel ORs the tuple offset
+    // into the buffer address) and the plan reserves the alignment slack; the wide build adds the offset instead (16 KB of
+    // slack would not fit beside 1024 columns) and needs no alignment
+    const size_t tupb = wide ? 128 : (size_t)COLS * 16;
+    Q.team_bytes = (int)((off + tupb - 1) & ~(tupb - 1));
+    Q.smem_bytes = Q.off_team + (wide ? 0 : (int)tupb) + (TEAMS - 1) * Q.team_bytes + (int)((off + 127) & ~(size_t)127);
     if ((size_t)Q.smem_bytes > c->smem_optin) return;
     std::vector<double> pet_pos(pet);
     for (double &x : pet_pos) x = x > 0.0 ? x : 0.0;
     auto up = [&](auto &vec, auto **dst) { if (e == cudaSuccess) e = upload(vec, dst, c->owned); };
     up(ent, &Q.ell_w); up(col_i, &Q.col_i); up(col_d, &Q.col_d); up(col_ia, &Q.col_ia);
+    if (wide) up(eq0, &Q.eq0);
     up(rbeg, &Q.rbeg); up(pet_pos, &Q.pet_pos);
     up(job_node, &Q.job_node); up(job_gauge, &Q.job_gauge); up(gauge_job_beg, &Q.gauge_job_beg);
     std::vector<double> inv_frac(nriv), obs_eps(nriv), log_obs(qobs.size(), 0.0);
@@ -587,8 +609,21 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
         int nac_pad = 32;
         while (nac_pad < nac) nac_pad <<= 1;
         const int S = DCP_RES_S, CT = DCP_RES_COMPUTE;
-        if (nac_pad > CT) c->plan_why = "nac > 512 HRUs";
-        else {
+        if (nac_pad > CT) {
+            c->plan_why = "nac > 512 HRUs (513 .. 1024: FAST policy only, wide resident kernel)";
+            // ---- wide build of the second-generation kernel: one team of 1024 columns (dcp_resident_v2w.cu) ----
+            c->plan2w = Res2Plan{};
+            bool lean_ok = d->ntt == 1;
+            for (int i = 0; i < nac; ++i) if (hru[i].ims_rz != 1 || hru[i].ims_uz != 1) lean_ok = false;
+            if (nac <= 1024 && lean_ok && !getenv("DCP_RES_NO_V2")) {
+                std::vector<int32_t> order(nac), thread_hru(1024, -1), hru_pos(nac, 0);
+                for (int i = 0; i < nac; ++i) order[i] = i;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+                    return (hru[a].row_end - hru[a].row_beg) > (hru[b].row_end - hru[b].row_beg); });
+                for (int i = 0; i < nac; ++i) { thread_hru[i] = order[i]; hru_pos[order[i]] = i; }
+                build_plan2(c, d, hru, w, thread_hru, hru_pos, 1024, pet, frac, qobs, obs, true, e);
+            }
+        } else {
             P.nac_pad = nac_pad; P.G = CT / nac_pad; P.Tt = DCP_RES_TT; P.nnz = (int)w.size();
             while (P.G > 1 && P.G * S * nriv > DCP_RES_MAXPAIRS) P.G >>= 1;    // river lanes carry 2 chains per (member, river)
             P.Mc = P.G * S;
@@ -646,7 +681,7 @@ int dcp_catchment_create(const dcp_catchment_desc *d, dcp_catchment **out) {
                 // ---- second-generation plan (dcp_resident_v2.cu) ----
                 c->plan2 = Res2Plan{};
                 if (P.lean_ok && !getenv("DCP_RES_NO_V2"))
-                    build_plan2(c, d, hru, w, thread_hru, hru_pos, nac_pad, pet, frac, qobs, obs, e);
+                    build_plan2(c, d, hru, w, thread_hru, hru_pos, nac_pad, pet, frac, qobs, obs, false, e);
             }
         }
     }
@@ -828,12 +863,13 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     // kernel choice: the resident kernel whenever the catchment fits on chip; the balance checks
     // (results_ts / root_zone1 STOP conditions) exist in the streamed kernel only
     bool use_res = false, use_sw = false;
+    const bool res_ok = c->plan.feasible || (fast && c->plan2w.feasible);     // 513 .. 1024 HRUs: the wide kernel, FAST policy
     if (o.kernel == DCP_KERNEL_RESIDENT) {
-        if (!c->plan.feasible) return fail(DCP_ERR_UNSUPPORTED, "resident kernel unavailable: %s", c->plan_why.c_str());
+        if (!res_ok) return fail(DCP_ERR_UNSUPPORTED, "resident kernel unavailable: %s", c->plan_why.c_str());
         if (check) return fail(DCP_ERR_UNSUPPORTED, "DCP_OPT_CHECK_BALANCE needs the streamed kernel");
         use_res = true;
     } else if (o.kernel == DCP_KERNEL_AUTO) {
-        use_res = c->plan.feasible && !check;
+        use_res = res_ok && !check;
         use_sw = !use_res && !check && c->dplan.feasible;      // catchments too large for the chip: one launch set per step
     } else if (o.kernel == DCP_KERNEL_STEPWISE) {
         if (!c->dplan.feasible) return fail(DCP_ERR_UNSUPPORTED, "stepwise kernels unavailable for this catchment");
@@ -852,16 +888,17 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     // time tile: the resident kernel runs a member group through ALL steps in one launch
     int tile = use_res ? C.nstep : (o.steps_per_tile > 0 ? o.steps_per_tile : 1024);
     tile = std::min(tile, C.nstep);
-    const int wave = use_res ? c->n_sm * c->plan.Mc : 32;       // members that fill the GPU once
+    const bool use_v2w = use_res && !c->plan.feasible;          // wide build: 2 members per CTA
+    const int wave = use_res ? c->n_sm * (use_v2w ? 2 : c->plan.Mc) : 32;       // members that fill the GPU once
     int64_t Bmax = o.members_per_batch > 0 ? o.members_per_batch : (use_res ? (int64_t)wave * 64 : 131072);
     Bmax = std::min<int64_t>(Bmax, n_member);
 
     // resident kernels route and score inside the kernel (dcp_route_fused.cuh): rings per member in flight instead of
     // nstep-long series per member.  (The two-column lean variant of the first generation keeps the separate kernels.)
-    const bool use_v2 = use_res && fast && c->plan2.feasible;
+    const bool use_v2 = use_res && fast && (use_v2w || c->plan2.feasible);
     const bool v1_two_col = use_res && !use_v2 && fast && c->plan.lean_ok && (c->plan.variant ? c->plan.variant : 2) == 2;
     const bool fused = use_res && !v1_two_col;
-    const int ring_slots = !fused ? 0 : use_v2 ? c->n_sm * 2 * c->plan2.G * 2 : c->n_sm * c->plan.Mc;
+    const int ring_slots = !fused ? 0 : use_v2w ? c->n_sm * 2 : use_v2 ? c->n_sm * 2 * c->plan2.G * 2 : c->n_sm * c->plan.Mc;
 
     c->stats = dcp_run_stats{};
     c->stats.kernel_used = use_res ? DCP_KERNEL_RESIDENT : use_sw ? DCP_KERNEL_STEPWISE : DCP_KERNEL_STREAMED;
@@ -972,20 +1009,21 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         dcp_launch_init(C, W, d_mcpar, check, s); ++n_launch;
         if (use_res) {
             ResPlan P = c->plan;
-            P.n_groups = (int)((Bn + P.Mc - 1) / P.Mc);
-            const int grid = std::min(c->n_sm, P.n_groups);
+            P.n_groups = use_v2w ? 0 : (int)((Bn + P.Mc - 1) / P.Mc);
+            const int grid = std::max(1, std::min(c->n_sm, P.n_groups));
             DevBuf dbg;
             if (getenv("DCP_RES_DEBUG")) { CUDA_TRY(dbg.reserve((size_t)grid * 20 * 8)); CUDA_TRY(cudaMemsetAsync(dbg.p, 0, (size_t)grid * 20 * 8, s)); P.dbg = (long long *)dbg.p; }
-            Res2Plan Q = c->plan2;
+            Res2Plan Q = use_v2w ? c->plan2w : c->plan2;
             int grid2 = 0;
             if (use_v2) {
-                const int Mv = Q.G * 2;                 // members per team group; two teams per CTA
+                const int Mv = Q.G * 2, teams = use_v2w ? 1 : 2;   // members per team group; teams per CTA
                 Q.n_groups = (int)((Bn + Mv - 1) / Mv);
-                grid2 = std::min(c->n_sm, (Q.n_groups + 1) / 2);
+                grid2 = std::min(c->n_sm, (Q.n_groups + teams - 1) / teams);
                 Q.dbg = P.dbg;
             }
             tm.mark(T_PHYS);
-            if (use_v2) CUDA_TRY(dcp_launch_physics_resident_v2(C, W, Q, aet, grid2, s));
+            if (use_v2w) CUDA_TRY(dcp_launch_physics_resident_v2w(C, W, Q, aet, grid2, s));
+            else if (use_v2) CUDA_TRY(dcp_launch_physics_resident_v2(C, W, Q, aet, grid2, s));
             else CUDA_TRY(dcp_launch_physics_resident(C, W, P, fast, aet, grid, s));
             ++n_launch; ++n_phys;
             if (P.dbg) {           // per-warp busy cycles of the persistent kernel (tuning aid)

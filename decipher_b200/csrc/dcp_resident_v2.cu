@@ -46,14 +46,34 @@
 
 #include <cstdint>
 
-#define R2_COLS DCP_RES_COMPUTE       // 512 unit columns per member slot
+// Two builds of this file (the second through dcp_resident_v2w.cu, which defines R2_WIDE and includes it):
+//   narrow  2 teams x (4 compute + 2 river warps), 512 unit columns per member slot   -- catchments of up to 512 HRUs
+//   WIDE    1 team  x (8 compute + 4 river warps), 1024 unit columns per member slot  -- 513 .. 1024 HRUs
+// Same thread count, register split and code; the wide build trims the per-column tables to fit 1024 columns in shared
+// memory: 1/ac is folded into the gather weights, q0 = exp(t0dt) * exp(-st) is rebuilt from a per-member and a per-column
+// factor instead of being stored per unit, and the column words shrink from three to two (+ the exp(-st) factor).
+#ifndef R2_WIDE
+#define R2_WIDE 0
+#endif
+#if R2_WIDE
+#define R2_TEAMS 1
+#define R2_KERNEL k_physics_resident_v2w
+#define R2_LAUNCH dcp_launch_physics_resident_v2w
+#else
 #define R2_TEAMS 2
-#define R2_TC 128                     // compute threads per team (4 columns each)
-#define R2_TR 64                      // river threads per team: contribution sums, routing convolution and objective terms of every
-                                      // step, one step behind the compute warps; lane 0 also drives the forcing TMA
+#define R2_KERNEL k_physics_resident_v2
+#define R2_LAUNCH dcp_launch_physics_resident_v2
+#endif
+#define R2_TC (256 / R2_TEAMS)        // compute threads per team (4 columns each)
+#define R2_COLS (4 * R2_TC)           // unit columns per member slot: 512 / 1024
+#define R2_TR (128 / R2_TEAMS)        // river threads per team: contribution sums one step behind the compute warps; lane 0 also
+                                      // drives the forcing TMA
 #define R2_TT (R2_TC + R2_TR)         // threads at a team's per-step barrier
 #define R2_CT (R2_TEAMS * R2_TC)      // 256 compute threads
 #define R2_THREADS (R2_TEAMS * (R2_TC + R2_TR)) // 384
+#define R2_TUPB (R2_COLS * 16)        // bytes of one time buffer of tuples (8 / 16 KB): the buffers are aligned to it
+#define R2_PARW (3 + R2_WIDE)         // 16-byte words per (member, layer) in par_s
+#define R2_COLW (3 - R2_WIDE)         // 16-byte words per column in cold_s
 #ifndef R2_REG_COMPUTE
 #define R2_REG_COMPUTE 240            // setmaxnreg (a) moves registers inside the CTA's LAUNCH allocation (384 x 168) only -- a request
                                       // beyond that pool blocks forever -- and (b) must be the SAME instruction for the four warps of a
@@ -102,6 +122,8 @@ struct R2Smem {                       // team-private views unless noted
     double *ellw_s;       // [ell_len]       packed gather list (weight | source tuple index)
     int4 *coli_s;         // [4][128]        per (column slot j, team thread): packed indices
     double2 *cold_s;      // [3][4][128]     word 0: {ac, 1/ac}, 1: {cq, cos(mslp)}, 2: {1/cos(mslp), -}; thread-fastest
+                          //                 WIDE: [2][4][256] word 0: {ac, cq}, 1: {cos(mslp), 1/cos(mslp)}
+    double *eq0_s;        // WIDE: [4][256]  exp(-st) of the column (q0 = exp(t0dt) * exp(-st), dyna_init_satzone.f90:108)
     int32_t *rbeg_s;      // [nriv+1]
 };
 
@@ -110,7 +132,11 @@ struct R2Smem {                       // team-private views unless noted
 // instead of mask + add + scale.  volatile: ordered against the team barrier (also a volatile asm).
 __device__ __forceinline__ double2 lds_tuple(int lo, uint32_t buf_u32) {
     uint32_t a;
-    asm("lop3.b32 %0, %1, 0x1ff0, %2, 0xEA;" : "=r"(a) : "r"(lo), "r"(buf_u32));
+#if R2_WIDE        // no alignment slack beside 1024 columns: mask + add (the add folds into the load's register + uniform-register address)
+    a = ((uint32_t)lo & (uint32_t)(R2_TUPB - 16)) + buf_u32;
+#else
+    asm("lop3.b32 %0, %1, %3, %2, 0xEA;" : "=r"(a) : "r"(lo), "r"(buf_u32), "n"(R2_TUPB - 16));
+#endif
     double2 v;
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
     return v;
@@ -129,12 +155,23 @@ __device__ __forceinline__ double2 lds_d2(uint32_t a) {
     asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
     return v;
 }
-static __device__ __noinline__ R2Fix r2_fix_unit(uint32_t cst_a, uint32_t par_a, uint32_t cold_a, double dtt, double inv_dtt,
+static __device__ __noinline__ R2Fix r2_fix_unit(uint32_t cst_a, uint32_t par_a, uint32_t cold_a, uint32_t eq0_a, double dtt, double inv_dtt,
                                                  int ntt, double qin, double uz, double exus, double sd0) {
-    const double2 c0v = lds_d2(cst_a);                                   // {q0, q2}
     const double2 p1 = lds_d2(par_a + 16), p2 = lds_d2(par_a + 32);      // {td/dt, smax}, {szm, dtt/szm}
+#if R2_WIDE
+    const double2 w0 = lds_d2(cold_a), w1 = lds_d2(cold_a + R2_H * R2_TC * 16);          // {ac, cq}, {cos, 1/cos}
+    double q2v, e0;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(q2v) : "r"(cst_a));
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(e0) : "r"(eq0_a));
+    const double2 c0v = make_double2(lds_d2(par_a + 48).x * e0, q2v);                      // {q0, q2}
+    const double2 d0 = make_double2(w0.x, 1.0), d1 = make_double2(w0.y, w1.x);            // 1/ac sits in the gather weights
+    const double icos = w1.y;
+#else
+    (void)eq0_a;
+    const double2 c0v = lds_d2(cst_a);                                   // {q0, q2}
     const double2 d0 = lds_d2(cold_a), d1 = lds_d2(cold_a + R2_H * R2_TC * 16);
     const double icos = lds_d2(cold_a + 2 * R2_H * R2_TC * 16).x;
+#endif
     HruConst c;
     c.ac = d0.x; c.inv_ac = d0.y;
     c.q0 = c0v.x; c.q2 = c0v.y; c.m2 = p2.x * icos; c.inv_m2 = (d1.y * p2.y) * inv_dtt;   // p2.y = dtt/szm
@@ -243,7 +280,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
     constexpr int H = R2_H, S = R2_S;
     const int B = W.B, npt = C.npt;
     const int forc_stride = P.Tt * (C.ngp + C.nge);
-    const int par_kstride = npt * 3;
+    const int par_kstride = npt * R2_PARW;
     const int ntiles = (C.nstep + P.Tt - 1) / P.Tt;
     const int Mv = P.G * S;                                  // members per team group
     uint32_t tiles_done = 0;
@@ -272,7 +309,8 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
             const int4 ci = M.coli_s[j * R2_TC + tt_id];
             const int tup = ci.z & 0xffff, g = (ci.y >> 16) & 0x7fff;
             const int ia = P.col_ia[j * R2_TC + tt_id];
-            const double cosm = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id].y;
+            const double2 cw1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];
+            const double cosm = R2_WIDE ? cw1.x : cw1.y;
             const int ipar = ia >= 0 ? C.hru[ia].ipar : 0;
 #pragma unroll
             for (int k = 0; k < S; ++k) {
@@ -292,7 +330,12 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #endif
                 reinterpret_cast<double *>(M.qbf_s + tup)[k] = qb0;                 // time buffer 0 = step 0's "old" qbf
                 reinterpret_cast<double *>(M.qbf_s + R2_COLS + tup)[k] = 0.0;
+#if R2_WIDE
+                reinterpret_cast<double *>(M.cst_s)[(k * H + j) * R2_TC + tt_id] = c_q2;   // q0 is rebuilt from exp(t0dt) and exp(-st)
+                (void)c_q0;
+#else
                 M.cst_s[(k * H + j) * R2_TC + tt_id] = make_double2(c_q0, c_q2);    // own-column table: [slot][column j][thread]
+#endif
             }
         }
         for (int i = tt_id; i < Mv * npt; i += R2_TC) {      // member parameters -> shared
@@ -305,9 +348,12 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                 td = W.par[(5 * npt + l) * (size_t)B + m];
                 smax = W.par[(6 * npt + l) * (size_t)B + m];
             }
-            M.par_s[i * 3 + 0] = make_double2(srmax, 1.0 / srmax);
-            M.par_s[i * 3 + 1] = make_double2(td / C.dt, smax);           // folded constants of hru_step_lean<., true>
-            M.par_s[i * 3 + 2] = make_double2(szm, C.dtt / szm);
+            M.par_s[i * R2_PARW + 0] = make_double2(srmax, 1.0 / srmax);
+            M.par_s[i * R2_PARW + 1] = make_double2(td / C.dt, smax);     // folded constants of hru_step_lean<., true>
+            M.par_s[i * R2_PARW + 2] = make_double2(szm, C.dtt / szm);
+#if R2_WIDE
+            M.par_s[i * R2_PARW + 3] = make_double2(m < B ? exp(W.t0dt[l * (size_t)B + m]) : 1.0, 0.0);   // exp(t0dt): q0 = exp(t0dt) * exp(-st)
+#endif
         }
         team_sync(team);
 
@@ -409,15 +455,29 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #pragma unroll
                     for (int jj = 0; jj < 2; ++jj) {
                         const int j = jp + jj;
+#if R2_WIDE
+                        const double2 w0 = M.cold_s[j * R2_TC + tt_id];      // {ac, cq}
+                        const double2 w1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];      // {cos, 1/cos}
+                        const double eq0 = M.eq0_s[j * R2_TC + tt_id];
+                        const double2 d0 = make_double2(w0.x, 1.0);          // 1/ac is folded into the gather weights
+                        const double2 d1 = make_double2(w0.y, w1.x);
+                        const double icos = w1.y;
+#else
                         const double2 d0 = M.cold_s[j * R2_TC + tt_id];      // {ac, 1/ac}
                         const double2 d1 = M.cold_s[R2_H * R2_TC + j * R2_TC + tt_id];      // {cq, cos}
                         const double icos = M.cold_s[2 * R2_H * R2_TC + j * R2_TC + tt_id].x;
+#endif
                         cq[jj] = d1.x;
                         const double p = forc_t[tt * C.ngp + (ci[j].y & 0xff)];
                         const double epp = forc_t[P.Tt * C.ngp + tt * C.nge + ((ci[j].y >> 8) & 0xff)];   // already max(ep, 0)
 #pragma unroll
                         for (int k = 0; k < S; ++k) {
+#if R2_WIDE
+                            const double2 c0v = make_double2(M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 3].x * eq0,
+                                                             reinterpret_cast<const double *>(M.cst_s)[(k * H + j) * R2_TC + tt_id]);
+#else
                             const double2 c0v = M.cst_s[(k * H + j) * R2_TC + tt_id];
+#endif
                             const double2 p0 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride];
                             const double2 p1 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 1];
                             const double2 p2 = M.par_s[(ONEPAR ? 0 : (ci[j].w & 0xffff)) + k * par_kstride + 2];
@@ -449,9 +509,10 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                                     const int j = jp + jj;
                                     // out of line (the loop body must stay small, see R2_GATHER_UNROLL): the unit's constants are
                                     // re-read from shared memory inside
-                                    const R2Fix f = r2_fix_unit(smem_u32(M.cst_s + (k * H + j) * R2_TC + tt_id),
+                                    const R2Fix f = r2_fix_unit(R2_WIDE ? smem_u32(reinterpret_cast<double *>(M.cst_s) + (k * H + j) * R2_TC + tt_id)
+                                                                        : smem_u32(M.cst_s + (k * H + j) * R2_TC + tt_id),
                                                                 smem_u32(M.par_s + (ci[j].w & 0xffff) + k * par_kstride),
-                                                                smem_u32(M.cold_s + j * R2_TC + tt_id), C.dtt, C.inv_dtt, C.ntt,
+                                                                smem_u32(M.cold_s + j * R2_TC + tt_id), smem_u32(M.eq0_s + j * R2_TC + tt_id), C.dtt, C.inv_dtt, C.ntt,
                                                                 qin[j][k], lo[jj][k].uz, lo[jj][k].exus, lo[jj][k].sd0);
                                     sd[j][k] = f.sd; lo[jj][k].qbf = f.qbf; lo[jj][k].exac = f.exac;
 #if R2_CARRY_E1
@@ -625,7 +686,7 @@ __device__ __forceinline__ void r2_river(const DevCatchment &C, const DevBatch &
 }
 
 template <bool AET, bool ONEPAR>
-__global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchment C, DevBatch W, Res2Plan P) {
+__global__ void __launch_bounds__(R2_THREADS, 1) R2_KERNEL(DevCatchment C, DevBatch W, Res2Plan P) {
     extern __shared__ __align__(128) unsigned char smem[];
     const int tid = threadIdx.x;
     // warps 0-3: team 0 compute, 4-7: team 1 compute, 8-9: team 0 river, 10-11: team 1 river
@@ -634,7 +695,7 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     R2Smem M;
     // team blocks start on an 8 KB boundary of the shared window (their first array is the tuple buffer pair, whose
     // 8 KB halves are addressed by OR-ing the tuple offset into the base: lds_tuple); the plan reserves the slack
-    const uint32_t pad = (8192u - ((smem_u32(smem) + (uint32_t)P.off_team) & 8191u)) & 8191u;
+    const uint32_t pad = R2_WIDE ? 0u : ((uint32_t)R2_TUPB - ((smem_u32(smem) + (uint32_t)P.off_team) & (R2_TUPB - 1u))) & (R2_TUPB - 1u);
     unsigned char *tb = smem + P.off_team + pad + (size_t)team * P.team_bytes;
     M.qbf_s = (double2 *)(tb + P.off_qbf);
     M.con_s = (double2 *)(tb + P.off_con);
@@ -647,13 +708,15 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
     M.ellw_s = (double *)(smem + P.off_ellw);
     M.coli_s = (int4 *)(smem + P.off_coli);
     M.cold_s = (double2 *)(smem + P.off_cold);
+    M.eq0_s = (double *)(smem + P.off_eq0);
     M.rbeg_s = (int32_t *)(smem + P.off_rbeg);
 
     for (int e = tid; e < P.ell_len; e += R2_THREADS) M.ellw_s[e] = P.ell_w[e];
     for (int i = tid; i < R2_H * R2_TC; i += R2_THREADS) {
         M.coli_s[i] = P.col_i[i];
     }
-    for (int i = tid; i < 3 * R2_H * R2_TC; i += R2_THREADS) M.cold_s[i] = P.col_d[i];
+    for (int i = tid; i < R2_COLW * R2_H * R2_TC; i += R2_THREADS) M.cold_s[i] = P.col_d[i];
+    if (R2_WIDE) for (int i = tid; i < R2_H * R2_TC; i += R2_THREADS) M.eq0_s[i] = P.eq0[i];
     for (int i = tid; i <= C.nriv; i += R2_THREADS) M.rbeg_s[i] = P.rbeg[i];
     if (!is_compute && (tid - R2_CT) % R2_TR == 0) {
         mbar_init(&M.bars[0], 1);
@@ -680,12 +743,12 @@ __global__ void __launch_bounds__(R2_THREADS, 1) k_physics_resident_v2(DevCatchm
 }
 #undef gc
 
-cudaError_t dcp_launch_physics_resident_v2(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, bool aet,
+cudaError_t R2_LAUNCH(const DevCatchment &C, const DevBatch &W, const Res2Plan &P, bool aet,
                                            int grid, cudaStream_t s) {
     const bool onepar = C.npt == 1 && P.G == 1;
     void (*k)(DevCatchment, DevBatch, Res2Plan) =
-        aet ? (onepar ? k_physics_resident_v2<true, true> : k_physics_resident_v2<true, false>)
-            : (onepar ? k_physics_resident_v2<false, true> : k_physics_resident_v2<false, false>);
+        aet ? (onepar ? R2_KERNEL<true, true> : R2_KERNEL<true, false>)
+            : (onepar ? R2_KERNEL<false, true> : R2_KERNEL<false, false>);
     cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, P.smem_bytes);
     if (e != cudaSuccess) return e;
     k<<<grid, R2_THREADS, P.smem_bytes, s>>>(C, W, P);

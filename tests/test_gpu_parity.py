@@ -145,6 +145,17 @@ def test_resident_matches_streamed_bitwise_in_exact_mode():
     assert np.array_equal(a["status"], b["status"])
 
 
+@pytest.mark.parametrize("nac,npt,M", [(513, 1, 9), (700, 1, 70), (1000, 1, 301), (1024, 1, 5), (600, 3, 40)])
+def test_resident_wide_kernel_513_to_1024_hrus(nac, npt, M):
+    """No cliff at 512 HRUs: catchments of 513 .. 1024 HRUs stay on chip (wide build of the second-generation kernel: one
+    team of 1024 columns per CTA, FAST policy), AUTO picks it, results within the 1e-9 contract of the oracle; ragged
+    member groups, one and several parameter layers, every column busy at nac = 1024."""
+    cat = synth.synth_catchment(nac=nac, nriv=3, npt=npt, ngp=4, nge=1, nstep=900, kW=8, seed=synth.BASE_SEED + 60 + nac, tree=(npt > 1))
+    ref, out = _run_both(cat, M, flags=OPT_FAST_MATH, kernel=0)
+    assert out["stats"]["kernel_used"] == KERNEL_RESIDENT and out["stats"]["n_physics_launches"] == 1
+    print(f"wide resident nac={nac}:", _check(ref, out))
+
+
 def test_wide_w_large_catchment_leaves_the_chip():
     """Config-4-like: more HRUs than the resident kernel holds (nac = 700 > 512) and a wide weighting
     matrix (64 targets per HRU): AUTO must pick the stepwise path (the streamed kernel when the balance

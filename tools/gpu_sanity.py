@@ -15,15 +15,18 @@ from parity import compare_flows, compare_perf                                  
 
 cases = [dict(nac=33, nriv=3, npt=2, ngp=2, nge=2, nstep=65, kW=3, seed=3, tree=True),
          dict(nac=500, nriv=3, npt=1, ngp=4, nge=1, nstep=700, kW=8, seed=synth.BASE_SEED + 2)]
-if len(sys.argv) > 1:
-    cases.append(dict(nac=int(sys.argv[1]), nriv=3, npt=1, ngp=4, nge=1, nstep=300, kW=8, seed=synth.BASE_SEED + 9))
+for a in sys.argv[1:]:
+    cases.append(dict(nac=int(a), nriv=3, npt=1, ngp=4, nge=1, nstep=300, kW=8, seed=synth.BASE_SEED + 9))
 for kw in cases:
     cat = synth.synth_catchment(**kw)
     M = 37 if kw["nac"] < 100 else 600
     mc = synth.sample_parameters(cat.npt, M)
     ref = oracle_run(cat, mc.copy(order="F"), n_threads=os.cpu_count() or 8)
     dev = DeviceCatchment(cat)
-    for name, kernel, flags in (("streamed", KERNEL_STREAMED, 0), ("resident exact", KERNEL_RESIDENT, 0), ("resident fast", KERNEL_RESIDENT, OPT_FAST_MATH)):
+    runs = (("streamed", KERNEL_STREAMED, 0), ("resident exact", KERNEL_RESIDENT, 0), ("resident fast", KERNEL_RESIDENT, OPT_FAST_MATH))
+    if kw["nac"] > 512:
+        runs = (("resident fast", KERNEL_RESIDENT, OPT_FAST_MATH),)
+    for name, kernel, flags in runs:
         t0 = time.time()
         out = dev.run(mc.copy(order="F"), flags=flags, kernel=kernel, want_q=True)
         d = compare_flows(out["q"], ref["q"]); p = compare_perf(out["perf"], ref["perf"])
