@@ -864,16 +864,54 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     // (results_ts / root_zone1 STOP conditions) exist in the streamed kernel only
     bool use_res = false, use_sw = false;
     const bool res_ok = c->plan.feasible || (fast && c->plan2w.feasible);     // 513 .. 1024 HRUs: the wide kernel, FAST policy
+    // The balance STOP conditions (results_ts, root_zone1) are statements about the reference's own rounding: they are
+    // evaluated by the streamed kernel in the EXACT policy.  AUTO runs checked ensembles there; an explicit resident /
+    // stepwise request keeps its kernel for every output and adds ONE streamed pass that only contributes the flag bits.
+    if (check && (o.kernel == DCP_KERNEL_RESIDENT || o.kernel == DCP_KERNEL_STEPWISE)) {
+        if (!status) return fail(DCP_ERR_INVALID, "DCP_OPT_CHECK_BALANCE without a status array");
+        const size_t nb = (size_t)C.npt * 7 * (size_t)n_member * 8;
+        dcp_run_opts om = o, oc = o;
+        om.flags &= ~DCP_OPT_CHECK_BALANCE;
+        oc.kernel = DCP_KERNEL_STREAMED;
+        oc.flags = (o.flags & DCP_OPT_DEVICE_BUFFERS) | DCP_OPT_CHECK_BALANCE;
+        const int32_t bits = DCP_ST_RZ_BALANCE | DCP_ST_TS_OUTSUM | DCP_ST_TS_WBAL;
+        int rc;
+        if (dev_io) {                           // the main pass clips srinit in place: the flag pass gets the caller's values
+            DevBuf tmp, st2;
+            CUDA_TRY(tmp.reserve(nb));
+            CUDA_TRY(st2.reserve((size_t)n_member * 4));
+            CUDA_TRY(cudaMemcpy(tmp.p, mcpar, nb, cudaMemcpyDeviceToDevice));
+            rc = dcp_run_ensemble(c, first_member, n_member, mcpar, &om, q_out, perf_out, reach_totals, init_diag, status);
+            if (rc != DCP_OK) return rc;
+            const dcp_run_stats main_stats = c->stats;
+            rc = dcp_run_ensemble(c, first_member, n_member, (double *)tmp.p, &oc, nullptr, nullptr, nullptr, nullptr, (int32_t *)st2.p);
+            if (rc != DCP_OK) return rc;
+            dcp_launch_or_status(status, (const int32_t *)st2.p, bits, n_member, c->stream);
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            const double ms_chk = c->stats.ms_total;
+            c->stats = main_stats; c->stats.ms_total += ms_chk; c->stats.n_launches += 1;
+        } else {
+            std::vector<double> tmp(mcpar, mcpar + nb / 8);
+            std::vector<int32_t> st2((size_t)n_member);
+            rc = dcp_run_ensemble(c, first_member, n_member, mcpar, &om, q_out, perf_out, reach_totals, init_diag, status);
+            if (rc != DCP_OK) return rc;
+            const dcp_run_stats main_stats = c->stats;
+            rc = dcp_run_ensemble(c, first_member, n_member, tmp.data(), &oc, nullptr, nullptr, nullptr, nullptr, st2.data());
+            if (rc != DCP_OK) return rc;
+            for (int64_t m = 0; m < n_member; ++m) status[m] |= st2[m] & bits;
+            const double ms_chk = c->stats.ms_total;
+            c->stats = main_stats; c->stats.ms_total += ms_chk;
+        }
+        return DCP_OK;
+    }
     if (o.kernel == DCP_KERNEL_RESIDENT) {
         if (!res_ok) return fail(DCP_ERR_UNSUPPORTED, "resident kernel unavailable: %s", c->plan_why.c_str());
-        if (check) return fail(DCP_ERR_UNSUPPORTED, "DCP_OPT_CHECK_BALANCE needs the streamed kernel");
         use_res = true;
     } else if (o.kernel == DCP_KERNEL_AUTO) {
         use_res = res_ok && !check;
         use_sw = !use_res && !check && c->dplan.feasible;      // catchments too large for the chip: one launch set per step
     } else if (o.kernel == DCP_KERNEL_STEPWISE) {
         if (!c->dplan.feasible) return fail(DCP_ERR_UNSUPPORTED, "stepwise kernels unavailable for this catchment");
-        if (check) return fail(DCP_ERR_UNSUPPORTED, "DCP_OPT_CHECK_BALANCE needs the streamed kernel");
         use_sw = true;
     } else if (o.kernel != DCP_KERNEL_STREAMED) {
         return fail(DCP_ERR_INVALID, "unknown kernel selector %d", o.kernel);

@@ -796,6 +796,14 @@ void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf,
     k_finalize<<<cdiv(W.B, 128), 128, 0, s>>>(C, W, perf, totals, diag, status);
 }
 
+__global__ void k_or_status(int32_t *__restrict__ status, const int32_t *__restrict__ extra, int32_t mask, int64_t n) {
+    const int64_t m = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    if (m < n) status[m] |= extra[m] & mask;
+}
+void dcp_launch_or_status(int32_t *status, const int32_t *extra, int32_t mask, int64_t n, cudaStream_t s) {
+    k_or_status<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(status, extra, mask, n);
+}
+
 void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s) {
     k_fp64_peak<<<blocks, 256, 0, s>>>(out, iters, 0.999999, 1e-9);
 }

@@ -26,6 +26,7 @@ void dcp_launch_route_prepare(const DevCatchment &C, const DevBatch &W, const do
 void dcp_launch_route_status(const DevCatchment &C, const DevBatch &W, int32_t *status, cudaStream_t s);
 void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,
                          int32_t *status, cudaStream_t s);
+void dcp_launch_or_status(int32_t *status, const int32_t *extra, int32_t mask, int64_t n, cudaStream_t s);
 void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s);
 cudaError_t dcp_launch_physics_resident(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast,
                                         bool aet, int grid, cudaStream_t s);

@@ -25,6 +25,7 @@
 #include "dcp_physics.cuh"
 
 #include <cstdint>
+#include <cstdlib>
 
 #define SW_THREADS 128
 
@@ -171,6 +172,109 @@ k_redistribute_dense(DensePlan D, const double *__restrict__ Bm, double *__restr
 }
 
 // ------------------------------------------------------------------------------------------------
+// (1c) dense redistribute on the FP64 tensor cores (FAST policy): the same 128 x 128 x 16 block tile and staging as (1b),
+// the inner product as mma.sync.m8n8k4.f64 (SASS DMMA).  8 warps as 2 (destinations) x 4 (members), warp tile 64 x 32 =
+// 8 x 4 MMA tiles, 32 accumulator pairs per lane.  Per k-step of 4 a warp issues 12 LDS.64 and 32 DMMA (8 192 FMAs) where
+// the vector kernel issues 32 LDS.128 and 256 DFMA: B200's FP64 tensor rate equals its DFMA rate, so the gain is issue
+// slots and operand bandwidth, not peak (A/B with ncu: profiles/r2_c4_dense_mma_vs_dfma.txt).
+// Shared tiles are k-major with a row stride of 136 doubles: the 4 k-rows x 8 consecutive columns of a fragment load then
+// fall into 32 distinct bank pairs (stride = 8 mod 16 doubles).
+// The accumulation order inside an MMA is the hardware's, so this kernel exists for the FAST policy only.
+// ------------------------------------------------------------------------------------------------
+#define GM_LD 136
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1)
+k_redistribute_dense_mma(DensePlan D, const double *__restrict__ Bm, double *__restrict__ Cm, int32_t *__restrict__ bad, int nac, int B) {
+    extern __shared__ __align__(16) double gsm[];
+    double *As = gsm;                                     // [2][BK][GM_LD]   (k-major: transposed W tile)
+    double *Bs = gsm + 2 * GM_BK * GM_LD;                 // [2][BK][GM_LD]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wm = (warp >> 2) * 64, wn = (warp & 3) * 32;        // warp tile origin inside the block tile
+    const int fr = lane >> 2, fk = lane & 3;                      // fragment row / k index of this lane
+    const int n0 = blockIdx.x * GM_BN, bm = D.bm_order[blockIdx.y], m0 = bm * GM_BM;
+    const int kt_b = D.kt_beg[bm], kt_e = D.kt_beg[bm + 1];
+    const int a_r = tid >> 1, a_k = (tid & 1) * 8;
+    const int b_k = tid >> 4, b_n = (tid & 15) * 8;
+    double ra[8], rb[8], rsc = 0.0;
+    auto gload = [&](int kt) {
+        const int k0 = D.kt_idx[kt] * GM_BK;
+        const double2 *ap = reinterpret_cast<const double2 *>(D.wd + (size_t)(m0 + a_r) * D.Kp + k0 + a_k);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { const double2 v = __ldg(ap + i); ra[2 * i] = v.x; ra[2 * i + 1] = v.y; }
+        const int k = k0 + b_k;
+        rsc = (k < nac) ? D.acs[k] : 0.0;
+        const double *bp = Bm + (size_t)k * B + n0 + b_n;
+        if (k < nac && n0 + b_n + 8 <= B && (B & 1) == 0) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { const double2 v = reinterpret_cast<const double2 *>(bp)[i]; rb[2 * i] = v.x; rb[2 * i + 1] = v.y; }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) rb[i] = (k < nac && n0 + b_n + i < B) ? bp[i] : 0.0;
+        }
+    };
+    auto sstore = [&](int buf) {
+        double *a = As + buf * GM_BK * GM_LD, *b = Bs + buf * GM_BK * GM_LD;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) a[(a_k + i) * GM_LD + a_r] = ra[i];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            if (!is_finite_bits(rb[i])) { bad[n0 + b_n + i] = 1; rb[i] = 0.0; }
+            rb[i] = rb[i] * rsc;                          // ac(src) folded into the staged tile
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) reinterpret_cast<double2 *>(b + b_k * GM_LD + b_n)[i] = make_double2(rb[2 * i], rb[2 * i + 1]);
+    };
+
+    double acc[8][4][2];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { acc[i][j][0] = 0.0; acc[i][j][1] = 0.0; }
+
+    if (kt_b < kt_e) {
+        gload(kt_b);
+        sstore(0);
+        __syncthreads();
+        for (int kt = kt_b; kt < kt_e; ++kt) {
+            const int buf = (kt - kt_b) & 1;
+            if (kt + 1 < kt_e) gload(kt + 1);
+            const double *a = As + buf * GM_BK * GM_LD + wm + fr;
+            const double *b = Bs + buf * GM_BK * GM_LD + wn + fr;
+#pragma unroll
+            for (int k4 = 0; k4 < GM_BK; k4 += 4) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) af[i] = a[(k4 + fk) * GM_LD + i * 8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = b[(k4 + fk) * GM_LD + j * 8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            if (kt + 1 < kt_e) sstore(buf ^ 1);
+            __syncthreads();
+        }
+    }
+    // C fragment: row = lane / 4, columns 2 * (lane % 4) + {0, 1} of each 8 x 8 tile
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = m0 + wm + i * 8 + fr;
+        if (r >= nac) continue;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int n = n0 + wn + j * 8 + 2 * fk;
+            double *cp = Cm + (size_t)r * B + n;
+            if (n + 1 < B && (B & 1) == 0) *reinterpret_cast<double2 *>(cp) = make_double2(acc[i][j][0], acc[i][j][1]);
+            else { if (n < B) cp[0] = acc[i][j][0]; if (n + 1 < B) cp[1] = acc[i][j][1]; }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
 // (2) one timestep of every (HRU, member): thread = member, blockIdx.y = HRU chunk
 // ------------------------------------------------------------------------------------------------
 template <bool FAST, bool AET, bool NPT1>
@@ -293,10 +397,18 @@ cudaError_t dcp_launch_physics_stepwise(const DevCatchment &C, const DevBatch &W
         if (e != cudaSuccess) return e;
     }
     const dim3 g_gemm((W.B + GM_BN - 1) / GM_BN, D.Mp / GM_BM);
+    // FAST policy: the tensor-core contraction unless DCP_DENSE_MMA=0 asks for the vector kernel (A/B runs)
+    const size_t gsm_mma = (size_t)(4 * GM_BK * GM_LD) * sizeof(double);
+    const bool use_mma = dense && fast && !(getenv("DCP_DENSE_MMA") && atoi(getenv("DCP_DENSE_MMA")) == 0);
+    if (use_mma) {
+        cudaError_t e = cudaFuncSetAttribute(k_redistribute_dense_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm_mma);
+        if (e != cudaSuccess) return e;
+    }
     for (int t = t0; t < t1; ++t) {
         const double *qbf_old = (t & 1) ? W.qbf1 : W.qbf0;
         if (dense) {
-            if (fast) k_redistribute_dense<false><<<g_gemm, GM_THREADS, gsm, s>>>(D, qbf_old, W.qin_ext, W.bad_src, C.nac, W.B);
+            if (use_mma) k_redistribute_dense_mma<<<g_gemm, GM_THREADS, gsm_mma, s>>>(D, qbf_old, W.qin_ext, W.bad_src, C.nac, W.B);
+            else if (fast) k_redistribute_dense<false><<<g_gemm, GM_THREADS, gsm, s>>>(D, qbf_old, W.qin_ext, W.bad_src, C.nac, W.B);
             else k_redistribute_dense<true><<<g_gemm, GM_THREADS, gsm, s>>>(D, qbf_old, W.qin_ext, W.bad_src, C.nac, W.B);
             k_redistribute_csr<true><<<g_phys, SW_THREADS, 0, s>>>(C, W, qbf_old, rows);      // members flagged non-finite only
         } else {

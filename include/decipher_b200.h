@@ -59,7 +59,11 @@ extern "C" {
 #define DCP_INIT_MAX_ITER     20000     /* cap on the while loop of dyna_init_satzone.f90:134-174     */
 
 /* ---- run option flags -------------------------------------------------------------------- */
-#define DCP_OPT_CHECK_BALANCE   0x1     /* evaluate the results_ts / root_zone1 STOP conditions       */
+#define DCP_OPT_CHECK_BALANCE   0x1     /* evaluate the results_ts / root_zone1 STOP conditions: they are statements
+                                           about the reference's own rounding, so the streamed kernel evaluates them
+                                           in the reference's arithmetic -- DCP_KERNEL_AUTO runs the whole ensemble
+                                           there, an explicit DCP_KERNEL_RESIDENT / _STEPWISE request keeps its kernel
+                                           for every output and adds one streamed pass that contributes the flag bits */
 #define DCP_OPT_DEVICE_BUFFERS  0x2     /* mcpar / outputs are DEVICE pointers (no H2D/D2H copies)    */
 #define DCP_OPT_FAST_MATH       0x4     /* reciprocal-hoisted arithmetic (<=1e-9 rel.; default is the
                                            reference's operation order with IEEE division)            */

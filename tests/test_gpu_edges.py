@@ -79,8 +79,6 @@ def test_invalid_descriptors_are_rejected():
     mc[0, 4, 1] = -5.0                                   # negative channel velocity
     with pytest.raises(DecipherError):
         dev.run(mc)
-    with pytest.raises(DecipherError):
-        dev.run(synth.sample_parameters(cat.npt, 2), flags=OPT_CHECK_BALANCE, kernel=KERNEL_RESIDENT)
     dev.close()
 
 
@@ -131,6 +129,14 @@ def test_balance_stop_conditions_raise_the_oracles_flags(depth):
     dev.close()
     assert out["stats"]["kernel_used"] == KERNEL_STREAMED          # AUTO routes checked runs to the kernel that has the checks
     assert np.array_equal(out["status"], ref["status"]), (out["status"] & bits, ref["status"] & bits)
+    # an explicit resident request (either policy) keeps its kernel for the outputs and still reports the reference's flags
+    dev = DeviceCatchment(cat)
+    for fl in (0, OPT_FAST_MATH):
+        res = dev.run(mc.copy(order="F"), flags=OPT_CHECK_BALANCE | fl, kernel=KERNEL_RESIDENT, want_q=True)
+        assert res["stats"]["kernel_used"] == KERNEL_RESIDENT
+        assert np.array_equal(res["status"] & bits, ref["status"] & bits) and np.array_equal(res["mcpar"], ref["mcpar"])
+        compare_flows(res["q"], ref["q"])
+    dev.close()
     assert not (plain["status"] & bits).any()                        # the checks are opt-in; flows are the same either way
     assert np.array_equal(out["q"], plain["q"], equal_nan=True)
     compare_flows(out["q"], ref["q"])

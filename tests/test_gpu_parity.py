@@ -4,7 +4,7 @@ import numpy as np
 import pytest
 
 from decipher_b200 import synth
-from decipher_b200.capi import (DeviceCatchment, KERNEL_STREAMED, NMEASURE, OPT_CHECK_BALANCE, OPT_FAST_MATH)
+from decipher_b200.capi import (DeviceCatchment, KERNEL_RESIDENT, KERNEL_STREAMED, NMEASURE, OPT_CHECK_BALANCE, OPT_FAST_MATH)
 from oracle_binding import oracle_run
 from parity import compare_close, compare_flows, compare_perf
 
@@ -88,7 +88,9 @@ def test_device_buffers_and_stats():
     perf = t_perf.cpu().numpy().transpose(2, 1, 0)
     compare_perf(perf, ref["perf"])
     assert np.array_equal(t_status.cpu().numpy(), ref["status"])
-    assert st["n_launches"] >= 5 and st["ms_total"] > 0 and st["ms_h2d"] < st["ms_total"]
+    # AUTO -> resident kernel: slowest-velocity reduction, init, the persistent time loop (routing + objective inside), finalize
+    assert st["kernel_used"] == KERNEL_RESIDENT and st["n_launches"] == 4 and st["n_physics_launches"] == 1
+    assert st["ms_total"] > 0 and st["ms_h2d"] < st["ms_total"]
     dev.close()
 
 
@@ -247,3 +249,22 @@ def test_stepwise_nonfinite_members_match_streamed(monkeypatch):
         print("non-finite members:", int(bad.sum()), "of 40")
         assert bad[3] and bad[21] and (inf_rain or bad.sum() == 2)
         _bitwise(a, b)
+
+
+@pytest.mark.parametrize("kw,nstep,M", [("64", 150, 6), ("512", 60, 6), ("dense", 16, 5)])
+def test_config4_full_size_5000_hrus(kw, nstep, M):
+    """BASELINE config 4 at its stated size: 5 000 HRUs, kW = 64 / 512 targets per HRU or a dense weighting matrix (every
+    HRU drains to every down-slope HRU: 12.5 M non-zeros).  AUTO runs it on the stepwise path (sparse CSR SpMM, or the
+    FP64 GEMM over the non-empty tiles when W is dense enough); both policies against the oracle."""
+    cfg = dict(synth.CONFIGS["C4"]); cfg.pop("members")
+    cfg.update(nstep=nstep)
+    if kw == "dense":
+        cfg.update(dense_w=True)
+    else:
+        cfg.update(kW=int(kw))
+    cat = synth.synth_catchment(**cfg)
+    assert cat.nac == 5000
+    for flags in (OPT_FAST_MATH, 0):
+        ref, out = _run_both(cat, M, flags=flags, kernel=0)
+        assert out["stats"]["kernel_used"] == KERNEL_STEPWISE
+        print(f"C4 nac=5000 kW={kw} flags={flags}:", _check(ref, out))
