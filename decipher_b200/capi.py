@@ -33,6 +33,11 @@ ST_HIST_DROPPED = 0x80
 OPT_CHECK_BALANCE = 0x1
 OPT_DEVICE_BUFFERS = 0x2
 OPT_FAST_MATH = 0x4
+OPT_SIGNATURES = 0x8
+NSIG = 4
+SIG_Q5, SIG_Q50, SIG_Q95, SIG_SLOPE = range(4)
+FDC_OCTAVE_LO, FDC_OCTAVES = -40, 48
+FDC_BINS = 8 * FDC_OCTAVES + 2
 KERNEL_AUTO, KERNEL_STREAMED, KERNEL_RESIDENT, KERNEL_STEPWISE = 0, 1, 2, 3
 NMEASURE = 5
 PERF_NSE, PERF_LOGNSE, PERF_KGE, PERF_PBIAS, PERF_RMSE = range(5)
@@ -62,7 +67,7 @@ class CatchmentDesc(C.Structure):
 class RunOpts(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("flags", C.c_int32), ("kernel", C.c_int32),
                 ("members_per_batch", C.c_int32), ("steps_per_tile", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("reserved", C.c_int32), ("sig_out", C.c_void_p)]
 
 
 class RunStats(C.Structure):
@@ -199,6 +204,9 @@ def load_library(path: str = LIB_PATH):
     lib.dcp_get_run_stats.argtypes = [C.c_void_p, C.POINTER(RunStats)]
     lib.dcp_route_timeseries.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32]
     lib.dcp_measure_fp64_peak.argtypes = [c_double_p, c_double_p]
+    if hasattr(lib, "dcp_select_behavioural"):
+        lib.dcp_select_behavioural.argtypes = [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_int32,
+                                               C.c_void_p, C.c_void_p, C.POINTER(C.c_int64), C.c_int32]
     if not hasattr(lib, "dcp_comm_init"):        # a kernel-tuning build of an older ABI (DCP_B200_LIB): single-GPU entry points only
         _lib = lib
         return lib
@@ -253,7 +261,7 @@ class DeviceCatchment:
             pass
 
     def run(self, mcpar: np.ndarray, *, flags=0, kernel=KERNEL_AUTO, want_q=False, want_perf=True,
-            want_totals=False, members_per_batch=0, steps_per_tile=0, first_member=1):
+            want_totals=False, want_sig=False, members_per_batch=0, steps_per_tile=0, first_member=1):
         """mcpar: (npt, 7, M) Fortran-ordered float64 host array (modified in place: srinit clip).
         Returns a dict of host arrays."""
         cat = self.cat
@@ -265,14 +273,17 @@ class DeviceCatchment:
         tot = np.empty((3, cat.nriv, M), order="F") if want_totals else None
         diag = np.empty((3, M), order="F")
         status = np.zeros(M, dtype=np.int32)
-        opts = make_opts(flags, kernel, members_per_batch, steps_per_tile)
+        sig = np.empty((NSIG, cat.nriv, M), order="F") if want_sig else None
+        opts = make_opts(flags | (OPT_SIGNATURES if want_sig else 0), kernel, members_per_batch, steps_per_tile)
+        if want_sig:
+            opts.sig_out = sig.ctypes.data_as(C.c_void_p)
 
         def p(a):
             return a.ctypes.data_as(C.c_void_p) if a is not None else None
         rc = self.lib.dcp_run_ensemble(self._h, int(first_member), int(M), p(mcpar), C.byref(opts),
                                        p(q), p(perf), p(tot), p(diag), p(status))
         _check(self.lib, rc, "dcp_run_ensemble")
-        out.update(q=q, perf=perf, reach_totals=tot, init_diag=diag, status=status, mcpar=mcpar)
+        out.update(q=q, perf=perf, reach_totals=tot, init_diag=diag, status=status, mcpar=mcpar, sig=sig)
         out["stats"] = self.stats()
         return out
 
@@ -367,6 +378,22 @@ class Communicator:
             self.close()
         except Exception:
             pass
+
+
+def select_behavioural(perf: np.ndarray, measure: int, threshold: float, gauge: int = -1, higher_is_better: bool = True):
+    """GLUE-style behavioural filter on the device (dcp_select_behavioural): perf (NMEASURE, nriv, M) Fortran-ordered host array.
+    Returns (member indexes ascending, normalised likelihood weights)."""
+    lib = load_library()
+    assert perf.dtype == np.float64 and perf.flags.f_contiguous and perf.shape[0] == NMEASURE
+    nriv, M = perf.shape[1], perf.shape[2]
+    idx = np.empty(M, dtype=np.int64)
+    wgt = np.empty(M, dtype=np.float64)
+    n = C.c_int64()
+    rc = lib.dcp_select_behavioural(perf.ctypes.data_as(C.c_void_p), M, nriv, int(measure), int(gauge), float(threshold),
+                                    int(bool(higher_is_better)), idx.ctypes.data_as(C.c_void_p), wgt.ctypes.data_as(C.c_void_p),
+                                    C.byref(n), 0)
+    _check(lib, rc, "dcp_select_behavioural")
+    return idx[:n.value].copy(), wgt[:n.value].copy()
 
 
 def measure_fp64_peak():

@@ -775,7 +775,8 @@ struct Carver {                     // carves a slab into aligned arrays
 // lays the batch workspace out (base == nullptr: size query only)
 // ring_slots > 0: fused routing (dcp_route_fused.cuh) -- qout / y are rings of R steps per member IN FLIGHT, and the
 // per-step objective series do not exist
-size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, bool aet, int stepwise_nq = -1, int ring_slots = 0) {
+size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, bool aet, int stepwise_nq = -1, int ring_slots = 0,
+                   bool want_sig = false) {
     Carver cv(base);
     const size_t B = W.B, nac = C.nac;
     W.par = cv.take<double>(7 * C.npt * B);
@@ -805,6 +806,7 @@ size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, b
     W.sse = cv.take<double>(C.nriv * B); W.lsse = cv.take<double>(C.nriv * B);
     W.sq = cv.take<double>(C.nriv * B); W.sqq = cv.take<double>(C.nriv * B); W.sqo = cv.take<double>(C.nriv * B);
     W.bad = cv.take<int32_t>(C.nriv * B);
+    W.fdc = want_sig ? cv.take<uint32_t>((size_t)DCP_FDC_BINS * C.nriv * B) : nullptr;
     W.status = cv.take<int32_t>(B);
     W.diag = cv.take<double>(3 * B);
     if (stepwise_nq >= 0) {
@@ -860,6 +862,8 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
     const bool fast = (o.flags & DCP_OPT_FAST_MATH) != 0;
     const bool aet = reach_totals != nullptr;
     const bool want_perf = perf_out != nullptr;
+    const bool want_sig = (o.flags & DCP_OPT_SIGNATURES) != 0;
+    if (want_sig && !o.sig_out) return fail(DCP_ERR_INVALID, "DCP_OPT_SIGNATURES without dcp_run_opts.sig_out");
     // kernel choice: the resident kernel whenever the catchment fits on chip; the balance checks
     // (results_ts / root_zone1 STOP conditions) exist in the streamed kernel only
     bool use_res = false, use_sw = false;
@@ -874,6 +878,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         om.flags &= ~DCP_OPT_CHECK_BALANCE;
         oc.kernel = DCP_KERNEL_STREAMED;
         oc.flags = (o.flags & DCP_OPT_DEVICE_BUFFERS) | DCP_OPT_CHECK_BALANCE;
+        oc.sig_out = nullptr;
         const int32_t bits = DCP_ST_RZ_BALANCE | DCP_ST_TS_OUTSUM | DCP_ST_TS_WBAL;
         int rc;
         if (dev_io) {                           // the main pass clips srinit in place: the flag pass gets the caller's values
@@ -954,6 +959,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             b += par_per_member * B * 8 + 256;
             if (q_out) b += (size_t)C.nriv * C.nstep * B * 8 + 256;
             if (want_perf) b += (size_t)DCP_NMEASURE * C.nriv * B * 8 + 256;
+            if (want_sig) b += (size_t)DCP_NSIG * C.nriv * B * 8 + 256;
             if (reach_totals) b += (size_t)3 * C.nriv * B * 8 + 256;
             if (init_diag) b += (size_t)3 * B * 8 + 256;
             if (status) b += (size_t)B * 4 + 256;
@@ -971,7 +977,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         // ---- first guess of the batch size: everything except the (still unknown) histogram length ----
         for (;;) {
             DevBatch Wq{}; Wq.B = (int)Bn; Wq.Lcap = 1; Wq.R = fused ? 512 : use_res ? C.nstep : tile + 64;
-            const size_t fixed = carve_batch(nullptr, C, Wq, check, aet, sw_nq, ring_slots) + io_size(Bn);
+            const size_t fixed = carve_batch(nullptr, C, Wq, check, aet, sw_nq, ring_slots, want_sig) + io_size(Bn);
             if ((double)fixed < 0.9 * mem_budget || Bn <= 1) break;
             Bn = shrink(Bn);
         }
@@ -979,12 +985,13 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
         CUDA_TRY(c->io.reserve(io_bytes));
         tm.mark(T_H2D);
         Carver iocv(c->io.p);
-        double *d_mcpar = nullptr, *d_q = nullptr, *d_perf = nullptr, *d_tot = nullptr, *d_diag = nullptr;
+        double *d_mcpar = nullptr, *d_q = nullptr, *d_perf = nullptr, *d_tot = nullptr, *d_diag = nullptr, *d_sig = nullptr;
         int32_t *d_status = nullptr;
         if (dev_io) {
             d_mcpar = mcpar + m0 * par_per_member;
             d_q = q_out ? q_out + (size_t)m0 * C.nriv * C.nstep : nullptr;
             d_perf = perf_out ? perf_out + (size_t)m0 * DCP_NMEASURE * C.nriv : nullptr;
+            d_sig = want_sig ? o.sig_out + (size_t)m0 * DCP_NSIG * C.nriv : nullptr;
             d_tot = reach_totals ? reach_totals + (size_t)m0 * 3 * C.nriv : nullptr;
             d_diag = init_diag ? init_diag + (size_t)m0 * 3 : nullptr;
             d_status = status ? status + m0 : nullptr;
@@ -992,6 +999,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             d_mcpar = iocv.take<double>(par_per_member * Bn);
             if (q_out) d_q = iocv.take<double>((size_t)C.nriv * C.nstep * Bn);
             if (want_perf) d_perf = iocv.take<double>((size_t)DCP_NMEASURE * C.nriv * Bn);
+            if (want_sig) d_sig = iocv.take<double>((size_t)DCP_NSIG * C.nriv * Bn);
             if (reach_totals) d_tot = iocv.take<double>((size_t)3 * C.nriv * Bn);
             if (init_diag) d_diag = iocv.take<double>((size_t)3 * Bn);
             if (status) d_status = iocv.take<int32_t>(Bn);
@@ -1031,7 +1039,7 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             while (R < tile + Tcap + 1) R <<= 1;
             W.R = R; W.Rmask = R - 1;
         }
-        const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet, sw_nq, ring_slots);
+        const size_t ws_bytes = carve_batch(nullptr, C, W, check, aet, sw_nq, ring_slots, want_sig);
         if ((double)(ws_bytes + io_bytes) > mem_budget) {
             if (Bn <= 1) return fail(DCP_ERR_NOMEM, "one member needs %zu MB, device has %zu MB free",
                                      (ws_bytes + io_bytes) >> 20, free_b >> 20);
@@ -1039,7 +1047,8 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             continue;
         }
         CUDA_TRY(c->ws.reserve(ws_bytes));
-        carve_batch(c->ws.p, C, W, check, aet, sw_nq, ring_slots);
+        carve_batch(c->ws.p, C, W, check, aet, sw_nq, ring_slots, want_sig);
+        if (want_sig) CUDA_TRY(cudaMemsetAsync(W.fdc, 0, (size_t)DCP_FDC_BINS * C.nriv * Bn * 4, s));
         W.q_user = fused ? d_q : nullptr;
         if (use_sw) CUDA_TRY(cudaMemsetAsync(W.bad_src, 0, (size_t)Bn * 4, s));
 
@@ -1090,12 +1099,13 @@ int dcp_run_ensemble(dcp_catchment *c, int64_t first_member, int64_t n_member, d
             }
         }
         tm.mark(T_FIN);
-        dcp_launch_finalize(C, W, d_perf, d_tot, d_diag, d_status, s); ++n_launch;
+        dcp_launch_finalize(C, W, d_perf, d_tot, d_diag, d_status, d_sig, s); ++n_launch;
         tm.mark(T_D2H);
         if (!dev_io) {
             CUDA_TRY(cudaMemcpyAsync(mcpar + m0 * par_per_member, d_mcpar, par_per_member * Bn * 8, cudaMemcpyDeviceToHost, s));
             if (q_out) CUDA_TRY(cudaMemcpyAsync(q_out + (size_t)m0 * C.nriv * C.nstep, d_q, (size_t)C.nriv * C.nstep * Bn * 8, cudaMemcpyDeviceToHost, s));
             if (want_perf) CUDA_TRY(cudaMemcpyAsync(perf_out + (size_t)m0 * DCP_NMEASURE * C.nriv, d_perf, (size_t)DCP_NMEASURE * C.nriv * Bn * 8, cudaMemcpyDeviceToHost, s));
+            if (want_sig) CUDA_TRY(cudaMemcpyAsync(o.sig_out + (size_t)m0 * DCP_NSIG * C.nriv, d_sig, (size_t)DCP_NSIG * C.nriv * Bn * 8, cudaMemcpyDeviceToHost, s));
             if (reach_totals) CUDA_TRY(cudaMemcpyAsync(reach_totals + (size_t)m0 * 3 * C.nriv, d_tot, (size_t)3 * C.nriv * Bn * 8, cudaMemcpyDeviceToHost, s));
             if (init_diag) CUDA_TRY(cudaMemcpyAsync(init_diag + (size_t)m0 * 3, d_diag, (size_t)3 * Bn * 8, cudaMemcpyDeviceToHost, s));
             if (status) CUDA_TRY(cudaMemcpyAsync(status + m0, d_status, (size_t)Bn * 4, cudaMemcpyDeviceToHost, s));
@@ -1224,6 +1234,47 @@ int dcp_route_timeseries(dcp_catchment *c, int64_t n_series, const double *veloc
     c->stats.ms_d2h = sums[T_D2H];
     c->stats.n_launches = n_launch;
     c->stats.hist_len = hist_len_max;
+    return DCP_OK;
+}
+
+int dcp_select_behavioural(const double *perf, int64_t n_member, int32_t nriv, int32_t measure, int32_t gauge, double threshold,
+                           int32_t higher_is_better, int64_t *index_out, double *weight_out, int64_t *n_selected, int32_t flags) {
+    if (!perf || !index_out || !n_selected) return fail(DCP_ERR_INVALID, "dcp_select_behavioural: null argument");
+    if (n_member < 1 || nriv < 1 || measure < 0 || measure >= DCP_NMEASURE || gauge < -1 || gauge >= nriv)
+        return fail(DCP_ERR_INVALID, "dcp_select_behavioural: bad n_member / nriv / measure / gauge");
+    if (flags & ~DCP_OPT_DEVICE_BUFFERS) return fail(DCP_ERR_INVALID, "dcp_select_behavioural takes DCP_OPT_DEVICE_BUFFERS only");
+    if (dcp_device_count() < 1) return fail(DCP_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    const size_t pb = (size_t)DCP_NMEASURE * nriv * (size_t)n_member * 8;
+    const int nblk = dcp_select_blocks(n_member);
+    DevBuf d_perf, d_cnt, d_off, d_idx, d_dist;
+    const double *dp = perf;
+    if (!(flags & DCP_OPT_DEVICE_BUFFERS)) {
+        CUDA_TRY(d_perf.reserve(pb));
+        CUDA_TRY(cudaMemcpy(d_perf.p, perf, pb, cudaMemcpyHostToDevice));
+        dp = (const double *)d_perf.p;
+    }
+    CUDA_TRY(d_cnt.reserve((size_t)nblk * 4));
+    CUDA_TRY(d_off.reserve((size_t)nblk * 8));
+    CUDA_TRY(d_idx.reserve((size_t)n_member * 8));
+    CUDA_TRY(d_dist.reserve((size_t)n_member * 8));
+    dcp_launch_select_count(dp, n_member, nriv, measure, gauge, threshold, higher_is_better, (int32_t *)d_cnt.p, 0);
+    std::vector<int32_t> cnt(nblk);
+    CUDA_TRY(cudaMemcpy(cnt.data(), d_cnt.p, (size_t)nblk * 4, cudaMemcpyDeviceToHost));
+    std::vector<int64_t> off(nblk);
+    int64_t total = 0;
+    for (int b = 0; b < nblk; ++b) { off[b] = total; total += cnt[b]; }
+    CUDA_TRY(cudaMemcpy(d_off.p, off.data(), (size_t)nblk * 8, cudaMemcpyHostToDevice));
+    dcp_launch_select_scatter(dp, n_member, nriv, measure, gauge, threshold, higher_is_better, (const int64_t *)d_off.p,
+                              (int64_t *)d_idx.p, (double *)d_dist.p, 0);
+    CUDA_TRY(cudaGetLastError());
+    if (total > 0) CUDA_TRY(cudaMemcpy(index_out, d_idx.p, (size_t)total * 8, cudaMemcpyDeviceToHost));
+    if (weight_out && total > 0) {
+        CUDA_TRY(cudaMemcpy(weight_out, d_dist.p, (size_t)total * 8, cudaMemcpyDeviceToHost));
+        double sum = 0.0;
+        for (int64_t i = 0; i < total; ++i) sum = sum + weight_out[i];        // ascending member order
+        for (int64_t i = 0; i < total; ++i) weight_out[i] = sum > 0.0 ? weight_out[i] / sum : 1.0 / (double)total;
+    }
+    *n_selected = total;
     return DCP_OK;
 }
 

@@ -107,6 +107,7 @@ struct DevBatch {
     double *sse, *lsse;
     double *sq, *sqq, *sqo;         // sums over the valid steps of q, q*q, q*qobs (KGE, PBIAS)
     int32_t *bad;                   // [nriv][B] non-finite flow seen
+    uint32_t *fdc;                  // [B][nriv][DCP_FDC_BINS] histogram of the routed flow (DCP_OPT_SIGNATURES), else null
     // per member
     int32_t *status;                // [B]
     double *diag;                   // [3][B]
@@ -116,6 +117,22 @@ struct DevBatch {
     double *qof_term;               // [nac][B]  (exs+exus)*ac of the current step (0 when not positive)
     int32_t *bad_src;               // [B]       member holds a non-finite baseflow (dense redistribute only)
 };
+
+// Flow-duration histogram bin of a routed flow (DCP_OPT_SIGNATURES): cut on the IEEE bits -- exponent and the top three
+// mantissa bits -- so that a host restatement bins the same doubles identically.  Bin 0: below 2^-40 (and anything not
+// positive, NaN included), last bin: 2^8 and above.
+__host__ __device__ inline int dcp_fdc_bin(double q) {
+    long long b;
+#if defined(__CUDA_ARCH__)
+    b = __double_as_longlong(q);
+#else
+    static_assert(sizeof(long long) == sizeof(double), "");
+    __builtin_memcpy(&b, &q, 8);
+#endif
+    if (!(q > 0.0)) return 0;
+    const int key = (int)(b >> 49) - (1023 + DCP_FDC_OCTAVE_LO) * 8;
+    return key < 0 ? 0 : (key >= 8 * DCP_FDC_OCTAVES ? DCP_FDC_BINS - 1 : key + 1);
+}
 
 // ---- stepwise path: plan of the redistribute step and of the ordered river sums -------------------
 struct DensePlan {

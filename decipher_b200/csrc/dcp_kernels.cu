@@ -521,6 +521,7 @@ k_route_gauge(DevCatchment C, DevBatch W, int t0, int t1, double *__restrict__ q
     const double q = q_sum / C.frac_sub_area[i];
     if (q_out) q_out[((size_t)m * C.nstep + t) * C.nriv + i] = q;
     if (!isfinite(q)) W.bad[i * (size_t)B + m] = 1;
+    if (W.fdc && t >= C.t_warm) atomicAdd(W.fdc + ((size_t)m * C.nriv + i) * DCP_FDC_BINS + dcp_fdc_bin(q), 1u);
     if (C.qobs != nullptr) {
         double d2 = 0.0, dl2 = 0.0;
         const int n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs;
@@ -629,9 +630,29 @@ k_route_status(DevCatchment C, DevBatch W, int32_t *__restrict__ status) {
 // ------------------------------------------------------------------------------------------------
 // K4: outputs in the ABI's layouts (member slowest)
 // ------------------------------------------------------------------------------------------------
+// Flow exceeded a fraction p of the time, from the histogram (counted from the top bin down, linear inside the bin)
+__device__ double fdc_quantile(const uint32_t *__restrict__ h, double n_total, double p) {
+    const double r = p * n_total;
+    double cum = 0.0;
+    for (int b = DCP_FDC_BINS - 1; b >= 0; --b) {
+        const double cnt = (double)h[b];
+        if (cnt == 0.0) continue;
+        cum = cum + cnt;
+        if (cum >= r) {
+            if (b == 0) return 0.0;
+            const int key = b - 1;                                                   // 8 * octave + sub-bin
+            const double lo = ldexp(1.0 + (double)(key & 7) * 0.125, (key >> 3) + DCP_FDC_OCTAVE_LO);
+            if (b == DCP_FDC_BINS - 1) return ldexp(1.0, DCP_FDC_OCTAVE_LO + DCP_FDC_OCTAVES);
+            const double hi = ldexp(1.0 + (double)((key & 7) + 1) * 0.125, (key >> 3) + DCP_FDC_OCTAVE_LO);
+            return lo + ((cum - r) / cnt) * (hi - lo);                              // (cum - r) / cnt of the bin lies below the target
+        }
+    }
+    return 0.0;
+}
+
 __global__ void __launch_bounds__(128)
 k_finalize(DevCatchment C, DevBatch W, double *__restrict__ perf, double *__restrict__ totals,
-           double *__restrict__ diag, int32_t *__restrict__ status) {
+           double *__restrict__ diag, int32_t *__restrict__ status, double *__restrict__ sig) {
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = W.B;
     if (m >= B) return;
@@ -678,6 +699,21 @@ k_finalize(DevCatchment C, DevBatch W, double *__restrict__ perf, double *__rest
             for (int ia = 0; ia < C.nac; ++ia)
                 if (C.hru[ia].ipriv == g) a = a + (W.aet[ia * (size_t)B + m] * C.hru[ia].ac);
             totals[((size_t)m * nriv + g) * 3 + 2] = (a / C.tot_frac[g]) * 1000.0;
+        }
+    }
+    if (sig && W.fdc) {
+        const double nan2 = __longlong_as_double(0x7ff8000000000000ll);
+        for (int g = 0; g < nriv; ++g) {
+            const uint32_t *h = W.fdc + ((size_t)m * nriv + g) * DCP_FDC_BINS;
+            double n_total = 0.0;
+            for (int b = 0; b < DCP_FDC_BINS; ++b) n_total = n_total + (double)h[b];
+            double *sg = sig + ((size_t)m * nriv + g) * DCP_NSIG;
+            const bool ok = n_total > 0.0 && !W.bad[g * (size_t)B + m];
+            const double q33 = ok ? fdc_quantile(h, n_total, 0.33) : nan2, q66 = ok ? fdc_quantile(h, n_total, 0.66) : nan2;
+            sg[DCP_SIG_Q5] = ok ? fdc_quantile(h, n_total, 0.05) : nan2;
+            sg[DCP_SIG_Q50] = ok ? fdc_quantile(h, n_total, 0.50) : nan2;
+            sg[DCP_SIG_Q95] = ok ? fdc_quantile(h, n_total, 0.95) : nan2;
+            sg[DCP_SIG_SLOPE] = (ok && q66 > 0.0) ? (log(q33) - log(q66)) / 0.33 : nan2;
         }
     }
     if (diag)
@@ -792,8 +828,63 @@ void dcp_launch_route_status(const DevCatchment &C, const DevBatch &W, int32_t *
 }
 
 void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,
-                         int32_t *status, cudaStream_t s) {
-    k_finalize<<<cdiv(W.B, 128), 128, 0, s>>>(C, W, perf, totals, diag, status);
+                         int32_t *status, double *sig, cudaStream_t s) {
+    k_finalize<<<cdiv(W.B, 128), 128, 0, s>>>(C, W, perf, totals, diag, status, sig);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Behavioural filtering (dcp_select_behavioural): per-member pass mask + distance from the threshold, per-block counts,
+// then an order-preserving scatter with host-scanned block offsets (<= 1024 blocks for 10^6 members).
+// ------------------------------------------------------------------------------------------------
+#define SEL_THREADS 1024
+__device__ __forceinline__ bool sel_eval(const double *__restrict__ perf, int64_t m, int nriv, int measure, int gauge, double thr, int hib, double &dist) {
+    bool pass = true;
+    double worst = 1e300;
+    for (int g = (gauge < 0 ? 0 : gauge); g < (gauge < 0 ? nriv : gauge + 1); ++g) {
+        double v = perf[((size_t)m * nriv + g) * DCP_NMEASURE + measure];
+        if (measure == DCP_PERF_PBIAS) v = fabs(v);
+        const bool ok = hib ? (v >= thr) : (v <= thr);                   // NaN compares false
+        pass = pass && ok;
+        const double d = fabs(v - thr);
+        worst = d < worst ? d : worst;
+    }
+    dist = worst;
+    return pass;
+}
+__global__ void __launch_bounds__(SEL_THREADS)
+k_select_count(const double *__restrict__ perf, int64_t n, int nriv, int measure, int gauge, double thr, int hib, int32_t *__restrict__ block_count) {
+    const int64_t m = blockIdx.x * (int64_t)SEL_THREADS + threadIdx.x;
+    double d;
+    const bool pass = m < n && sel_eval(perf, m, nriv, measure, gauge, thr, hib, d);
+    const int c = __syncthreads_count(pass);
+    if (threadIdx.x == 0) block_count[blockIdx.x] = c;
+}
+__global__ void __launch_bounds__(SEL_THREADS)
+k_select_scatter(const double *__restrict__ perf, int64_t n, int nriv, int measure, int gauge, double thr, int hib,
+                 const int64_t *__restrict__ block_off, int64_t *__restrict__ index_out, double *__restrict__ dist_out) {
+    __shared__ int warp_cnt[SEL_THREADS / 32];
+    const int64_t m = blockIdx.x * (int64_t)SEL_THREADS + threadIdx.x;
+    double d = 0.0;
+    const bool pass = m < n && sel_eval(perf, m, nriv, measure, gauge, thr, hib, d);
+    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) warp_cnt[w] = __popc(bal);
+    __syncthreads();
+    int base = 0;
+    for (int i = 0; i < w; ++i) base += warp_cnt[i];
+    if (pass) {
+        const int64_t o = block_off[blockIdx.x] + base + __popc(bal & ((1u << lane) - 1u));
+        index_out[o] = m;
+        dist_out[o] = d;
+    }
+}
+int dcp_select_blocks(int64_t n) { return (int)((n + SEL_THREADS - 1) / SEL_THREADS); }
+void dcp_launch_select_count(const double *perf, int64_t n, int nriv, int measure, int gauge, double thr, int hib, int32_t *block_count, cudaStream_t s) {
+    k_select_count<<<dcp_select_blocks(n), SEL_THREADS, 0, s>>>(perf, n, nriv, measure, gauge, thr, hib, block_count);
+}
+void dcp_launch_select_scatter(const double *perf, int64_t n, int nriv, int measure, int gauge, double thr, int hib, const int64_t *block_off,
+                               int64_t *index_out, double *dist_out, cudaStream_t s) {
+    k_select_scatter<<<dcp_select_blocks(n), SEL_THREADS, 0, s>>>(perf, n, nriv, measure, gauge, thr, hib, block_off, index_out, dist_out);
 }
 
 __global__ void k_or_status(int32_t *__restrict__ status, const int32_t *__restrict__ extra, int32_t mask, int64_t n) {

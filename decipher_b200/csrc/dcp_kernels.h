@@ -25,7 +25,11 @@ void dcp_launch_route_prepare(const DevCatchment &C, const DevBatch &W, const do
                               cudaStream_t s);
 void dcp_launch_route_status(const DevCatchment &C, const DevBatch &W, int32_t *status, cudaStream_t s);
 void dcp_launch_finalize(const DevCatchment &C, const DevBatch &W, double *perf, double *totals, double *diag,
-                         int32_t *status, cudaStream_t s);
+                         int32_t *status, double *sig, cudaStream_t s);
+int dcp_select_blocks(int64_t n);
+void dcp_launch_select_count(const double *perf, int64_t n, int nriv, int measure, int gauge, double thr, int hib, int32_t *block_count, cudaStream_t s);
+void dcp_launch_select_scatter(const double *perf, int64_t n, int nriv, int measure, int gauge, double thr, int hib, const int64_t *block_off,
+                               int64_t *index_out, double *dist_out, cudaStream_t s);
 void dcp_launch_or_status(int32_t *status, const int32_t *extra, int32_t mask, int64_t n, cudaStream_t s);
 void dcp_launch_fp64_peak(double *out, int iters, int blocks, cudaStream_t s);
 cudaError_t dcp_launch_physics_resident(const DevCatchment &C, const DevBatch &W, const ResPlan &P, bool fast,

@@ -214,7 +214,9 @@ int dcp_run_ensemble_multi(dcp_comm *c, const dcp_catchment_desc *desc, int64_t 
     const size_t npar = (size_t)desc->npt * 7;
     // Large outputs (flow series, reach totals) go straight from each device into the caller's arrays; then nothing
     // is left to gather.  The measures-only run keeps everything on the devices and gathers once at the end.
-    const bool direct = q_out != nullptr || reach_totals != nullptr;
+    const bool want_sig = (o.flags & DCP_OPT_SIGNATURES) != 0;
+    if (want_sig && !o.sig_out) return mfail(DCP_ERR_INVALID, "DCP_OPT_SIGNATURES without dcp_run_opts.sig_out");
+    const bool direct = q_out != nullptr || reach_totals != nullptr || want_sig;
     const size_t perf_b = perf_out ? (size_t)DCP_NMEASURE * nriv * 8 : 0, diag_b = init_diag ? 24 : 0, st_b = status ? 4 : 0;
     std::vector<int> rc(G, DCP_OK);
     std::vector<std::string> err(G);
@@ -236,7 +238,9 @@ int dcp_run_ensemble_multi(dcp_comm *c, const dcp_catchment_desc *desc, int64_t 
         int k = dcp_catchment_create(desc, &cat);
         if (k != DCP_OK) return bail(k, "dcp_catchment_create", dcp_last_error());
         if (direct) {
-            k = dcp_run_ensemble(cat, lo + 1, n, mcpar + npar * lo, &o, q_out ? q_out + (size_t)nriv * desc->nstep * lo : nullptr,
+            dcp_run_opts orank = o;                      // this rank's block of the signature table
+            if (want_sig) orank.sig_out = o.sig_out + (size_t)DCP_NSIG * nriv * lo;
+            k = dcp_run_ensemble(cat, lo + 1, n, mcpar + npar * lo, &orank, q_out ? q_out + (size_t)nriv * desc->nstep * lo : nullptr,
                                  perf_out ? perf_out + (size_t)DCP_NMEASURE * nriv * lo : nullptr,
                                  reach_totals ? reach_totals + (size_t)3 * nriv * lo : nullptr,
                                  init_diag ? init_diag + 3 * lo : nullptr, status ? status + lo : nullptr);

@@ -204,6 +204,7 @@ static __device__ __noinline__ R2Fix r2_fix_unit(uint32_t cst_a, uint32_t par_a,
 struct R2RouteArgs {
     const double *dh, *ring, *qobs, *log_obs, *inv_frac, *obs_eps;
     double *q_user;
+    uint32_t *fdc;
     const int32_t *gauge_job_beg;
     uint32_t job_s, acc_s;            // shared-memory addresses
     int Rmask, nriv, njm, n_pairs, m_base, B, nstep, n_t, t_warm;
@@ -235,6 +236,7 @@ static __device__ __noinline__ void r2_route_tile(const R2RouteArgs a, const int
                 }
                 const double q = q_sum * a.inv_frac[i];
                 if (a.q_user) a.q_user[((size_t)m * a.nstep + t) * a.nriv + i] = q;
+                if (a.fdc && t >= a.t_warm) atomicAdd(a.fdc + ((size_t)m * a.nriv + i) * DCP_FDC_BINS + dcp_fdc_bin(q), 1u);
                 const bool fin = isfinite(q);
                 bad |= !fin;
                 if (a.qobs != nullptr && t >= a.t_warm && t < a.n_t) {
@@ -292,7 +294,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
         auto route_args = [&]() {
             R2RouteArgs a;
             a.dh = W.dh; a.ring = W.qout; a.qobs = C.qobs; a.log_obs = P.log_obs; a.inv_frac = P.inv_frac; a.obs_eps = P.obs_eps;
-            a.q_user = W.q_user; a.gauge_job_beg = P.gauge_job_beg;
+            a.q_user = W.q_user; a.fdc = W.fdc; a.gauge_job_beg = P.gauge_job_beg;
             a.job_s = smem_u32(M.job_s); a.acc_s = smem_u32(M.acc_s);
             a.Rmask = W.Rmask; a.nriv = C.nriv; a.njm = P.jobs_per_member; a.n_pairs = Mv * C.nriv; a.m_base = m_base; a.B = B;
             a.nstep = C.nstep; a.n_t = C.nstep < C.nstep_obs ? C.nstep : C.nstep_obs; a.t_warm = C.t_warm; a.flow_err = C.flow_err;

@@ -109,6 +109,7 @@ __device__ __forceinline__ void rt_chunk(const DevCatchment &C, const DevBatch &
                 q_sum = __dadd_rn(q_sum, rt_node_at_column(C, W, m, sl, C.up_idx[e], col, t));
             q = __ddiv_rn(q_sum, C.frac_sub_area[i]);
             if (W.q_user) W.q_user[((size_t)m * C.nstep + t) * C.nriv + i] = q;
+            if (W.fdc && t >= C.t_warm) atomicAdd(W.fdc + ((size_t)m * C.nriv + i) * DCP_FDC_BINS + dcp_fdc_bin(q), 1u);
         }
         const bool bad = in && !isfinite(q);
         if (__any_sync(0xffffffffu, bad) && lane == 0) W.bad[i * (size_t)B + m] = 1;

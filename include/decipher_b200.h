@@ -35,7 +35,8 @@
 extern "C" {
 #endif
 
-#define DCP_ABI_VERSION 3   /* 2: DCP_NMEASURE 2 -> 5 (layout of perf_out) and dcp_route_timeseries; 3: dcp_comm_* / dcp_run_ensemble_multi */
+#define DCP_ABI_VERSION 4   /* 2: DCP_NMEASURE 2 -> 5 (layout of perf_out) and dcp_route_timeseries; 3: dcp_comm_* / dcp_run_ensemble_multi;
+                               4: dcp_run_opts.sig_out (flow-duration signatures), dcp_select_behavioural */
 
 /* ---- error codes ------------------------------------------------------------------------- */
 #define DCP_OK               0
@@ -68,6 +69,8 @@ extern "C" {
 #define DCP_OPT_FAST_MATH       0x4     /* reciprocal-hoisted arithmetic (<=1e-9 rel.; default is the
                                            reference's operation order with IEEE division)            */
 
+#define DCP_OPT_SIGNATURES      0x8     /* flow-duration-curve signatures into dcp_run_opts.sig_out (extension)    */
+
 /* kernel selector (dcp_run_opts.kernel) */
 #define DCP_KERNEL_AUTO      0
 #define DCP_KERNEL_STREAMED  1          /* state streamed through L2/HBM, any nac                     */
@@ -83,6 +86,19 @@ extern "C" {
 #define DCP_PERF_KGE    2   /* Kling-Gupta efficiency (2009 form: r, sigma ratio, mean ratio) */
 #define DCP_PERF_PBIAS  3   /* 100 * sum(sim - obs) / sum(obs)                            */
 #define DCP_PERF_RMSE   4   /* root mean square error, m/timestep                         */
+
+/* Flow-duration-curve signatures per (gauge, member) (extension, DESIGN.md "Objective"; nothing upstream): computed on the
+ * device from a streaming histogram of the routed flow (steps after t_warm) -- no flow series has to leave the chip.
+ * Histogram bins are cut on the IEEE bits of the flow: 8 linear sub-bins per octave over [2^-40, 2^8) m/timestep
+ * (+ one bin below, one above); quantiles interpolate linearly inside their bin.                                      */
+#define DCP_NSIG 4
+#define DCP_SIG_Q5      0   /* flow exceeded 5 % of the time (high flows)                  */
+#define DCP_SIG_Q50     1   /* median flow                                                 */
+#define DCP_SIG_Q95     2   /* flow exceeded 95 % of the time (low flows)                  */
+#define DCP_SIG_SLOPE   3   /* slope of the FDC mid-segment: (ln Q33 - ln Q66) / 0.33      */
+#define DCP_FDC_OCTAVE_LO (-40)
+#define DCP_FDC_OCTAVES   48
+#define DCP_FDC_BINS      (8 * DCP_FDC_OCTAVES + 2)
 
 /*
  * Static description of one catchment: everything the reference holds after
@@ -151,6 +167,8 @@ typedef struct dcp_run_opts {
     int32_t members_per_batch;  /* 0 = library chooses                                               */
     int32_t steps_per_tile;     /* 0 = library chooses (time tile of the flow ring buffer)           */
     int32_t reserved;
+    double *sig_out;            /* DCP_OPT_SIGNATURES: [DCP_NSIG x nriv x n_member] (host, or device with
+                                   DCP_OPT_DEVICE_BUFFERS); ignored otherwise                          */
 } dcp_run_opts;
 
 /* timing of the last dcp_run_ensemble call on this handle, CUDA events on the library's stream */
@@ -221,6 +239,19 @@ int  dcp_route_timeseries(dcp_catchment *c, int64_t n_series, const double *velo
                           double *routed, int32_t *status, int32_t flags);
 
 int  dcp_get_run_stats(const dcp_catchment *c, dcp_run_stats *out);
+
+/*
+ * GLUE-style behavioural filtering (extension): members whose measure `measure` (DCP_PERF_*) passes
+ * `threshold` at gauge `gauge` (0-based; -1: at EVERY gauge) are behavioural.  higher_is_better != 0: pass = value >=
+ * threshold (NSE, log-NSE, KGE), else value <= threshold (RMSE; PBIAS is compared on its absolute value).  NaN never passes.
+ *   perf        [DCP_NMEASURE x nriv x n_member], host -- or device with flags = DCP_OPT_DEVICE_BUFFERS
+ *   index_out   [n_member] host: the behavioural members (0-based), ascending
+ *   weight_out  [n_member] host or NULL: likelihood weights |value - threshold| (worst gauge when gauge = -1), normalised
+ *               to sum 1 over the behavioural members (all equal when every distance is 0)
+ * The mask and the order-preserving compaction run on the device.                                                  */
+int  dcp_select_behavioural(const double *perf, int64_t n_member, int32_t nriv, int32_t measure, int32_t gauge,
+                            double threshold, int32_t higher_is_better, int64_t *index_out, double *weight_out,
+                            int64_t *n_selected, int32_t flags);
 
 /* ---- all GPUs of one box (dcp_comm_init / dcp_gather_perf) ----------------------------------------
  * One process, one host thread per rank.  Rank r owns device devices[r] (NULL: rank r -> device r) and runs the

@@ -206,3 +206,57 @@ def run_member(cat, mcpar):
             F[:, 0] = 0
             F = np.roll(F, -1, axis=1)
     return q
+
+
+# ------------------------------------------------------------------------------------------------
+# Flow-duration-curve signatures (extension; include/decipher_b200.h DCP_SIG_*): NumPy restatement of the device's
+# streaming histogram (bins cut on the IEEE bits: exponent + top three mantissa bits) and of its quantile rule.
+# ------------------------------------------------------------------------------------------------
+FDC_OCTAVE_LO, FDC_OCTAVES = -40, 48
+FDC_BINS = 8 * FDC_OCTAVES + 2
+
+
+def fdc_bins(q):
+    q = np.ascontiguousarray(q, dtype=np.float64)
+    key = (q.view(np.int64) >> 49).astype(np.int64) - (1023 + FDC_OCTAVE_LO) * 8
+    b = np.where(key < 0, 0, np.where(key >= 8 * FDC_OCTAVES, FDC_BINS - 1, key + 1))
+    return np.where(q > 0.0, b, 0)
+
+
+def fdc_quantile(h, n_total, p):
+    r = p * n_total
+    cum = 0.0
+    for b in range(FDC_BINS - 1, -1, -1):
+        cnt = float(h[b])
+        if cnt == 0.0:
+            continue
+        cum = cum + cnt
+        if cum >= r:
+            if b == 0:
+                return 0.0
+            key = b - 1
+            lo = np.ldexp(1.0 + (key & 7) * 0.125, (key >> 3) + FDC_OCTAVE_LO)
+            if b == FDC_BINS - 1:
+                return float(np.ldexp(1.0, FDC_OCTAVE_LO + FDC_OCTAVES))
+            hi = np.ldexp(1.0 + ((key & 7) + 1) * 0.125, (key >> 3) + FDC_OCTAVE_LO)
+            return float(lo + ((cum - r) / cnt) * (hi - lo))
+    return 0.0
+
+
+def fdc_signatures(q, t_warm=0):
+    """q: (nriv, nstep, M) -> (4, nriv, M): Q5, Q50, Q95 (flows exceeded 5 / 50 / 95 % of the time) and the mid-segment slope."""
+    nriv, nstep, M = q.shape
+    out = np.full((4, nriv, M), np.nan)
+    for m in range(M):
+        for g in range(nriv):
+            series = q[g, t_warm:, m]
+            if not np.isfinite(series).all():
+                continue
+            h = np.bincount(fdc_bins(series), minlength=FDC_BINS)
+            n = float(h.sum())
+            q33, q66 = fdc_quantile(h, n, 0.33), fdc_quantile(h, n, 0.66)
+            out[0, g, m] = fdc_quantile(h, n, 0.05)
+            out[1, g, m] = fdc_quantile(h, n, 0.50)
+            out[2, g, m] = fdc_quantile(h, n, 0.95)
+            out[3, g, m] = (np.log(q33) - np.log(q66)) / 0.33 if q66 > 0.0 else np.nan
+    return out

@@ -37,6 +37,7 @@ module decipher_c_api
 
     type, bind(C) :: dcp_run_opts
         integer(c_int32_t) :: struct_size, flags, kernel, members_per_batch, steps_per_tile, reserved
+        type(c_ptr) :: sig_out          ! DCP_OPT_SIGNATURES: (DCP_NSIG, nriv, n_member) flow-duration signatures, else c_null_ptr
     end type
 
     interface

@@ -137,7 +137,7 @@ program main
 
     ! ---- ONE call replaces `do i_mc = 1, numsim ... call mainloop(...)` ----
     opts%struct_size = int(c_sizeof(opts), c_int32_t); opts%flags = 0; opts%kernel = 0
-    opts%members_per_batch = 0; opts%steps_per_tile = 0; opts%reserved = 0
+    opts%members_per_batch = 0; opts%steps_per_tile = 0; opts%reserved = 0; opts%sig_out = c_null_ptr
     rc = dcp_run_ensemble(handle, 1_c_int64_t, int(numsim, c_int64_t), c_loc(all_mcpar), opts, c_loc(q_all), c_loc(perf), &
                           c_loc(totals), c_loc(diag), c_loc(status))
     if (rc /= DCP_OK) stop 'dcp_run_ensemble failed'

@@ -110,7 +110,7 @@ def test_abi_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     lib.dcp_abi_version.restype = C.c_int
-    assert lib.dcp_abi_version() == 3
+    assert lib.dcp_abi_version() == 4
     assert C.sizeof(CatchmentDesc) == 304 or C.sizeof(CatchmentDesc) > 0
 
 
