@@ -813,7 +813,8 @@ size_t carve_batch(void *base, const DevCatchment &C, DevBatch &W, bool check, b
         W.qin_ext = cv.take<double>(nac * B); W.qof_term = cv.take<double>(nac * B);
         W.qb_term = cv.take<double>((size_t)std::max(stepwise_nq, 1) * B);
         W.bad_src = cv.take<int32_t>(B);
-    } else { W.qin_ext = W.qof_term = W.qb_term = nullptr; W.bad_src = nullptr; }
+        W.t_dev = cv.take<int32_t>(64);
+    } else { W.qin_ext = W.qof_term = W.qb_term = nullptr; W.bad_src = nullptr; W.t_dev = nullptr; }
     return cv.off + 256;
 }
 

@@ -116,6 +116,7 @@ struct DevBatch {
     double *qb_term;                // [nq][B]   per river entry: (((dtt*qbf)*w_riv)*rivers)*ac of the current step
     double *qof_term;               // [nac][B]  (exs+exus)*ac of the current step (0 when not positive)
     int32_t *bad_src;               // [B]       member holds a non-finite baseflow (dense redistribute only)
+    int32_t *t_dev;                 // [1]       timestep counter read by the graph-replayed launch sets
 };
 
 // Flow-duration histogram bin of a routed flow (DCP_OPT_SIGNATURES): cut on the IEEE bits -- exponent and the top three

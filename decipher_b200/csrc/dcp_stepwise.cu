@@ -279,7 +279,9 @@ k_redistribute_dense_mma(DensePlan D, const double *__restrict__ Bm, double *__r
 // ------------------------------------------------------------------------------------------------
 template <bool FAST, bool AET, bool NPT1>
 __global__ void __launch_bounds__(SW_THREADS)
-k_physics_step(DevCatchment C, DevBatch W, int t, int rows_per_chunk) {
+k_physics_step(DevCatchment C, DevBatch W, const int *__restrict__ t_base, int t_off, int rows_per_chunk) {
+    const int t = *t_base + t_off;                 // the launch set of a step is replayed from a CUDA graph: the timestep
+                                                   // comes from a device counter (+ the node's offset inside the graph)
     const int m = blockIdx.x * blockDim.x + threadIdx.x;
     const int B = W.B;
     if (m >= B) return;
@@ -349,7 +351,8 @@ k_physics_step(DevCatchment C, DevBatch W, int t, int rows_per_chunk) {
 // (3) river sums in the reference's order: thread = member, blockIdx.y = river
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SW_THREADS)
-k_river_sum(DevCatchment C, DevBatch W, DensePlan D, int t) {
+k_river_sum(DevCatchment C, DevBatch W, DensePlan D, const int *__restrict__ t_base, int t_off) {
+    const int t = *t_base + t_off;
     const int m = blockIdx.x * blockDim.x + threadIdx.x, r = blockIdx.y;
     const int B = W.B;
     if (m >= B) return;
@@ -375,11 +378,15 @@ k_river_sum(DevCatchment C, DevBatch W, DensePlan D, int t) {
 // ------------------------------------------------------------------------------------------------
 // launch wrapper: steps [t0, t1)
 // ------------------------------------------------------------------------------------------------
+__global__ void k_step_counter(int *t_base, int set_to, int add) { *t_base = set_to >= 0 ? set_to : *t_base + add; }
+
 template <bool FAST, bool AET>
-static void launch_step(const DevCatchment &C, const DevBatch &W, int t, int rows, dim3 grid, cudaStream_t s) {
-    if (C.npt == 1) k_physics_step<FAST, AET, true><<<grid, SW_THREADS, 0, s>>>(C, W, t, rows);
-    else k_physics_step<FAST, AET, false><<<grid, SW_THREADS, 0, s>>>(C, W, t, rows);
+static void launch_step(const DevCatchment &C, const DevBatch &W, const int *t_base, int t_off, int rows, dim3 grid, cudaStream_t s) {
+    if (C.npt == 1) k_physics_step<FAST, AET, true><<<grid, SW_THREADS, 0, s>>>(C, W, t_base, t_off, rows);
+    else k_physics_step<FAST, AET, false><<<grid, SW_THREADS, 0, s>>>(C, W, t_base, t_off, rows);
 }
+
+#define SW_GRAPH_STEPS 32             // timesteps per CUDA graph (even: the baseflow double buffer repeats with period 2)
 
 cudaError_t dcp_launch_physics_stepwise(const DevCatchment &C, const DevBatch &W, const DensePlan &D, int t0, int t1,
                                         bool fast, bool aet, bool dense, int n_sm, cudaStream_t s) {
@@ -404,8 +411,12 @@ cudaError_t dcp_launch_physics_stepwise(const DevCatchment &C, const DevBatch &W
         cudaError_t e = cudaFuncSetAttribute(k_redistribute_dense_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gsm_mma);
         if (e != cudaSuccess) return e;
     }
-    for (int t = t0; t < t1; ++t) {
-        const double *qbf_old = (t & 1) ? W.qbf1 : W.qbf0;
+    // one timestep = 3-4 kernels; the launch set of SW_GRAPH_STEPS consecutive steps is captured ONCE into a CUDA graph and
+    // replayed, so host launches do not scale with nstep (8 760 steps = 274 graph launches instead of 35 040 kernel launches).
+    // Kernel arguments are frozen in a graph: the timestep is read from a device counter that the graph's last node advances.
+    int *t_base = W.t_dev;
+    auto enqueue_step = [&](int t_abs, int t_off) {         // t_abs only selects the baseflow buffer (parity)
+        const double *qbf_old = (t_abs & 1) ? W.qbf1 : W.qbf0;
         if (dense) {
             if (use_mma) k_redistribute_dense_mma<<<g_gemm, GM_THREADS, gsm_mma, s>>>(D, qbf_old, W.qin_ext, W.bad_src, C.nac, W.B);
             else if (fast) k_redistribute_dense<false><<<g_gemm, GM_THREADS, gsm, s>>>(D, qbf_old, W.qin_ext, W.bad_src, C.nac, W.B);
@@ -414,9 +425,32 @@ cudaError_t dcp_launch_physics_stepwise(const DevCatchment &C, const DevBatch &W
         } else {
             k_redistribute_csr<false><<<g_phys, SW_THREADS, 0, s>>>(C, W, qbf_old, rows);
         }
-        if (aet) { if (fast) launch_step<true, true>(C, W, t, rows, g_phys, s); else launch_step<false, true>(C, W, t, rows, g_phys, s); }
-        else { if (fast) launch_step<true, false>(C, W, t, rows, g_phys, s); else launch_step<false, false>(C, W, t, rows, g_phys, s); }
-        k_river_sum<<<g_riv, SW_THREADS, 0, s>>>(C, W, D, t);
+        if (aet) { if (fast) launch_step<true, true>(C, W, t_base, t_off, rows, g_phys, s); else launch_step<false, true>(C, W, t_base, t_off, rows, g_phys, s); }
+        else { if (fast) launch_step<true, false>(C, W, t_base, t_off, rows, g_phys, s); else launch_step<false, false>(C, W, t_base, t_off, rows, g_phys, s); }
+        k_river_sum<<<g_riv, SW_THREADS, 0, s>>>(C, W, D, t_base, t_off);
+    };
+    int t = t0;
+    k_step_counter<<<1, 1, 0, s>>>(t_base, t0, 0);
+    if (t & 1) { enqueue_step(t, 0); k_step_counter<<<1, 1, 0, s>>>(t_base, -1, 1); ++t; }      // graphs start on an even step
+    const int n_graph = (t1 - t) / SW_GRAPH_STEPS;
+    if (n_graph >= 2 && !getenv("DCP_STEPWISE_NO_GRAPH")) {
+        cudaGraph_t graph = nullptr;
+        cudaGraphExec_t exec = nullptr;
+        cudaError_t e = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal);
+        if (e != cudaSuccess) return e;
+        for (int i = 0; i < SW_GRAPH_STEPS; ++i) enqueue_step(t + i, i);
+        k_step_counter<<<1, 1, 0, s>>>(t_base, -1, SW_GRAPH_STEPS);
+        e = cudaStreamEndCapture(s, &graph);
+        if (e == cudaSuccess) e = cudaGraphInstantiate(&exec, graph, 0);
+        if (e != cudaSuccess) { if (graph) cudaGraphDestroy(graph); return e; }
+        for (int g2 = 0; g2 < n_graph && e == cudaSuccess; ++g2) e = cudaGraphLaunch(exec, s);
+        t += n_graph * SW_GRAPH_STEPS;
+        // the executable graph must outlive its launches: the stream is synchronised before it is destroyed
+        if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+        cudaGraphExecDestroy(exec);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) return e;
     }
+    for (int i = 0; t + i < t1; ++i) enqueue_step(t + i, i);      // remainder (and short tiles): direct launches off the same counter
     return cudaGetLastError();
 }

@@ -198,18 +198,20 @@ def _bitwise(a, b):
     assert np.array_equal(a["status"], b["status"])
 
 
+@pytest.mark.parametrize("tile", [150, 77])
 @pytest.mark.parametrize("min_density", ["2.0", "0.0"], ids=["csr", "gemm"])
-def test_stepwise_exact_is_bitwise_streamed(min_density, monkeypatch):
+def test_stepwise_exact_is_bitwise_streamed(min_density, tile, monkeypatch):
     """EXACT mode: redistribute (sparse CSR, or the dense GEMM with one ascending accumulation chain per output),
     physics over (HRU, member) and ordered river sums perform the reference's operations in the reference's order,
     so the result must equal the streamed kernel's bit for bit.  nac = 300 is not a multiple of the GEMM tile,
-    M = 37 is odd (ragged member tile), several time tiles."""
+    M = 37 is odd (ragged member tile), several time tiles -- of 150 steps (four 32-step CUDA graphs + 22 direct steps per
+    tile) and of 77 steps (every second tile starts on an odd step: one direct step before the graphs)."""
     monkeypatch.setenv("DCP_DENSE_MIN_DENSITY", min_density)
     cat = synth.synth_catchment(nac=300, nriv=4, npt=2, ngp=3, nge=2, nstep=400, kW=40, seed=synth.BASE_SEED + 41, tree=True)
     mc = synth.sample_parameters(cat.npt, 37)
     dev = DeviceCatchment(cat)
-    a = dev.run(mc.copy(order="F"), kernel=KERNEL_STREAMED, want_q=True, want_totals=True, steps_per_tile=150)
-    b = dev.run(mc.copy(order="F"), kernel=KERNEL_STEPWISE, want_q=True, want_totals=True, steps_per_tile=150)
+    a = dev.run(mc.copy(order="F"), kernel=KERNEL_STREAMED, want_q=True, want_totals=True, steps_per_tile=tile)
+    b = dev.run(mc.copy(order="F"), kernel=KERNEL_STEPWISE, want_q=True, want_totals=True, steps_per_tile=tile)
     dev.close()
     assert b["stats"]["kernel_used"] == KERNEL_STEPWISE
     _bitwise(a, b)
