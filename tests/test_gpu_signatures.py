@@ -50,17 +50,21 @@ def test_behavioural_selection_matches_numpy():
     perf = dev.run(mc, flags=OPT_FAST_MATH)["perf"]
     dev.close()
     perf[0, 1, 7] = np.nan                                             # a NaN never passes
-    for measure, thr, gauge, hib in [(PERF_NSE, -0.5, -1, True), (PERF_KGE, 0.0, 2, True), (PERF_RMSE, 6e-5, 0, False), (PERF_PBIAS, 30.0, -1, False)]:
-        idx, w = select_behavioural(perf, measure, thr, gauge=gauge, higher_is_better=hib)
+    for measure, gauge, hib in [(PERF_NSE, -1, True), (PERF_KGE, 2, True), (PERF_RMSE, 0, False), (PERF_PBIAS, -1, False)]:
         v = np.abs(perf[measure]) if measure == PERF_PBIAS else perf[measure]
         rows = v if gauge < 0 else v[gauge:gauge + 1]
+        worst = np.nanmin(rows, axis=0) if hib else np.nanmax(rows, axis=0)
+        thr = float(np.nanquantile(worst, 0.7 if hib else 0.3))         # about 30 % of the members are behavioural
+        idx, w = select_behavioural(perf, measure, thr, gauge=gauge, higher_is_better=hib)
         with np.errstate(invalid="ignore"):
             ok = (rows >= thr).all(axis=0) if hib else (rows <= thr).all(axis=0)
         want = np.nonzero(ok)[0]
         assert np.array_equal(idx, want), (measure, len(idx), len(want))
+        assert 0 < len(want) < M
+        if measure == PERF_NSE:
+            assert 7 not in want                                       # the NaN at gauge 1 fails the every-gauge rule
         dist = np.abs(rows - thr).min(axis=0)[want]
-        ww = dist / np.add.accumulate(dist)[-1] if len(want) and dist.sum() > 0 else dist
-        assert len(want) > 0 and len(want) < M
+        ww = dist / np.add.accumulate(dist)[-1]
         assert np.allclose(w, ww, rtol=1e-13, atol=0) and abs(w.sum() - 1.0) < 1e-12
     idx, w = select_behavioural(perf, PERF_NSE, 2.0)                   # impossible threshold: empty selection
     assert len(idx) == 0
