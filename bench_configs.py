@@ -136,16 +136,16 @@ def run_c4(args):
     dev.close()
 
 
-def make_c5_catchments(n_cat, nstep, seed0=20260119 + 5000):
-    """C5 catchments: nac ~ U{100..1000}, 2-4 gauged reaches, own forcing."""
-    from decipher_b200 import synth
+def c5_shapes(n_cat, seed0=20260119 + 5000):
+    """C5 catchment shapes: nac ~ U{100..1000}, 2-4 gauged reaches; cheap, identical on every rank."""
     rng = np.random.default_rng(seed0)
-    cats = []
-    for i in range(n_cat):
-        nac = int(rng.integers(100, 1001))
-        nriv = int(rng.integers(2, 5))
-        cats.append(synth.synth_catchment(nac=nac, nriv=nriv, npt=1, ngp=4, nge=1, nstep=nstep, kW=8, seed=seed0 + 1 + i, tree=True))
-    return cats
+    return [(int(rng.integers(100, 1001)), int(rng.integers(2, 5))) for _ in range(n_cat)]
+
+
+def make_c5_catchment(i, nac, nriv, nstep, seed0=20260119 + 5000):
+    """One C5 catchment with its own forcing (only the rank that owns it builds it)."""
+    from decipher_b200 import synth
+    return synth.synth_catchment(nac=nac, nriv=nriv, npt=1, ngp=4, nge=1, nstep=nstep, kW=8, seed=seed0 + 1 + i, tree=True)
 
 
 def run_c5(args):
@@ -161,26 +161,27 @@ def run_c5(args):
     n_cat = args.catchments or (8 * world)
     M = args.members or 2000
     nstep = args.nstep or 87600
-    cats = make_c5_catchments(n_cat, nstep)
-    costs = [c.nac * c.nstep * M for c in cats]
+    shapes = c5_shapes(n_cat)
+    costs = [nac * nstep * M for nac, _ in shapes]
     owner = lpt_assign(costs, world)
     mine = [i for i in range(n_cat) if owner[i] == rank]
     flags = capi.OPT_FAST_MATH if args.math == "fast" else 0
+    cats = {i: make_c5_catchment(i, shapes[i][0], shapes[i][1], nstep) for i in mine}
     tables = {i: synth.sample_parameters(1, M, seeds=(5 + i, 2000)) for i in mine}
     handles = {i: capi.DeviceCatchment(cats[i], device=local_rank) for i in mine}        # static data of a catchment lives on its GPU only
 
-    def one_pass(timed):
+    def one_pass(n_mem):
         busy = 0.0; kernels = {}; launches = 0; perf = {}
         t0 = time.perf_counter()
         for i in mine:
-            out = handles[i].run(tables[i].copy(order="F"), flags=flags, want_q=False, want_perf=True)
+            out = handles[i].run(np.asfortranarray(tables[i][:, :, :n_mem]), flags=flags, want_q=False, want_perf=True)
             busy += out["stats"]["ms_total"]; launches += out["stats"]["n_launches"]
             kernels[out["stats"]["kernel_used"]] = kernels.get(out["stats"]["kernel_used"], 0) + 1
             perf[i] = out["perf"]
         return busy, (time.perf_counter() - t0) * 1e3, kernels, launches, perf
 
-    for _ in range(max(args.warmup - 2, 1)):            # a pass is minutes of GPU time: one warm-up pass (clocks, allocations)
-        one_pass(False)
+    one_pass(max(M // 10, 1))                           # a full pass is minutes of GPU time: the warm-up pass (clocks, allocations,
+                                                        # first NCCL call below) runs a tenth of the members
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -188,7 +189,7 @@ def run_c5(args):
     busy = wall = 0.0; launches = 0; kernels = {}; perf = {}
     steps = max(1, min(args.steps, 2))
     for _ in range(steps):
-        b, w, kernels, l, perf = one_pass(True)
+        b, w, kernels, l, perf = one_pass(M)
         busy += b; wall += w; launches += l
     # the only collective: the measures of every catchment to rank 0 (ragged blocks: grouped send / recv)
     g_ms = 0.0
@@ -196,7 +197,7 @@ def run_c5(args):
         nmax = max(sum(1 for o in owner if o == r) for r in range(world))
         blk = torch.zeros((nmax, capi.NMEASURE, 4, M), dtype=torch.float64, device="cuda")
         for j, i in enumerate(mine):
-            blk[j, :, :cats[i].nriv, :] = torch.from_numpy(np.ascontiguousarray(perf[i])).cuda()
+            blk[j, :, :shapes[i][1], :] = torch.from_numpy(np.ascontiguousarray(perf[i])).cuda()
         outs = [torch.empty_like(blk) for _ in range(world)] if rank == 0 else None
         torch.cuda.synchronize(); dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -214,7 +215,7 @@ def run_c5(args):
     if rank == 0:
         units = float(sum(costs)) * steps
         ms_max = max(per_rank) * steps
-        nac_all = [c.nac for c in cats]
+        nac_all = [nac for nac, _ in shapes]
         line = {"metric": METRIC, "value": units / (ms_max * 1e-3), "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": 1,
                 "ms_per_step": ms_max / steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"C5: {n_cat} synthetic gauged catchments (nac ~ U{{100..1000}}: min {min(nac_all)}, median {int(np.median(nac_all))}, "
@@ -223,8 +224,8 @@ def run_c5(args):
                            "catchments": n_cat, "members_per_catchment": M, "nstep_per_step": nstep, "ensemble_of_config": "1000 catchments x 1e4 members",
                            "math": args.math, "kernels_used_rank0": {str(k): v for k, v in kernels.items()},
                            "parallelism": "catchments partitioned over ranks, no data-path collective; one gather of the measures"},
-                "e2e": {"value": units / (max(per_rank_wall) * steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(7 * 8 * M for _ in cats)),
-                        "d2h_bytes_per_step": int(sum((7 + capi.NMEASURE * c.nriv + 3) * 8 * M + 4 * M for c in cats)),
+                "e2e": {"value": units / (max(per_rank_wall) * steps * 1e-3), "unit": UNIT, "h2d_bytes_per_step": int(sum(7 * 8 * M for _ in shapes)),
+                        "d2h_bytes_per_step": int(sum((7 + capi.NMEASURE * nr + 3) * 8 * M + 4 * M for _, nr in shapes)),
                         "clock": "host wall clock around the rank's dcp_run_ensemble calls (host buffers), max over ranks"},
                 "gpu_launches": int(launches),
                 "clocks": {"sm_mhz": clk["sm_mhz"], "sm_max_mhz": clk["sm_max_mhz"], "reasons": clk["reasons"], "power_w_max": clk.get("power_w_max"),
