@@ -77,7 +77,10 @@ def test_cli_selected_members_binary_flows_and_two_ranks(tmp_path):
         r2 = subprocess.run([EXE, "-dir", root, "-ids", "1", "1", "1", "-no-flow", "-fast", "-gpus", "2"], capture_output=True, text=True, timeout=300)
         assert r2.returncode == 0, r2.stdout + r2.stderr
         tab2 = formats.read_perf_table(p.out_prefix + "ensemble_perf.bin")
-        assert np.array_equal(tab2["perf"], tab["perf"], equal_nan=True) and np.array_equal(tab2["status"], tab["status"])
+        # (the single-device pass also produced reach totals: another instantiation of the FAST kernel, so 1e-9, not bits)
+        compare_perf(tab2["perf"], ref["perf"])
+        assert np.array_equal(tab2["status"], tab["status"]) and np.array_equal(tab2["mcpar"], tab["mcpar"])
+        assert "NCCL gather" in r2.stdout
     bad = subprocess.run([EXE, "-dir", root, "-ids", "1", "1", "1", "-write-members", "0:3"], capture_output=True, text=True, timeout=60)
     assert bad.returncode == 2
     p.close()
