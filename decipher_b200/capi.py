@@ -343,7 +343,7 @@ class Communicator:
         return bool(self.lib.dcp_comm_uses_nccl(self._h))
 
     def run(self, cat: Catchment, mcpar: np.ndarray, *, flags=0, kernel=KERNEL_AUTO, want_q=False, want_perf=True,
-            want_totals=False, members_per_batch=0):
+            want_totals=False, want_sig=False, members_per_batch=0):
         """dcp_run_ensemble_multi: the whole (npt, 7, M) table over every rank; same outputs as DeviceCatchment.run."""
         assert mcpar.dtype == np.float64 and mcpar.flags.f_contiguous and mcpar.shape[:2] == (cat.npt, 7)
         M = mcpar.shape[2]
@@ -353,7 +353,10 @@ class Communicator:
         tot = np.empty((3, cat.nriv, M), order="F") if want_totals else None
         diag = np.empty((3, M), order="F")
         status = np.zeros(M, dtype=np.int32)
-        opts = make_opts(flags, kernel, members_per_batch, 0)
+        sig = np.empty((NSIG, cat.nriv, M), order="F") if want_sig else None
+        opts = make_opts(flags | (OPT_SIGNATURES if want_sig else 0), kernel, members_per_batch, 0)
+        if want_sig:
+            opts.sig_out = sig.ctypes.data_as(C.c_void_p)
         st = MultiStats()
 
         def p(a):
@@ -366,7 +369,7 @@ class Communicator:
         stats = dict(n_ranks=n, used_nccl=bool(st.used_nccl), kernel_used=st.kernel_used, ms_wall=st.ms_wall, ms_gather=st.ms_gather,
                      ms_busy_max=st.ms_busy_max, ms_busy_sum=st.ms_busy_sum, ms_rank_device=list(st.ms_rank_device[:n]),
                      ms_rank_wall=list(st.ms_rank_wall[:n]))
-        return dict(q=q, perf=perf, reach_totals=tot, init_diag=diag, status=status, mcpar=mcpar, stats=stats)
+        return dict(q=q, perf=perf, reach_totals=tot, init_diag=diag, status=status, mcpar=mcpar, sig=sig, stats=stats)
 
     def close(self):
         if self._h:

@@ -103,6 +103,10 @@
 #endif
 #define R2_S 2                        // member slots per team
 #define R2_H 4                        // columns per compute thread
+#ifndef R2_BC
+#define R2_BC 2                       // columns per physics block: R2_BC x 2 member slots = 4 interleaved dependency chains
+                                      // (4 columns = 8 chains spill and lose 17 %: 6.56e10 vs 7.93e10, profiles/r2_ab_routing_designs.txt)
+#endif
 #ifndef R2_CARRY_E1
 #define R2_CARRY_E1 1                 // carry exp(sd/m2) from step to step instead of recomputing it (dcp_physics.cuh)
 #endif
@@ -391,11 +395,11 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                 // this batch's tuples are fetched ----
                 const double *ep = ent0;
 #pragma unroll
-                for (int jp = 0; jp < H; jp += 2) {          // two columns = four (HRU, member) units per basic block
+                for (int jp = 0; jp < H; jp += R2_BC) {      // R2_BC columns = 2 R2_BC (HRU, member) units per basic block
                     int4 ci[H];
                     double qin[H][S];
 #pragma unroll
-                    for (int j = jp; j < jp + 2; ++j) {
+                    for (int j = jp; j < jp + R2_BC; ++j) {
                         ci[j] = M.coli_s[j * R2_TC + tt_id];
 #ifdef R2_TUNE_NO_GATHER                                                                // timing experiment only (wrong results)
                         const int nb = 0;
@@ -451,11 +455,11 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                         qin[j][0] = q0; qin[j][1] = q1;
                     }
                     // ---- root zone, unsaturated zone, saturated zone: 4 interleaved dependency chains ----
-                    LeanOut lo[2][S];
-                    double cq[2];
+                    LeanOut lo[R2_BC][S];
+                    double cq[R2_BC];
                     bool any_slow = false;
 #pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
+                    for (int jj = 0; jj < R2_BC; ++jj) {
                         const int j = jp + jj;
 #if R2_WIDE
                         const double2 w0 = M.cold_s[j * R2_TC + tt_id];      // {ac, cq}
@@ -504,7 +508,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                     }
                     if (__builtin_expect(any_slow, 0)) {                                                     // rare: sd > smax, out-of-range exponent
 #pragma unroll
-                        for (int jj = 0; jj < 2; ++jj)
+                        for (int jj = 0; jj < R2_BC; ++jj)
 #pragma unroll
                             for (int k = 0; k < S; ++k)
                                 if (lo[jj][k].slow) {
@@ -525,11 +529,11 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
                     // publish: both loads of the old baseflow first (straight-line, so that they overlap), then the stores.
                     // Idle columns (bit 31 of .y) take part except for the tuple store: their tuples must stay 0.0 (they are
                     // the zero-weight padding targets of the gather list) and their contribution slots lie past every river.
-                    double2 qold[2];
+                    double2 qold[R2_BC];
 #pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) qold[jj] = qbf_cur[ci[jp + jj].z & 0xffff];  // baseflow at the start of the step
+                    for (int jj = 0; jj < R2_BC; ++jj) qold[jj] = qbf_cur[ci[jp + jj].z & 0xffff];  // baseflow at the start of the step
 #pragma unroll
-                    for (int jj = 0; jj < 2; ++jj) {
+                    for (int jj = 0; jj < R2_BC; ++jj) {
                         const int j = jp + jj;
                         const int tup = ci[j].z & 0xffff, ctup = (int)((uint32_t)ci[j].w >> 16);
                         if (ci[j].y >= 0) qbf_nxt[tup] = make_double2(lo[jj][0].qbf, lo[jj][1].qbf);

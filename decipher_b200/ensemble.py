@@ -25,6 +25,21 @@ def run_members_sharded(cat: capi.Catchment, mcpar: np.ndarray, rank: int = 0, w
     return out
 
 
+def run_members_all_devices(cat: capi.Catchment, mcpar: np.ndarray, n_devices: Optional[int] = None, devices: Optional[Sequence[int]] = None,
+                            **run_kw) -> Dict:
+    """Single-process multi-GPU run through the C ABI (dcp_comm_init + dcp_run_ensemble_multi): one host thread per
+    device inside the library, contiguous member blocks of the ONE table `mcpar`, one NCCL gather of the measures at
+    the end (BASELINE config 3 without torchrun).  `devices` may repeat a device (several ranks on one GPU: testing)."""
+    if devices is None:
+        n = n_devices if n_devices is not None else capi.load_library().dcp_device_count()
+        devices = list(range(n))
+    comm = capi.Communicator(len(devices), devices=list(devices))
+    try:
+        return comm.run(cat, np.asfortranarray(mcpar), **run_kw)
+    finally:
+        comm.close()
+
+
 def run_catchments(catchments: Sequence[capi.Catchment], mcpars: Sequence[np.ndarray], rank: int = 0, world: int = 1,
                    device: Optional[int] = None, **run_kw) -> Dict[int, Dict]:
     """Multi-catchment run: catchments are dealt to ranks longest-processing-time first by

@@ -48,6 +48,21 @@ def test_multi_rank_over_nccl_when_two_gpus_are_visible():
     comm.close()
 
 
+def test_ensemble_driver_all_devices_with_signatures():
+    """decipher_b200.ensemble.run_members_all_devices (two ranks on device 0 here) incl. the flow-duration signatures,
+    which every rank writes straight into its block of the caller's table."""
+    from decipher_b200.ensemble import run_members_all_devices
+    cat = synth.synth_catchment(nac=700, nriv=3, npt=1, ngp=4, nge=1, nstep=500, kW=8, seed=4242)      # wide resident kernel
+    table = synth.sample_parameters(cat.npt, 33)
+    dev = DeviceCatchment(cat)
+    want = dev.run(table.copy(order="F"), flags=OPT_FAST_MATH, want_sig=True)
+    dev.close()
+    got = run_members_all_devices(cat, table.copy(order="F"), devices=[0, 0], flags=OPT_FAST_MATH, want_sig=True)
+    assert np.array_equal(got["perf"], want["perf"], equal_nan=True) and got["stats"]["kernel_used"] == 2
+    assert np.array_equal(got["sig"], want["sig"], equal_nan=True)
+    assert np.isfinite(want["sig"][:3]).all() and (want["sig"][0] >= want["sig"][2]).all()
+
+
 def test_communicator_rejects_bad_devices():
     from decipher_b200.capi import DecipherError
     with pytest.raises(DecipherError):
