@@ -175,7 +175,11 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(secs) / len(secs),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, cat, 1, {"note": "bounded member sample per step, see cpu_baseline.sample"}),
+            # same keys as the GPU arm's config (the driver compares the two lines); the CPU arm times a bounded member sample
+            "config": workload_config(args, cat, 1, {
+                "kernel": "cpu", "math": "exact", "distinct_members_simulated": int(info["sample"].split()[0]) * (args.warmup + args.steps),
+                "l2": "n/a (host cores)", "parallelism": f"{cores} host threads over disjoint members (C++ port of the reference path); "
+                                                         "bounded member sample per step, see cpu_baseline.sample"}),
             "cpu_baseline": info,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
