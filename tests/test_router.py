@@ -15,6 +15,38 @@ def _network(tree=True, nriv=4, nstep=400, seed=7):
     return synth.synth_catchment(nac=24, nriv=nriv, npt=1, nstep=nstep, tree=tree, seed=seed)
 
 
+def _with_sea_outlet(cat, reach_m=4000.0, cell_m=50.0):
+    """The network `route_run_standalone` also accepts (DTA/route_run_standalone.f90:139-151): a first node that is an
+    UNGAUGED sea outlet (node type 1) below the old outlet.  The flow input then has no column for it and column i feeds
+    node i + 1; outputs stay `flow_output_indexes(k) = k` (route_processing_init, dta_route_processing.f90:141-148, counts the
+    gauge nodes but stores the COUNTER, not the node index): output k reads node k -- the sea node first, the last gauge
+    never.  That is the reference's behaviour and it is reproduced, not corrected."""
+    import dataclasses
+    nn = cat.nnode
+    down_old = np.asarray(cat.meta["down"])
+    down = np.concatenate([[0], np.where(down_old > 0, down_old + 1, 1)]).astype(np.int32)      # old outlet drains to the sea node
+    _, tree = synth.full_upstream(down)
+    nc = int(round(reach_m / cell_m))
+    rd = cat.river_data.copy()
+    rd[:, 2] += reach_m; rd[:, 6] += reach_m                              # dist, ds_dist of every old cell move up by the new reach
+    sea = np.zeros((nc, 8))
+    sea[:, 0] = 900.0                                                     # riv_id of the sea node
+    sea[:, 1] = 2500.0                                                    # cell area
+    sea[:, 6] = np.arange(nc) * cell_m                                    # ds_dist
+    sea[:, 2] = sea[:, 6] + cell_m                                        # dist
+    sea[:, 3] = np.arange(nc) * cell_m                                    # section_dist
+    sea[:, 5] = 0.002
+    return dataclasses.replace(
+        cat, node_gauge_id=np.concatenate([[900], cat.node_gauge_id]).astype(np.int32),
+        node_type=np.concatenate([[1], cat.node_type]).astype(np.int32),
+        uptree_count=np.array([len(t) for t in tree], dtype=np.int32),
+        uptree_index=np.array([u for t in tree for u in t], dtype=np.int32),
+        frac_sub_area=np.concatenate([[1.0], cat.frac_sub_area]),
+        river_data=np.asfortranarray(np.vstack([sea, rd])),
+        node_to_flow_mapping=(np.arange(cat.nriv) + 2).astype(np.int32),
+        meta=dict(down=down))
+
+
 def _inflow(cat, n, seed=3):
     rng = np.random.default_rng(seed)
     x = rng.exponential(1e-4, size=(cat.nriv, cat.nstep, n)) * (rng.random((cat.nriv, cat.nstep, n)) < 0.3)
@@ -41,9 +73,12 @@ def _fir_reference(cat, v, inflow):
     return out
 
 
-@pytest.mark.parametrize("tree", [False, True])
-def test_oracle_router_matches_closed_form(tree):
+@pytest.mark.parametrize("tree,sea", [(False, False), (True, False), (True, True)])
+def test_oracle_router_matches_closed_form(tree, sea):
     cat = _network(tree=tree)
+    if sea:
+        cat = _with_sea_outlet(cat)
+        assert cat.nnode == cat.nriv + 1 and cat.node_type[0] == 1
     v = np.array([300.0, 1111.1, 5000.0])
     x = _inflow(cat, len(v))
     routed, status = oracle_route_timeseries(cat, v, x)
@@ -73,10 +108,12 @@ def test_oracle_router_linearity_and_mass():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("tree,nriv,nstep", [(False, 3, 700), (True, 5, 1500)])
-def test_gpu_router_bit_exact(tree, nriv, nstep):
+@pytest.mark.parametrize("tree,nriv,nstep,sea", [(False, 3, 700, False), (True, 5, 1500, False), (True, 4, 900, True)])
+def test_gpu_router_bit_exact(tree, nriv, nstep, sea):
     from decipher_b200.capi import DeviceCatchment
     cat = _network(tree=tree, nriv=nriv, nstep=nstep, seed=11)
+    if sea:                                                        # ungauged sea outlet as the first node (route_run_standalone.f90:139-151)
+        cat = _with_sea_outlet(cat)
     rng = np.random.default_rng(5)
     n = 37
     v = rng.uniform(150.0, 6000.0, n)
