@@ -6,6 +6,7 @@
 // {physics, routing convolution, gauge summation + objective}, then the finalize kernel.
 // No CPU compute path exists here: without a device every entry point fails.
 #include "dcp_kernels.h"
+#include "dcp_fastmath.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -345,6 +346,7 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     Q.off_cold = take((size_t)H * TC * 16 * COLW);
     Q.off_rbeg = take((size_t)(nriv + 1) * 4);
     Q.off_eq0 = take(wide ? (size_t)H * TC * 8 : 0);
+    Q.off_fmtab = take(wide ? 0 : (size_t)(FM_EXP_TAB + 2 * FM_LOG_TAB) * 8);
     Q.off_team = (int)((off + 127) & ~(size_t)127);
     off = 0;
     Q.off_qbf = take((size_t)2 * COLS * 16);
@@ -367,6 +369,11 @@ void build_plan2(dcp_catchment *c, const dcp_catchment_desc *d, const std::vecto
     auto up = [&](auto &vec, auto **dst) { if (e == cudaSuccess) e = upload(vec, dst, c->owned); };
     up(ent, &Q.ell_w); up(col_i, &Q.col_i); up(col_d, &Q.col_d); up(col_ia, &Q.col_ia);
     if (wide) up(eq0, &Q.eq0);
+    {
+        std::vector<double> fm_tab(FM_EXP_TAB + 2 * FM_LOG_TAB);
+        fm_build_tables(fm_tab.data(), fm_tab.data() + FM_EXP_TAB);
+        up(fm_tab, &Q.fm_tab);
+    }
     up(rbeg, &Q.rbeg); up(pet_pos, &Q.pet_pos);
     up(job_node, &Q.job_node); up(job_gauge, &Q.job_gauge); up(gauge_job_beg, &Q.gauge_job_beg);
     std::vector<double> inv_frac(nriv), obs_eps(nriv), log_obs(qobs.size(), 0.0);
@@ -1281,12 +1288,16 @@ int dcp_select_behavioural(const double *perf, int64_t n_member, int32_t nriv, i
 
 int dcp_debug_fastmath(int op, int64_t n, const double *x, double *y) {
     if (dcp_device_count() < 1) return fail(DCP_ERR_NO_DEVICE, "no CUDA device");
-    if (op < 0 || op > 2 || n < 1 || !x || !y) return fail(DCP_ERR_INVALID, "bad argument");
-    DevBuf bx, by;
+    if (op < 0 || op > 4 || n < 1 || !x || !y) return fail(DCP_ERR_INVALID, "bad argument");
+    DevBuf bx, by, bt;
     CUDA_TRY(bx.reserve(n * 8));
     CUDA_TRY(by.reserve(n * 8));
+    std::vector<double> tab(FM_EXP_TAB + 2 * FM_LOG_TAB);
+    fm_build_tables(tab.data(), tab.data() + FM_EXP_TAB);
+    CUDA_TRY(bt.reserve(tab.size() * 8));
+    CUDA_TRY(cudaMemcpy(bt.p, tab.data(), tab.size() * 8, cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(bx.p, x, n * 8, cudaMemcpyHostToDevice));
-    dcp_launch_debug_fastmath(op, n, (const double *)bx.p, (double *)by.p, 0);
+    dcp_launch_debug_fastmath(op, n, (const double *)bx.p, (double *)by.p, (const double *)bt.p, 0);
     CUDA_TRY(cudaMemcpy(y, by.p, n * 8, cudaMemcpyDeviceToHost));
     return DCP_OK;
 }

@@ -202,7 +202,7 @@ struct Res2Plan {
     int32_t smem_bytes, team_bytes;
     int32_t off_team;               // start of the team-private region; offsets below off_forc.. are relative to a team's base
     int32_t off_qbf, off_con, off_cst, off_par, off_forc, off_bar, off_job, off_acc;
-    int32_t off_ellw, off_coli, off_cold, off_rbeg, off_eq0;       // shared, absolute
+    int32_t off_ellw, off_coli, off_cold, off_rbeg, off_eq0, off_fmtab;   // shared, absolute
     int32_t wide;                   // 1: plan of the wide build (one team, 1024 columns)
     const double *ell_w;            // [ell_len] w * ac(src)   (dyna_dynamic_dist.f90:50-51), 0 in padding; the low 9
                                     //           mantissa bits hold the source's tuple index (0..511)
@@ -211,6 +211,7 @@ struct Res2Plan {
     const double2 *col_d;           // [4][128][2] {ac, 1/ac}, {dtt*w_riv*share*ac, cos(mslp)}
     const int32_t *col_ia;          // [4][128] HRU of the column (-1 idle)
     const double *eq0;              // wide build: [4][256] exp(-st) of the column
+    const double *fm_tab;           // narrow build: [64 + 256] tables of fm_exp_tab / fm_log_tab (dcp_fastmath.cuh)
     const int32_t *rbeg;            // [nriv+1] contribution-slot ranges per river
     // routing inside the kernel: jobs of ONE member (gauge i x node u in {i} + upstream tree of i, gauge-major, own node first)
     int32_t jobs_per_member;

@@ -171,3 +171,69 @@ FM_HD double fm_log(double x) {
     // log(x) = k*ln2_hi - ((hfsq - (s*(hfsq+R) + k*ln2_lo)) - f)
     return FM_FMA(dk, FMC(1), -((hfsq - FM_FMA(s, hfsq + R, dk * FMC(2))) - f));
 }
+
+// ------------------------------------------------------------------------------------------------
+// Table-driven exp / log for the second-generation resident kernel: a short table in SHARED memory replaces most of
+// the polynomial -- 10 FP64 instructions per exp (16 above) and 12 per log (25 above).  The physics blocks of that kernel
+// are FP64-pipe bound whenever both teams of a sub-partition are inside one.
+//   fm_exp_tab : x = (64 k2 + j) ln2/64 + r, |r| <= ln2/128:  exp(x) = 2^k2 T[j] (1 + r + r^2/2 + ... + r^5/120),
+//                T[j] = 2^(j/64) (64 doubles); truncation r^6/720 < 4e-17.  Valid for |x| <= 700.
+//   fm_log_tab : x = 2^k m, m in [1, 2), j = top 7 mantissa bits, c_j ~ 1/m: r = m c_j - 1 in ONE rounding (|r| < 2^-7.9),
+//                log(x) = (k + a_j) ln2 + L[j] + log1p(r) with log1p by its series to r^7; for m above sqrt(2), a_j = 1 and
+//                L[j] = -log(c_j) - ln2, so that x near 1 takes k + a_j = 0 and a small L[j] (no cancellation).
+//                128 pairs {c_j, L[j]}.  Valid for finite normal x > 0.
+// fm_build_tables fills both tables on the host in long double; the kernels copy them to shared memory once per CTA.
+// ------------------------------------------------------------------------------------------------
+#define FM_EXP_TAB 64
+#define FM_LOG_TAB 128
+#define FM_LOG_SPLIT 53               // first j whose interval midpoint 1 + (j + 0.5)/128 lies above sqrt(2)
+inline void fm_build_tables(double *etab /*[FM_EXP_TAB]*/, double *ltab /*[2 * FM_LOG_TAB]: c_j, L_j*/) {      // host only
+    for (int j = 0; j < FM_EXP_TAB; ++j) etab[j] = (double)exp2l((long double)j / FM_EXP_TAB);
+    for (int j = 0; j < FM_LOG_TAB; ++j) {
+        const long double mid = 1.0L + ((long double)j + 0.5L) / FM_LOG_TAB;
+        const double c = (double)(1.0L / mid);
+        long double L = -logl((long double)c);
+        if (j >= FM_LOG_SPLIT) L -= 0.693147180559945309417232121458L;
+        ltab[2 * j] = c;
+        ltab[2 * j + 1] = (double)L;
+    }
+}
+
+FM_HD double fm_exp_tab(double x, const double *etab) {
+    const double t = FM_FMA(x, 92.332482616893656768, FMC(3));            // 64 / ln2; magic 1.5 * 2^52: k = nearest integer
+    const int32_t k = fm_lo(t);
+    const double kf = t - FMC(3);
+    double r = FM_FMA(kf, -0x1.62e42fee00000p-7, x);                      // ln2/64 hi: 21 trailing zero bits, kf * hi is exact
+    r = FM_FMA(kf, -0x1.a39ef35793c76p-39, r);                            // ln2/64 lo
+    const double T = etab[k & (FM_EXP_TAB - 1)];
+    double q = FM_FMA(r, 8.3333333333333332e-03, 4.1666666666666664e-02);  // 1/120, 1/24
+    q = FM_FMA(q, r, 1.6666666666666666e-01);
+    q = FM_FMA(q, r, 0.5);
+    q = FM_FMA(q, r, 1.0);
+    const double y = FM_FMA(T * r, q, T);                                 // T (1 + r q)
+    return fm_make(fm_hi(y) + ((k >> 6) << 20), fm_lo(y));                // * 2^(k >> 6); y in [1, 2.01), stays normal for |x| <= 700
+}
+
+FM_HD double fm_log_tab(double x, const double *ltab) {
+    const int32_t hi = fm_hi(x);
+    const int32_t j = (hi >> 13) & (FM_LOG_TAB - 1);
+    const int32_t k = (hi >> 20) - 1023 + (j >= FM_LOG_SPLIT ? 1 : 0);
+    const double m = fm_make((hi & 0x000fffff) | 0x3ff00000, fm_lo(x));  // [1, 2)
+#if defined(__CUDA_ARCH__)
+    const double2 cl = reinterpret_cast<const double2 *>(ltab)[j];      // one 16-byte load (the table is 16-byte aligned)
+    const double c = cl.x, L = cl.y;
+#else
+    const double c = ltab[2 * j], L = ltab[2 * j + 1];
+#endif
+    const double r = FM_FMA(m, c, -1.0);
+    // log1p(r) = r - r^2/2 + r^3/3 - ... + r^7/7, |r| < 2^-7.9: next term r^8/8 < 2^-66
+    double p = FM_FMA(r, 1.4285714285714285e-01, -1.6666666666666666e-01);
+    p = FM_FMA(p, r, 0.2);
+    p = FM_FMA(p, r, -0.25);
+    p = FM_FMA(p, r, 3.3333333333333331e-01);
+    p = FM_FMA(p, r, -0.5);
+    const double dk = (double)k;
+    const double r2 = r * r;
+    // (k ln2_hi + L) carries the large part; the series and k ln2_lo are added last
+    return FM_FMA(dk, FMC(1), L) + (FM_FMA(r2, p, r) + dk * FMC(2));
+}

@@ -734,16 +734,19 @@ __global__ void __launch_bounds__(256) k_fp64_peak(double *out, int iters, doubl
     out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
-// device evaluation of the fast-math primitives (accuracy tests): op 0 exp, 1 log, 2 rcp
-__global__ void k_debug_fastmath(int op, int64_t n, const double *__restrict__ x, double *__restrict__ y) {
+// device evaluation of the fast-math primitives (accuracy tests): op 0 exp, 1 log, 2 rcp, 3 table exp, 4 table log
+__global__ void k_debug_fastmath(int op, int64_t n, const double *__restrict__ x, double *__restrict__ y, const double *__restrict__ tab) {
+    __shared__ double tab_s[FM_EXP_TAB + 2 * FM_LOG_TAB];
+    for (int i = threadIdx.x; i < FM_EXP_TAB + 2 * FM_LOG_TAB; i += blockDim.x) tab_s[i] = tab[i];
+    __syncthreads();
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const double v = x[i];
-        y[i] = op == 0 ? fm_exp(v) : (op == 1 ? fm_log(v) : fm_rcp(v));
+        y[i] = op == 0 ? fm_exp(v) : op == 1 ? fm_log(v) : op == 2 ? fm_rcp(v) : op == 3 ? fm_exp_tab(v, tab_s) : fm_log_tab(v, tab_s + FM_EXP_TAB);
     }
 }
 
-void dcp_launch_debug_fastmath(int op, int64_t n, const double *x, double *y, cudaStream_t s) {
-    k_debug_fastmath<<<592, 256, 0, s>>>(op, n, x, y);
+void dcp_launch_debug_fastmath(int op, int64_t n, const double *x, double *y, const double *tab, cudaStream_t s) {
+    k_debug_fastmath<<<592, 256, 0, s>>>(op, n, x, y, tab);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -40,4 +40,4 @@ cudaError_t dcp_launch_physics_resident_v2w(const DevCatchment &C, const DevBatc
                                             int grid, cudaStream_t s);
 cudaError_t dcp_launch_physics_stepwise(const DevCatchment &C, const DevBatch &W, const DensePlan &D, int t0, int t1,
                                         bool fast, bool aet, bool dense, int n_sm, cudaStream_t s);
-void dcp_launch_debug_fastmath(int op, int64_t n, const double *x, double *y, cudaStream_t s);
+void dcp_launch_debug_fastmath(int op, int64_t n, const double *x, double *y, const double *tab, cudaStream_t s);

@@ -24,6 +24,7 @@ struct HruConst {            // per (HRU, member) constants for one step
 struct StepConst {
     double dt, dtt, inv_dtt;
     int ntt;
+    const double *etab = nullptr, *ltab = nullptr;   // shared-memory tables of fm_exp_tab / fm_log_tab (hru_step_lean<., ., true>)
 };
 
 struct HruState {
@@ -243,7 +244,8 @@ struct LeanOut {
 // being recomputed (one exp and the quotient correction less per step).  The stored sd stays the rounded
 // m2*log(arg), consistent with the carried value to an ulp each step, so nothing drifts; callers re-derive e1
 // with exp() whenever they replace sd (slow path, initial state).
-template <bool CARRY = false, bool FOLD = false>
+// TAB: table-driven exp / log (dcp_fastmath.cuh: 22 FP64 instructions instead of 41 for the pair)
+template <bool CARRY = false, bool FOLD = false, bool TAB = false>
 __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst &g, double p, double epp,
                                               double qin, HruState &s, LeanOut &o) {
     // root_zone1 (dyna_root_zone1.f90:39-66)
@@ -288,12 +290,12 @@ __device__ __forceinline__ void hru_step_lean(const HruConst &c, const StepConst
         e1 = LEAN_EXP(x1);
     }
     const double r = LEAN_DIV(c.q1, u2);
-    const double e2 = LEAN_EXP(-a);
+    const double e2 = TAB ? fm_exp_tab(-a, g.etab) : LEAN_EXP(-a);
     const double b = FOLD ? c.q1 * c.dtt_inv_m2 : (c.q1 * g.dtt) * c.inv_m2;
     const double arg_small = (e1 + b) - a * (e1 - 0.5 * b);      // :76-77 (and :84 when u2 == 0)
     const double arg_reg = fma(e1 - r, e2, r);                    // :80
     const double arg = fm_sel_lt(a, DCP_F32_1EM10, arg_small, arg_reg);
-    double sd = c.m2 * LEAN_LOG(arg);
+    double sd = c.m2 * (TAB ? fm_log_tab(arg, g.ltab) : LEAN_LOG(arg));
     // rare cases: sd0 > smax, exponential arguments beyond 700, an argument of the logarithm that is not a positive
     // finite number in [2^-963, 2^964) (one unsigned compare of the exponent bits; it rejects the sign bit too)
     const bool arg_ok = (uint32_t)(fm_hi(arg) - 0x03c00000) < (uint32_t)(0x7c300000 - 0x03c00000);

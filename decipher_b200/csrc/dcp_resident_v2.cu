@@ -107,6 +107,9 @@
 #define R2_BC 2                       // columns per physics block: R2_BC x 2 member slots = 4 interleaved dependency chains
                                       // (4 columns = 8 chains spill and lose 17 %: 6.56e10 vs 7.93e10, profiles/r2_ab_routing_designs.txt)
 #endif
+#ifndef R2_TAB
+#define R2_TAB (R2_WIDE ? 2 : 1)      // table-driven exp / log in the lean step (dcp_fastmath.cuh): 1 = tables in shared memory (2.5 KB),
+#endif                                // 2 = read through L1 from global memory (the wide build has no shared memory left), 0 = polynomials
 #ifndef R2_CARRY_E1
 #define R2_CARRY_E1 1                 // carry exp(sd/m2) from step to step instead of recomputing it (dcp_physics.cuh)
 #endif
@@ -128,6 +131,7 @@ struct R2Smem {                       // team-private views unless noted
     double2 *cold_s;      // [3][4][128]     word 0: {ac, 1/ac}, 1: {cq, cos(mslp)}, 2: {1/cos(mslp), -}; thread-fastest
                           //                 WIDE: [2][4][256] word 0: {ac, cq}, 1: {cos(mslp), 1/cos(mslp)}
     double *eq0_s;        // WIDE: [4][256]  exp(-st) of the column (q0 = exp(t0dt) * exp(-st), dyna_init_satzone.f90:108)
+    double *fmtab_s;      // R2_TAB: [64 + 256] tables of fm_exp_tab / fm_log_tab
     int32_t *rbeg_s;      // [nriv+1]
 };
 
@@ -148,7 +152,7 @@ __device__ __forceinline__ double2 lds_tuple(int lo, uint32_t buf_u32) {
 
 __device__ __forceinline__ void team_sync(int team) { asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "n"(R2_TT) : "memory"); }
 
-#define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt})
+#define gc (StepConst{C.dt, C.dtt, C.inv_dtt, C.ntt, M.fmtab_s, M.fmtab_s + FM_EXP_TAB})
 
 // Completes a unit whose lean step raised `slow` (sd > smax, exponent out of the fast range, non-finite): the generic
 // saturated-zone statements (hru_step_lean_fixup -> sat_zone_slow) from the saved inputs.  Kept OUT of the time loop's
@@ -498,7 +502,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #if R2_CARRY_E1
                             st.e1 = e1s[j][k];
 #endif
-                            hru_step_lean<R2_CARRY_E1 != 0, true>(c, gc, p, epp, qin[j][k], st, lo[jj][k]);
+                            hru_step_lean<R2_CARRY_E1 != 0, true, R2_TAB != 0>(c, gc, p, epp, qin[j][k], st, lo[jj][k]);
                             sd[j][k] = st.sd; suz[j][k] = st.suz; srz[j][k] = st.srz;  // ntt == 1: qint1 is not carried
 #if R2_CARRY_E1
                             e1s[j][k] = st.e1;
@@ -715,6 +719,8 @@ __global__ void __launch_bounds__(R2_THREADS, 1) R2_KERNEL(DevCatchment C, DevBa
     M.coli_s = (int4 *)(smem + P.off_coli);
     M.cold_s = (double2 *)(smem + P.off_cold);
     M.eq0_s = (double *)(smem + P.off_eq0);
+    M.fmtab_s = R2_TAB == 2 ? const_cast<double *>(P.fm_tab) : (double *)(smem + P.off_fmtab);
+    if (R2_TAB == 1) for (int i = tid; i < FM_EXP_TAB + 2 * FM_LOG_TAB; i += R2_THREADS) M.fmtab_s[i] = P.fm_tab[i];
     M.rbeg_s = (int32_t *)(smem + P.off_rbeg);
 
     for (int e = tid; e < P.ell_len; e += R2_THREADS) M.ellw_s[e] = P.ell_w[e];

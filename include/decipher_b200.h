@@ -294,7 +294,7 @@ int  dcp_gather_bytes(dcp_comm *c, const void *const *send, const size_t *bytes,
 int  dcp_measure_fp64_peak(double *tflops, double *ms);
 
 /* Test hook: evaluates the FAST policy's branch-free primitives on the device
-   (op 0: exp, 1: log, 2: reciprocal) for host arrays x -> y; used by the accuracy tests. */
+   (op 0: exp, 1: log, 2: reciprocal, 3: table-driven exp, 4: table-driven log) for host arrays x -> y; used by the accuracy tests. */
 int  dcp_debug_fastmath(int op, int64_t n, const double *x, double *y);
 
 #ifdef __cplusplus

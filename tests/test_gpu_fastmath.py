@@ -34,3 +34,19 @@ def test_fast_exp_log_rcp_within_two_ulp():
     assert l[np.abs(np.log(y)) > 1e-3].max() <= 2.0
     assert np.abs(_dev(1, y) - np.log(y))[np.abs(np.log(y)) <= 1e-3].max() < 1e-18
     assert r.max() <= 1.5
+
+
+def test_table_driven_exp_log():
+    """fm_exp_tab / fm_log_tab (the lean step of the second-generation resident kernel): 64- and 128-entry shared-memory
+    tables + short polynomials.  exp within 2 ulp; log within 3 ulp where |log| > 1e-3 and 1e-18 absolute near 1."""
+    rng = np.random.default_rng(5)
+    x = np.concatenate([rng.uniform(-700, 700, 400000), rng.uniform(-1, 1, 200000), rng.uniform(-1e-6, 1e-6, 1000)])
+    e = _ulps(_dev(3, x), np.exp(x))
+    y = np.concatenate([np.exp(rng.uniform(-690, 690, 400000)), rng.uniform(0.5, 2.0, 200000), rng.uniform(0.999, 1.001, 50000)])
+    ref = np.log(y)
+    got = _dev(4, y)
+    big = np.abs(ref) > 1e-3
+    l = np.abs(got - ref)[big] / np.spacing(np.abs(ref[big]))
+    print("table exp max ulp %.2f, table log max ulp %.2f, near 1 max abs %.2e" % (e.max(), l.max(), np.abs(got - ref)[~big].max()))
+    assert e.max() <= 2.0 and l.max() <= 3.5
+    assert np.abs(got - ref)[~big].max() < 1e-18
