@@ -405,11 +405,7 @@ __device__ __forceinline__ void r2_compute(const DevCatchment &C, const DevBatch
 #pragma unroll
                     for (int j = jp; j < jp + R2_BC; ++j) {
                         ci[j] = M.coli_s[j * R2_TC + tt_id];
-#ifdef R2_TUNE_NO_GATHER                                                                // timing experiment only (wrong results)
-                        const int nb = 0;
-#else
                         const int nb = (ci[j].x >> 20) / GB;                            // K / batch, warp-uniform
-#endif
                         // R2_NACC independent partial sums per member slot: a row of K entries is K dependent DFMAs per
                         // slot otherwise (8.9 cycles each), the longest chain of the gather phase
                         double qa[R2_NACC][2];
