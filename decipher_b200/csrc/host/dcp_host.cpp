@@ -11,6 +11,7 @@
 #include <fstream>
 #include <sstream>
 #include <stdexcept>
+#include <memory>
 #include <string>
 #include <vector>
 
@@ -82,6 +83,7 @@ public:
         return (int)v;
     }
     bool at_end() const { return rec_ >= lines_.size(); }
+    std::string peek_record() const { return rec_ < lines_.size() ? lines_[rec_] : std::string(); }   // next record, not consumed
     size_t record_index() const { return rec_; }
     void rewind() { rec_ = 0; col_ = std::string::npos; }
     // counts the records from the cursor that hold at least one token (read(fid,*,iostat=io) tmp loop)
@@ -179,6 +181,9 @@ struct dcph_model {
     std::vector<double> ll, ul;          // [npt x 7]
     std::string out_prefix, log_path, proj_dir;
     std::vector<std::string> log;
+    // standalone router (dcph_load_router): the input series in the ABI layout [nriv x nstep] and the output column headers
+    std::vector<double> router_inflow;
+    std::vector<std::string> router_headers;
 };
 
 namespace {
@@ -646,6 +651,107 @@ int dcph_load_project(const char *workdir, int id_project, int id_cat, int id_fl
         delete M;
         return DCP_ERR_INVALID;
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Standalone router front end (DTA/route_run_standalone.f90:83-189): route_processing_read_info (flow tree + river data) and the
+// ASCII-grid flow series (dta_utility.f90:519-580: one ROW per timestep, one COLUMN per input point).  The series has one column
+// per node, or one column less when the first node is an ungauged sea outlet (route_run_standalone.f90:139-151: column i then
+// feeds node i + 1).  The HRU part of the descriptor is a placeholder (one HRU per input, no forcing): dcp_route_timeseries
+// only uses the river network.
+// ------------------------------------------------------------------------------------------------
+int dcph_load_router(const char *river_data_file, const char *flow_conn_file, const char *timeseries_file, dcph_model **out) {
+    if (!river_data_file || !flow_conn_file || !timeseries_file || !out) { g_err = "null argument"; return DCP_ERR_INVALID; }
+    *out = nullptr;
+    try {
+        std::unique_ptr<dcph_model> M(new dcph_model());
+        const std::string conn = flow_conn_file;
+        if (conn.size() < 14) die("-tree: '%s' is not a *_flow_conn.txt file", conn.c_str());
+        const std::string point = conn.substr(0, conn.size() - 14) + "_flow_point.txt";          // dta_route_processing.f90:72
+        // ---- ASCII grid (read_ascii_grid): header of 5 or 6 records, then nrows records of ncols values ----
+        Unit u(timeseries_file);
+        auto header = [&](const char *name) {
+            u.begin_list();
+            const std::string key = u.token();
+            std::string a = key, b = name;
+            for (auto &c : a) c = (char)tolower(c);
+            for (auto &c : b) c = (char)tolower(c);
+            if (a != b) die("invalid ascii grid '%s': expected %s, found %s", timeseries_file, name, key.c_str());
+            const double v = u.real();
+            u.end_list();
+            return v;
+        };
+        const int ncols = (int)header("ncols"), nrows = (int)header("nrows");
+        header("xllcorner"); header("yllcorner"); header("cellsize");
+        {   // optional nodata record (dta_utility.f90:548-556): anything else is already grid data
+            const std::string rec = u.peek_record();
+            std::string low = rec;
+            for (auto &c : low) c = (char)tolower(c);
+            if (low.find("nodata") != std::string::npos) u.skip_record();
+        }
+        if (ncols < 1 || nrows < 1) die("ascii grid '%s': ncols / nrows must be positive", timeseries_file);
+        M->router_inflow.assign((size_t)ncols * nrows, 0.0);
+        for (int t = 0; t < nrows; ++t) {
+            u.begin_list();
+            for (int i = 0; i < ncols; ++i) M->router_inflow[(size_t)t * ncols + i] = u.real();     // ABI layout: input column fastest
+            u.end_list();
+        }
+        // ---- placeholder HRU part: one HRU per input column ----
+        dcp_catchment_desc &d = M->d;
+        const int nriv = ncols;
+        d.nac = nriv; d.nriv = nriv; d.npt = 1; d.nstep = nrows; d.ngp = 1; d.nge = 1; d.ntt = 1; d.dt = 1.0;
+        M->ac.assign(nriv, 1.0 / nriv); M->st.assign(nriv, 8.0); M->mslp.assign(nriv, 0.1);
+        M->ippt.assign(nriv, 1); M->ipet.assign(nriv, 1); M->ipar.assign(nriv, 1); M->ipriv.resize(nriv);
+        M->ims_rz.assign(nriv, 1); M->ims_uz.assign(nriv, 1); M->ntrans.assign(nriv, 0); M->itrans.clear();
+        M->wtrans.assign(nriv, 1.0); M->rivers.assign((size_t)nriv * nriv, 0.0);
+        for (int i = 0; i < nriv; ++i) { M->ipriv[i] = i + 1; M->rivers[(size_t)i * nriv + i] = 1.0; }
+        M->sum_ac_riv.assign(nriv, 1.0 / nriv); M->qobs_start.assign(nriv, 1e-5);
+        M->rain.assign(nrows, 0.0); M->pet.assign(nrows, 0.0);
+        read_routingdata(*M, conn, river_data_file, point);
+        const int nnode = d.nnode;
+        if (nriv == nnode) {                                                   // "flow file points matches nodes"
+            for (int i = 0; i < nriv; ++i) M->node_to_flow_mapping[i] = i + 1;
+        } else if (nriv + 1 == nnode) {                                        // no column for the sea outlet: column i -> node i + 1
+            for (int i = 0; i < nriv; ++i) M->node_to_flow_mapping[i] = i + 2;
+        } else {
+            die("timeseries_flow_input does not match the _flow_conn.txt: %d columns for %d nodes "
+                "(timeseries data must have one column for each node)", nriv, nnode);
+        }
+        for (int i = 0; i < nnode; ++i) M->frac_sub_area[i] = 1.0;
+        // output headers: gauge ids of the gauge nodes, in node order (route_processing_init, dta_route_processing.f90:141-148)
+        for (int i = 0; i < nnode; ++i)
+            if (M->node_type[i] == 2) M->router_headers.push_back(std::to_string(M->node_gauge_id[i]));
+        if ((int)M->router_headers.size() != nriv)
+            die("route_process_run_timeseries: error size mismatch (%d gauge nodes, %d flow columns)", (int)M->router_headers.size(), nriv);
+        finish_desc(*M);
+        d.qobs = nullptr; d.nstep_obs = 0;
+        *out = M.release();
+        return DCP_OK;
+    } catch (const std::exception &e) {
+        g_err = e.what();
+        return DCP_ERR_INVALID;
+    }
+}
+
+const double *dcph_router_inflow(const dcph_model *m) { return m ? m->router_inflow.data() : nullptr; }
+
+// write_numeric_list (DTA/dta_utility.f90:402-470): tab-separated headers, then one record per timestep in
+// '(1(F0.p) n-1(1x,F0.p))' -- gfortran's F0.d drops the leading zero
+int dcph_write_routed(const dcph_model *m, const double *routed /*[nriv x nstep]*/, const char *path, int precision, int f0_leading_zero) {
+    if (!m || !routed || !path) { g_err = "null argument"; return DCP_ERR_INVALID; }
+    FILE *f = fopen(path, "w");
+    if (!f) { g_err = std::string("error opening output file: ") + path; return DCP_ERR_INVALID; }
+    std::string hdr;
+    for (size_t i = 0; i < m->router_headers.size(); ++i) hdr += (i ? "\t" : "") + m->router_headers[i];
+    fprintf(f, "%s\n", hdr.c_str());
+    const int nriv = m->d.nriv;
+    for (int t = 0; t < m->d.nstep; ++t) {
+        std::string rec;
+        for (int i = 0; i < nriv; ++i) rec += (i ? " " : "") + fmt_F0(routed[(size_t)t * nriv + i], precision, f0_leading_zero != 0);
+        fprintf(f, "%s\n", rec.c_str());
+    }
+    fclose(f);
+    return DCP_OK;
 }
 
 void dcph_free(dcph_model *m) { delete m; }

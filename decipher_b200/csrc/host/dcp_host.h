@@ -58,6 +58,15 @@ void dcph_ranmar(int ij, int kl, int64_t n_skip, int64_t n, double *out);
 int dcph_write_member(const dcph_model *m, int64_t i_mc, const double *mcpar, const double *q,
                       const double *totals, const double *diag, int32_t status, int f0_leading_zero);
 
+/* Standalone router front end (DTA/route_run_standalone.f90): flow tree (*_flow_conn.txt + the *_flow_point.txt beside it), river
+ * data and the ASCII-grid flow series (one row per timestep, one column per node -- or one column less when the first node is an
+ * ungauged sea outlet).  dcph_desc() then describes the river network (placeholder HRUs) for dcp_catchment_create +
+ * dcp_route_timeseries; dcph_router_inflow() is the series in the ABI layout [nriv x nstep]; dcph_write_routed writes the routed
+ * series like write_numeric_list (tab-separated gauge ids, then '(1(F0.p) n-1(1x,F0.p))' records). */
+int dcph_load_router(const char *river_data_file, const char *flow_conn_file, const char *timeseries_file, dcph_model **out);
+const double *dcph_router_inflow(const dcph_model *m);
+int dcph_write_routed(const dcph_model *m, const double *routed, const char *path, int precision, int f0_leading_zero);
+
 #ifdef __cplusplus
 }
 #endif

@@ -133,3 +133,29 @@ def read_flow_table(path: str) -> Dict:
     ids = np.frombuffer(raw[32:32 + 8 * nsel], dtype=np.int64)
     q = np.frombuffer(raw[32 + 8 * nsel:], dtype=np.float64).reshape((nriv, nstep, nsel), order="F")
     return dict(members=ids, q=q)
+
+
+def write_router_inputs(cat, inflow: np.ndarray, root: str, stem: str = "net") -> Dict[str, str]:
+    """Files of the standalone router (DTA/route_run_standalone.f90): <stem>_flow_conn.txt + <stem>_flow_point.txt (routing tree),
+    <stem>_river_data.txt and the flow series as an ASCII grid (one row per timestep, one column per input point).
+    `cat` supplies the network (node ids / types, meta['down'], river_data); inflow is (n_points, nstep)."""
+    os.makedirs(root, exist_ok=True)
+    down = np.asarray(cat.meta["down"])
+    gid = np.asarray(cat.node_gauge_id)
+    nn = len(gid)
+    fp = np.array([(gid[n], 1000.0 + n, 2000.0 + n, cat.node_type[n], 0.0, 10.0) for n in range(nn)], dtype=np.float64)
+    fc = np.array([(gid[n], 1000.0 + n, 2000.0 + n, cat.node_type[n], gid[down[n] - 1] if down[n] > 0 else 0, 0.0, 0.0, 0.0, 1.0, 0.002)
+                   for n in range(nn)], dtype=np.float64)
+    paths = {k: os.path.join(root, f"{stem}_{k}.txt") for k in ("flow_conn", "flow_point", "river_data")}
+    np.savetxt(paths["flow_point"], fp, fmt="%.3f", delimiter="\t", header="Node_ID\tx_easting\ty_northing\tType\tdist\th", comments="")
+    np.savetxt(paths["flow_conn"], fc, fmt="%.3f", delimiter="\t",
+               header="Node_ID\tx\ty\tType\tID_down\tx2\ty2\tdelta_dist\tdelta_h\tslope", comments="")
+    np.savetxt(paths["river_data"], cat.river_data, fmt="%.3f", delimiter="\t",
+               header="riv_id\tarea\tdist\tsection_dist\televation\tslope\tds_dist\tds_elevation", comments="")
+    paths["timeseries"] = os.path.join(root, f"{stem}_flow.txt")
+    n_points, nstep = inflow.shape
+    with open(paths["timeseries"], "w") as f:
+        f.write(f"ncols {n_points}\nnrows {nstep}\nxllcorner 0\nyllcorner 0\ncellsize 1\nNODATA_value -9999\n")
+        for t in range(nstep):
+            f.write(" ".join(repr(float(v)) for v in inflow[:, t]) + "\n")
+    return paths

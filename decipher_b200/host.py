@@ -39,6 +39,10 @@ def load_host_library(path: str = HOST_LIB_PATH):
     lib.dcph_genpar.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     lib.dcph_ranmar.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
     lib.dcph_write_member.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
+    lib.dcph_load_router.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
+    lib.dcph_router_inflow.argtypes = [C.c_void_p]
+    lib.dcph_router_inflow.restype = C.POINTER(C.c_double)
+    lib.dcph_write_routed.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p, C.c_int, C.c_int]
     _lib = lib
     return lib
 
@@ -105,6 +109,46 @@ class Project:
         rc = self.lib.dcph_write_member(self._h, int(i_mc), *[x.ctypes.data_as(C.c_void_p) for x in a], int(status),
                                         int(bool(f0_leading_zero)))
         if rc != 0:
+            raise DecipherError(self.lib.dcph_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self.lib.dcph_free(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RouterInputs:
+    """The standalone router's inputs (DTA/route_run_standalone.f90) parsed by the C++ host: routing tree, river data and the
+    ASCII-grid flow series; `desc` describes the river network for dcp_catchment_create / dcp_route_timeseries."""
+
+    def __init__(self, river_data_file: str, flow_conn_file: str, timeseries_file: str):
+        self.lib = load_host_library()
+        self._h = C.c_void_p()
+        rc = self.lib.dcph_load_router(river_data_file.encode(), flow_conn_file.encode(), timeseries_file.encode(), C.byref(self._h))
+        if rc != 0:
+            raise DecipherError(f"dcph_load_router: {self.lib.dcph_last_error().decode()}")
+        self.desc = self.lib.dcph_desc(self._h).contents
+        d = self.desc
+        self.inflow = _arr(self.lib.dcph_router_inflow(self._h), d.nriv * d.nstep, np.float64).reshape((d.nriv, d.nstep), order="F")
+
+    def network(self):
+        d = self.desc
+        uc = _arr(d.uptree_count, d.nnode, np.int32)
+        return dict(nnode=d.nnode, nriv=d.nriv, nstep=d.nstep, node_gauge_id=_arr(d.node_gauge_id, d.nnode, np.int32),
+                    node_type=_arr(d.node_type, d.nnode, np.int32), uptree_count=uc,
+                    uptree_index=_arr(d.uptree_index, int(uc.sum()), np.int32),
+                    node_to_flow_mapping=_arr(d.node_to_flow_mapping, d.nriv, np.int32),
+                    river_data=_arr(d.river_data, d.ncell * 8, np.float64).reshape((d.ncell, 8), order="F"))
+
+    def write_routed(self, routed: np.ndarray, path: str, precision: int = 6, f0_leading_zero: bool = False):
+        a = np.ascontiguousarray(np.asarray(routed, dtype=np.float64).ravel(order="F"))
+        if self.lib.dcph_write_routed(self._h, a.ctypes.data_as(C.c_void_p), path.encode(), precision, int(f0_leading_zero)) != 0:
             raise DecipherError(self.lib.dcph_last_error().decode())
 
     def close(self):

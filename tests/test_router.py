@@ -73,6 +73,63 @@ def _fir_reference(cat, v, inflow):
     return out
 
 
+@pytest.mark.parametrize("sea", [False, True])
+def test_router_front_end_reads_the_reference_file_set(sea, tmp_path):
+    """The C++ host parses what DTA/route_run_standalone.f90 reads -- *_flow_conn.txt (+ the *_flow_point.txt beside it),
+    *_river_data.txt and the ASCII-grid flow series -- into the network the generator wrote, maps the series' columns to nodes
+    (one column less than nodes = ungauged sea outlet first: column i feeds node i + 1) and writes the routed series like
+    write_numeric_list."""
+    from decipher_b200 import formats, host
+    cat = _network(tree=True, nriv=4, nstep=60, seed=5)
+    if sea:
+        cat = _with_sea_outlet(cat)
+    x = _inflow(cat, 1)[:, :, 0]
+    paths = formats.write_router_inputs(cat, x, str(tmp_path))
+    r = host.RouterInputs(paths["river_data"], paths["flow_conn"], paths["timeseries"])
+    net = r.network()
+    assert net["nnode"] == cat.nnode and net["nriv"] == cat.nriv and net["nstep"] == cat.nstep
+    for k in ("node_gauge_id", "node_type", "uptree_count", "uptree_index", "node_to_flow_mapping"):
+        assert np.array_equal(net[k], getattr(cat, k)), k
+    assert np.array_equal(net["river_data"], cat.river_data) and np.array_equal(r.inflow, x)
+    out = str(tmp_path / "routed.txt")
+    r.write_routed(x * 1000.0, out)
+    lines = open(out).read().splitlines()
+    assert lines[0].split("\t") == [str(g) for g, t in zip(cat.node_gauge_id, cat.node_type) if t == 2]
+    vals = np.array([[float(v) for v in ln.split(" ")] for ln in lines[1:]]).T
+    assert vals.shape == x.shape and np.abs(vals - x * 1000.0).max() <= 0.5e-6 + 1e-12
+    assert not any(v.startswith("0.") for ln in lines[1:] for v in ln.split(" "))          # gfortran F0.6: ".123456"
+    r.close()
+    with pytest.raises(Exception):
+        host.RouterInputs(paths["river_data"], paths["flow_conn"], paths["river_data"])      # not an ASCII grid
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sea", [False, True])
+def test_router_cli_matches_oracle(sea, tmp_path):
+    """decipher_route_run (the reference executable's interface) end to end: files -> GPU router -> *_routed.txt, against the
+    oracle at the 6 decimals write_numeric_list prints; three velocities in one call."""
+    import os
+    import subprocess
+    from decipher_b200 import formats
+    cat = _network(tree=True, nriv=4, nstep=300, seed=9)
+    if sea:
+        cat = _with_sea_outlet(cat)
+    x = _inflow(cat, 1)[:, :, 0] * 1e3
+    paths = formats.write_router_inputs(cat, x, str(tmp_path))
+    exe = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "decipher_b200", "csrc", "build", "decipher_route_run")
+    v = [400.0, 1500.0, 5000.0]
+    r = subprocess.run([exe, "-river_data", paths["river_data"], "-tree", paths["flow_conn"], "-timeseries_in", paths["timeseries"],
+                        "-velocities", ",".join(str(a) for a in v)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    want, _ = oracle_route_timeseries(cat, np.array(v), np.asfortranarray(np.repeat(x[:, :, None], 3, axis=2)))
+    for s in range(3):
+        lines = open(paths["timeseries"][:-4] + f"_routed_{s + 1}.txt").read().splitlines()
+        got = np.array([[float(a) for a in ln.split(" ")] for ln in lines[1:]]).T
+        assert got.shape == want[:, :, s].shape and np.abs(got - want[:, :, s]).max() <= 0.5e-6 + 1e-12
+    bad = subprocess.run([exe, "-river_data", paths["river_data"]], capture_output=True, text=True, timeout=60)
+    assert bad.returncode == 2
+
+
 @pytest.mark.parametrize("tree,sea", [(False, False), (True, False), (True, True)])
 def test_oracle_router_matches_closed_form(tree, sea):
     cat = _network(tree=tree)
