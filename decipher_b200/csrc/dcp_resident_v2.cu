@@ -35,6 +35,14 @@
 //     an HRU class carries its gauge id); other catchments use the first generation.
 //   * blocks of 32 positions are dealt to the four compute warps longest-first (LPT) so that the
 //     per-step gather work of the warps is even.
+//   * (round 2) river ROUTING and the OBJECTIVE sums inside the kernel: the river warps store qout(t) into a ring per
+//     member in flight, and once per 64-step forcing tile the team's compute warps route the finished tile with lane =
+//     timestep (r2_route_tile: route_process_run_step, DTA/dta_route_processing.f90:671-727, + dyna_river.f90:57-59);
+//     only measures leave the chip.  Measured alternatives (routing warp, routing in the river warps, a split per-step
+//     barrier): profiles/r2_ab_routing_designs.txt.
+//   * (round 2) table-driven exp / log in the lean step (fm_exp_tab / fm_log_tab, tables in shared memory): 84 instead
+//     of 102 executed FP64 instructions per unit.
+//   * (round 2) a second build of this file, dcp_resident_v2w.cu, holds 1024 columns per member slot (513 .. 1024 HRUs).
 //
 // Built WITH FMA contraction (no operation-order contract in the lean policy; parity is checked against
 // the oracle at 1e-9).  Hot path citations: RRMODEL/dyna_topmod.f90:92-233, dyna_dynamic_dist.f90:47-67,
