@@ -27,8 +27,10 @@ program main
 
     ! ---- declarations of dyna_main.f90:33-79 (unchanged) ----
     integer :: seed_1, seed_2, i, nac, nstep, num_rivers
-    double precision, dimension(:,:), allocatable :: pe_step, r_gau_step, rivers
-    double precision, dimension(:), allocatable :: qobs_riv_step_start, sum_ac_riv
+    ! TARGET: their addresses go into the descriptor through c_loc
+    double precision, dimension(:,:), allocatable, target :: pe_step, r_gau_step
+    double precision, dimension(:,:), allocatable :: rivers
+    double precision, dimension(:), allocatable, target :: qobs_riv_step_start, sum_ac_riv
     type(dyna_hru_type), dimension(:), allocatable :: dyna_hru
     type(dyna_riv_type), dimension(:), allocatable :: dyna_riv
     type(route_river_info_type) :: route_riv
