@@ -754,6 +754,36 @@ int dcph_write_routed(const dcph_model *m, const double *routed /*[nriv x nstep]
     return DCP_OK;
 }
 
+// "-write-members 1:10,250,9000:9003" (decipher_b200_run): 1-based member ids, ranges inclusive -> ascending unique 0-based indexes.
+// Returns the count (<= cap entries are written), or -1 with dcph_last_error() set.
+int64_t dcph_parse_member_list(const char *list, int64_t numsim, int64_t *out, int64_t cap) {
+    if (!list) { g_err = "null member list"; return -1; }
+    std::vector<int64_t> sel;
+    const char *p = list;
+    while (*p) {
+        char *e = nullptr;
+        long long a = strtoll(p, &e, 10), b = a;
+        if (e == p) { g_err = std::string("-write-members: cannot parse '") + p + "'"; return -1; }
+        if (*e == ':') {
+            p = e + 1;
+            b = strtoll(p, &e, 10);
+            if (e == p) { g_err = "-write-members: range without an end"; return -1; }
+        }
+        if (a < 1 || b < a || b > numsim) {
+            g_err = "-write-members: " + std::to_string(a) + ":" + std::to_string(b) + " outside 1.." + std::to_string(numsim);
+            return -1;
+        }
+        for (long long m = a; m <= b; ++m) sel.push_back(m - 1);
+        p = e;
+        if (*p == ',') ++p;
+        else if (*p) { g_err = std::string("-write-members: unexpected '") + *p + "'"; return -1; }
+    }
+    std::sort(sel.begin(), sel.end());
+    sel.erase(std::unique(sel.begin(), sel.end()), sel.end());
+    for (int64_t i = 0; i < (int64_t)sel.size() && i < cap; ++i) out[i] = sel[i];
+    return (int64_t)sel.size();
+}
+
 void dcph_free(dcph_model *m) { delete m; }
 const dcp_catchment_desc *dcph_desc(const dcph_model *m) { return m ? &m->d : nullptr; }
 int dcph_numsim(const dcph_model *m) { return m ? m->numsim : 0; }

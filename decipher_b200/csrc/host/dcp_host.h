@@ -58,6 +58,9 @@ void dcph_ranmar(int ij, int kl, int64_t n_skip, int64_t n, double *out);
 int dcph_write_member(const dcph_model *m, int64_t i_mc, const double *mcpar, const double *q,
                       const double *totals, const double *diag, int32_t status, int f0_leading_zero);
 
+/* member selection of `decipher_b200_run -write-members 1:10,250` -> ascending unique 0-based indexes; returns the count or -1 */
+int64_t dcph_parse_member_list(const char *list, int64_t numsim, int64_t *out, int64_t cap);
+
 /* Standalone router front end (DTA/route_run_standalone.f90): flow tree (*_flow_conn.txt + the *_flow_point.txt beside it), river
  * data and the ASCII-grid flow series (one row per timestep, one column per node -- or one column less when the first node is an
  * ungauged sea outlet).  dcph_desc() then describes the river network (placeholder HRUs) for dcp_catchment_create +

@@ -88,20 +88,10 @@ int main(int argc, char **argv) {
     // members whose series are wanted on the host: all (reference behaviour), none (-no-flow) or the -write-members list
     std::vector<long> selected;                       // 0-based, ascending, unique
     if (!member_list.empty()) {
-        const char *p = member_list.c_str();
-        while (*p) {
-            char *e = nullptr;
-            long a = strtol(p, &e, 10), b = a;
-            if (e == p) { fprintf(stderr, "-write-members: cannot parse '%s'\n", p); return 2; }
-            if (*e == ':') { p = e + 1; b = strtol(p, &e, 10); if (e == p) { fprintf(stderr, "-write-members: bad range\n"); return 2; } }
-            if (a < 1 || b < a || b > numsim) { fprintf(stderr, "-write-members: %ld:%ld outside 1..%ld\n", a, b, numsim); return 2; }
-            for (long m = a; m <= b; ++m) selected.push_back(m - 1);
-            p = e;
-            if (*p == ',') ++p;
-            else if (*p) { fprintf(stderr, "-write-members: unexpected '%c'\n", *p); return 2; }
-        }
-        std::sort(selected.begin(), selected.end());
-        selected.erase(std::unique(selected.begin(), selected.end()), selected.end());
+        std::vector<int64_t> tmp((size_t)numsim);
+        const int64_t n_sel = dcph_parse_member_list(member_list.c_str(), numsim, tmp.data(), numsim);
+        if (n_sel < 0) { fprintf(stderr, "%s\n", dcph_last_error()); return 2; }
+        selected.assign(tmp.begin(), tmp.begin() + n_sel);
         write_text = true;
     } else if (write_text) {
         for (long m = 0; m < numsim; ++m) selected.push_back(m);

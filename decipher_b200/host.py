@@ -39,6 +39,8 @@ def load_host_library(path: str = HOST_LIB_PATH):
     lib.dcph_genpar.argtypes = [C.c_void_p, C.c_int64, C.c_void_p]
     lib.dcph_ranmar.argtypes = [C.c_int, C.c_int, C.c_int64, C.c_int64, C.c_void_p]
     lib.dcph_write_member.argtypes = [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int]
+    lib.dcph_parse_member_list.argtypes = [C.c_char_p, C.c_int64, C.c_void_p, C.c_int64]
+    lib.dcph_parse_member_list.restype = C.c_int64
     lib.dcph_load_router.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_void_p)]
     lib.dcph_router_inflow.argtypes = [C.c_void_p]
     lib.dcph_router_inflow.restype = C.POINTER(C.c_double)
@@ -161,6 +163,16 @@ class RouterInputs:
             self.close()
         except Exception:
             pass
+
+
+def parse_member_list(text: str, numsim: int) -> np.ndarray:
+    """`decipher_b200_run -write-members` syntax -> ascending unique 0-based member indexes (raises on a bad list)."""
+    lib = load_host_library()
+    out = np.empty(max(int(numsim), 1), dtype=np.int64)
+    n = lib.dcph_parse_member_list(text.encode(), int(numsim), out.ctypes.data_as(C.c_void_p), out.size)
+    if n < 0:
+        raise DecipherError(lib.dcph_last_error().decode())
+    return out[:n].copy()
 
 
 def ranmar(ij, kl, n_skip, n):

@@ -123,3 +123,16 @@ def test_compare_with_fortran_tool_on_oracle_written_files(tmp_path):
                        ref["init_diag"][:, m], int(ref["status"][m]))
     p.close()
     assert cwf.compare(root) == 0
+
+
+def test_member_selection_syntax():
+    """`-write-members` of decipher_b200_run (ensemble-scale output: text files for selected members only)."""
+    assert host.parse_member_list("3:5,17,40", 40).tolist() == [2, 3, 4, 16, 39]
+    assert host.parse_member_list("7,7,5:8,1", 10).tolist() == [0, 4, 5, 6, 7]
+    assert host.parse_member_list("1:100000", 100000).size == 100000
+    for bad in ("0:3", "5:4", "3:41", "a", "3;4", "3:", ""):
+        if bad == "":
+            assert host.parse_member_list(bad, 40).size == 0
+            continue
+        with pytest.raises(Exception):
+            host.parse_member_list(bad, 40)
