@@ -324,72 +324,4 @@ __device__ __forceinline__ void hru_step_lean_fixup(const HruConst &c, const Ste
     o.exac = (ex > 0.0) ? ex * c.ac : 0.0;
 }
 
-// ------------------------------------------------------------------------------------------------
-// The lean step in TWO halves (second-generation resident kernel with the split per-step barrier):
-//   hru_lean_upper  root_zone1 + unsat_zone1 of step t: needs only the unit's own stores, the deficit left by step
-//                   t-1 and the forcing of step t -- NOT the redistributed inflow qin(t), so it runs between a warp's
-//                   arrival at the step barrier and the moment every other warp of the team has arrived
-//                   (RRMODEL/dyna_topmod.f90:133-180: the three zones of an HRU are called in sequence, and only
-//                   satzone_analyticalsolver reads qin);
-//   hru_lean_sat    satzone_analyticalsolver + the results_ac contribution, after the gather.
-// Statement for statement the arithmetic of hru_step_lean<true, true>: the two halves return the same bits.
-// ------------------------------------------------------------------------------------------------
-struct LeanUpperConst { double srmax, inv_srmax, td_dt; };
 
-__device__ __forceinline__ void hru_lean_upper(const LeanUpperConst &c, double inv_dtt, double p, double epp, double sd0,
-                                               double &srz_io, double &suz_io, double &uz_o, double &exus_o, double &ea_o) {
-    // root_zone1 (dyna_root_zone1.f90:39-66)
-    double srz = srz_io + p;
-    const double pex = fm_relu(srz - c.srmax);
-    srz = srz - pex;
-    double ea = epp * (srz * c.inv_srmax);
-    ea = fm_min(ea, srz);
-    srz = srz - ea;
-    // unsat_zone1 (dyna_unsat_zone1.f90:49-78)
-    double suz = suz_io + pex;
-    const double lim = fm_relu(sd0);
-    const double exus = fm_relu(suz - lim);
-    suz = suz - exus;
-    const double den = sd0 * c.td_dt;
-    double uz2 = LEAN_DIV(suz, den);
-    uz2 = fm_min(uz2, suz);
-    suz = suz - uz2;
-    const double fl = fm_sel_lt(suz, 0.0000001, suz, 0.0);
-    uz2 = uz2 + fl;
-    suz = suz - fl;
-    srz_io = srz; suz_io = suz;
-    uz_o = uz2 * inv_dtt; exus_o = exus; ea_o = ea;
-}
-
-struct LeanSatConst { double ac, inv_ac, q0, q1, q2, m2, dtt_inv_m2, smax; };
-
-// returns `slow` (the unit needs the generic solver: r2_fix_unit)
-__device__ __forceinline__ bool hru_lean_sat(const LeanSatConst &c, double dtt, double inv_dtt, double qin, double uz, double exus,
-                                             double &sd_io, double &e1_io, double &qbf_o, double &exac_o) {
-    const double sd0 = sd_io;
-    const double qin_ac = qin * c.inv_ac;
-    const double u = qin_ac + uz;
-    const double u2 = c.q2 + u;
-    const double a = u2 * c.dtt_inv_m2;
-    const double e1 = e1_io;
-    const double r = LEAN_DIV(c.q1, u2);
-    const double e2 = LEAN_EXP(-a);
-    const double b = c.q1 * c.dtt_inv_m2;
-    const double arg_small = (e1 + b) - a * (e1 - 0.5 * b);      // :76-77 (and :84 when u2 == 0)
-    const double arg_reg = fma(e1 - r, e2, r);                    // :80
-    const double arg = fm_sel_lt(a, DCP_F32_1EM10, arg_small, arg_reg);
-    double sd = c.m2 * LEAN_LOG(arg);
-    const bool arg_ok = (uint32_t)(fm_hi(arg) - 0x03c00000) < (uint32_t)(0x7c300000 - 0x03c00000);
-    const bool slow = !(sd0 <= c.smax) || !(a <= 700.0) || !arg_ok;
-    double qbf = (sd - sd0) * inv_dtt + uz + qin_ac;              // :98
-    e1_io = fm_sel_lt(sd, 0.0, 1.0, arg);                         // exp(max(sd, 0)/m2)
-    double exs = fm_relu(-sd);                                    // :107-112
-    sd = sd + exs;
-    const double over = fm_relu(qbf - c.q0);                      // :115-119
-    exs = fma(over, dtt, exs);
-    qbf = qbf - over;
-    sd_io = sd;
-    qbf_o = qbf;
-    exac_o = (exs + exus) * c.ac;
-    return slow;
-}
