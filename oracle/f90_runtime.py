@@ -1,0 +1,462 @@
+"""f90_runtime.py -- TEST INFRASTRUCTURE (never imported by the product path).
+
+Run-time support for the Python text that `oracle/f90_translate.py` produces from the reference's own Fortran source
+files.  It fixes the semantics the translated statements rely on:
+
+* scalars: Fortran `integer` = Python int, `real` = numpy.float32, `double precision` = numpy.float64.  NumPy 2's
+  promotion rules (NEP 50) then give Fortran's mixed-mode arithmetic: int*real -> real, real*double -> double with the
+  single-precision value WIDENED (so the literal 0.0000001 in a double expression is float(np.float32(1e-7)), as a Fortran
+  compiler evaluates it), int/int truncates (`f_div`).
+* exp / log / cos go through the C library (`math`), the same libm a gfortran build of the reference calls.
+* arrays: `FArr`, 1-based (or declared lower bounds), column-major index order, sections are views, whole-array
+  arithmetic elementwise, `sum` left to right in element order (what gfortran inlines without -ffast-math).
+* arguments: arrays and derived types by reference (Python objects); scalar dummies by copy-in/copy-out, which equals
+  by-reference whenever no two arguments alias -- true of every call on the path.
+"""
+import copy
+import math
+
+import numpy as np
+
+F32 = np.float32
+F64 = np.float64
+D0 = F64(0.0)
+
+
+class FStop(Exception):
+    """A Fortran STOP statement was executed."""
+
+
+class FUnsupported(Exception):
+    """A statement or procedure outside the translated subset was reached at run time."""
+
+
+class IOLog:
+    """print / write statements are not formatted: the first string literal of the I/O list names the event and the
+    values of the other list items are kept (the reference's warnings -- ' Storebal SD wrong KINEMATIC ', ' Problem with EX '
+    -- and the numbers it writes to the .res / .flow units)."""
+
+    def __init__(self, cap=2000000):
+        self.events = []
+        self.counts = {}
+        self.cap = cap
+
+    def __call__(self, where, text, values):
+        self.counts[text] = self.counts.get(text, 0) + 1
+        if len(self.events) < self.cap:
+            vals = [np.array(v.a, copy=True) if isinstance(v, FArr) else v for v in values]
+            self.events.append((where, text, vals))
+
+    def clear(self):
+        self.events.clear()
+        self.counts.clear()
+
+
+IO = IOLog()
+
+
+def f_io(where, text, values=()):
+    IO(where, text, values)
+
+
+def f_unsupported(where, text):
+    raise FUnsupported(f"{where}: {text}")
+
+
+def f_stop(where, text):
+    raise FStop(f"{where}: STOP {text}")
+
+
+# ------------------------------------------------------------------------------------------------ arrays
+class FArr:
+    __slots__ = ("a", "lb", "isint", "n0", "l0")
+
+    def __init__(self, a, lb=None):
+        self.a = a
+        self.lb = tuple(lb) if lb is not None else (1,) * a.ndim
+        self.isint = a.dtype.kind in "iu"
+        self.n0 = a.shape[0] if a.ndim else 0
+        self.l0 = self.lb[0] if a.ndim else 1
+
+    # -- indexing ---------------------------------------------------------------------------------
+    def _key(self, k):
+        if not isinstance(k, tuple):
+            k = (k,)
+        if len(k) != self.a.ndim:
+            raise IndexError(f"rank mismatch: {len(k)} subscripts for rank {self.a.ndim}")
+        out = []
+        sec = False
+        for kk, l, n in zip(k, self.lb, self.a.shape):
+            if isinstance(kk, slice):
+                lo = l if kk.start is None else int(kk.start)
+                hi = l + n - 1 if kk.stop is None else int(kk.stop)
+                st = 1 if kk.step is None else int(kk.step)
+                if st != 1:
+                    raise FUnsupported("strided section")
+                if hi < lo:
+                    out.append(slice(0, 0))
+                else:
+                    if lo < l or hi > l + n - 1:
+                        raise IndexError(f"section {lo}:{hi} outside {l}:{l + n - 1}")
+                    out.append(slice(lo - l, hi - l + 1))
+                sec = True
+            else:
+                i = int(kk) - l
+                if i < 0 or i >= n:
+                    raise IndexError(f"subscript {kk} outside {l}:{l + n - 1}")
+                out.append(i)
+        return tuple(out), sec
+
+    def __getitem__(self, k):
+        if type(k) is int and self.a.ndim == 1:
+            i = k - self.l0
+            if i < 0 or i >= self.n0:
+                raise IndexError(f"subscript {k} outside {self.l0}:{self.l0 + self.n0 - 1}")
+            v = self.a[i]
+            return int(v) if self.isint else v
+        key, sec = self._key(k)
+        v = self.a[key]
+        if sec:
+            return FArr(v)
+        return int(v) if self.isint else v
+
+    def __setitem__(self, k, v):
+        if type(k) is int and self.a.ndim == 1:
+            i = k - self.l0
+            if i < 0 or i >= self.n0:
+                raise IndexError(f"subscript {k} outside {self.l0}:{self.l0 + self.n0 - 1}")
+            self.a[i] = v
+            return
+        key, sec = self._key(k)
+        if isinstance(v, FArr):
+            v = v.a
+        self.a[key] = v
+
+    # -- whole-array arithmetic (elementwise IEEE operations) ---------------------------------------
+    @staticmethod
+    def _u(x):
+        return x.a if isinstance(x, FArr) else x
+
+    def __add__(self, o): return FArr(self.a + FArr._u(o))
+    def __radd__(self, o): return FArr(FArr._u(o) + self.a)
+    def __sub__(self, o): return FArr(self.a - FArr._u(o))
+    def __rsub__(self, o): return FArr(FArr._u(o) - self.a)
+    def __mul__(self, o): return FArr(self.a * FArr._u(o))
+    def __rmul__(self, o): return FArr(FArr._u(o) * self.a)
+    def __neg__(self): return FArr(-self.a)
+
+    def __truediv__(self, o):
+        u = FArr._u(o)
+        if self.isint and (isinstance(u, int) or getattr(u, "dtype", np.dtype("f8")).kind in "iu"):
+            raise FUnsupported("integer array division")
+        return FArr(self.a / u)
+
+    def __rtruediv__(self, o):
+        if self.isint and isinstance(o, int):
+            raise FUnsupported("integer array division")
+        return FArr(FArr._u(o) / self.a)
+
+    def tolist(self):
+        return self.a.tolist()
+
+    def __len__(self):
+        return self.a.size
+
+    def __repr__(self):
+        return f"FArr(lb={self.lb}, {self.a!r})"
+
+
+_DT = {"i": np.int64, "r": np.float32, "d": np.float64, "l": np.bool_, "c": object, "t": object}
+
+
+def f_alloc(base, bounds, factory=None):
+    """bounds: list of (lo, hi).  Derived-type arrays are filled with fresh instances."""
+    lb = [int(b[0]) for b in bounds]
+    shape = [max(int(b[1]) - int(b[0]) + 1, 0) for b in bounds]
+    a = np.zeros(shape, dtype=_DT[base], order="F")
+    if base == "t":
+        flat = a.reshape(-1, order="F") if a.size else a
+        for i in range(a.size):
+            flat[i] = factory()
+        a = flat.reshape(shape, order="F") if a.size else a
+    elif base == "c":
+        a[...] = ""
+    return FArr(a, lb)
+
+
+def f_aassign(dst, src):
+    """whole-array assignment `a = expr` (scalar broadcast or conforming array; allocates an unallocated allocatable)."""
+    if dst is None:
+        if isinstance(src, FArr):
+            return FArr(np.array(src.a, order="F", copy=True))
+        raise FUnsupported("assignment of a scalar to an unallocated array")
+    if isinstance(src, FArr):
+        if src.a.shape != dst.a.shape:
+            raise IndexError(f"shape mismatch {src.a.shape} -> {dst.a.shape}")
+        dst.a[...] = src.a
+    else:
+        dst.a[...] = src
+    return dst
+
+
+def f_gather(arr, comp):
+    """`x%c` where x is an array of derived type: the array of that component (a copy, read-only use)."""
+    flat = arr.a.reshape(-1, order="F")
+    vals = [getattr(e, comp) for e in flat]
+    kind = "d"
+    if vals and isinstance(vals[0], (int, np.integer)) and not isinstance(vals[0], bool):
+        kind = "i"
+    out = np.array(vals, dtype=_DT[kind]).reshape(arr.a.shape, order="F")
+    return FArr(out, arr.lb)
+
+
+def f_scatter(arr, comp, value, conv):
+    flat = arr.a.reshape(-1, order="F")
+    if isinstance(value, FArr):
+        src = value.a.reshape(-1, order="F")
+        for e, v in zip(flat, src):
+            setattr(e, comp, conv(v))
+    else:
+        for e in flat:
+            setattr(e, comp, conv(value))
+
+
+def f_slice(lo, hi, step=None):
+    return slice(lo, hi, step)
+
+
+def f_range(a, b, c=1):
+    a, b, c = int(a), int(b), int(c)
+    return range(a, b + (1 if c > 0 else -1), c)
+
+
+# ------------------------------------------------------------------------------------------------ scalars
+def cv_d(x):
+    return F64(x)
+
+
+def cv_r(x):
+    return F32(x)
+
+
+def cv_i(x):
+    if isinstance(x, (float, np.floating)):
+        return int(x)               # truncation toward zero, as Fortran's implicit conversion
+    return int(x)
+
+
+def cv_l(x):
+    return bool(x)
+
+
+def cv_c(x):
+    return x
+
+
+def cv_t(x):
+    return copy.deepcopy(x)
+
+
+def _isint(x):
+    return isinstance(x, (int, np.integer)) and not isinstance(x, (bool, np.bool_))
+
+
+def f_div(a, b):
+    if isinstance(a, FArr) or isinstance(b, FArr):
+        return a / b if isinstance(a, FArr) else b.__rtruediv__(a)
+    if _isint(a) and _isint(b):
+        a, b = int(a), int(b)
+        q = abs(a) // abs(b)
+        return q if (a >= 0) == (b >= 0) else -q
+    if _isint(a):
+        a = type(b)(a)
+    if _isint(b):
+        b = type(a)(b)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        return a / b
+
+
+def f_pow(a, b):
+    if _isint(b):
+        if _isint(a):
+            return int(a) ** int(b)
+        # libgcc __powidf2 (what gfortran emits for real**integer)
+        n = abs(int(b))
+        x = a
+        y = x if n % 2 else type(a)(1)
+        n >>= 1
+        while n:
+            x = x * x
+            if n % 2:
+                y = y * x
+            n >>= 1
+        return type(a)(1) / y if b < 0 else y
+    t = F64 if isinstance(a, F64) or isinstance(b, F64) else F32
+    return t(math.pow(float(a), float(b)))
+
+
+def _common(args):
+    if any(isinstance(x, F64) for x in args):
+        return F64
+    if any(isinstance(x, F32) for x in args):
+        return F32
+    return int
+
+
+def i_min(*a):
+    t = _common(a)
+    return min(t(x) for x in a)
+
+
+def i_max(*a):
+    t = _common(a)
+    return max(t(x) for x in a)
+
+
+def _fl(fn):
+    def g(x):
+        t = F32 if isinstance(x, F32) else F64
+        try:
+            return t(fn(float(x)))
+        except OverflowError:
+            return t(math.inf)
+        except ValueError:
+            return t(math.nan)
+    return g
+
+
+i_exp = _fl(math.exp)
+i_cos = _fl(math.cos)
+i_sin = _fl(math.sin)
+i_tan = _fl(math.tan)
+i_atan = _fl(math.atan)
+i_sqrt = _fl(math.sqrt)
+
+
+def i_log(x):
+    t = F32 if isinstance(x, F32) else F64
+    xf = float(x)
+    if xf > 0.0:
+        return t(math.log(xf))
+    if xf == 0.0:
+        return t(-math.inf)
+    return t(math.nan)
+
+
+def i_abs(x):
+    if isinstance(x, FArr):
+        return FArr(np.abs(x.a))
+    return abs(x)
+
+
+def i_dble(x):
+    return F64(x)
+
+
+def i_real(x, kind=None):
+    return F64(x) if kind == 8 else F32(x)
+
+
+def i_int(x, kind=None):
+    return int(x)
+
+
+def i_nint(x):
+    xf = float(x)
+    r = math.floor(abs(xf))
+    if abs(xf) - r >= 0.5:
+        r += 1
+    return int(r) if xf >= 0 else -int(r)
+
+
+def i_floor(x):
+    return int(math.floor(float(x)))
+
+
+def i_ceiling(x):
+    return int(math.ceil(float(x)))
+
+
+def i_mod(a, b):
+    if _isint(a) and _isint(b):
+        return int(math.fmod(int(a), int(b)))
+    t = _common((a, b))
+    return t(math.fmod(float(a), float(b)))
+
+
+def i_sign(a, b):
+    return abs(a) if b >= 0 else -abs(a)
+
+
+def i_size(x, dim=None):
+    if dim is None:
+        return int(x.a.size)
+    return int(x.a.shape[int(dim) - 1])
+
+
+def i_allocated(x):
+    return x is not None
+
+
+def i_sum(x):
+    flat = x.a.reshape(-1, order="F")
+    if x.isint:
+        return int(flat.sum())
+    s = flat.dtype.type(0)
+    for v in flat:
+        s = s + v
+    return s
+
+
+def i_minval(x):
+    flat = x.a.reshape(-1, order="F")
+    v = flat.min()
+    return int(v) if x.isint else v
+
+
+def i_maxval(x):
+    flat = x.a.reshape(-1, order="F")
+    v = flat.max()
+    return int(v) if x.isint else v
+
+
+def i_cshift(x, shift, dim=1):
+    return FArr(np.roll(x.a, -int(shift), axis=int(dim) - 1), x.lb)
+
+
+def i_trim(x):
+    return str(x).rstrip()
+
+
+def i_len_trim(x):
+    return len(str(x).rstrip())
+
+
+def i_adjustl(x):
+    return str(x).lstrip()
+
+
+def i_huge(x):
+    if _isint(x):
+        return 2147483647
+    return F64(np.finfo(np.float64).max) if isinstance(x, F64) else F32(np.finfo(np.float32).max)
+
+
+def i_isnan(x):
+    return bool(np.isnan(x))
+
+
+def i_move_alloc(src, dst):
+    raise FUnsupported("move_alloc is handled by the translator")
+
+
+class Namespace:
+    """module variables and named constants of the translated modules"""
+
+
+def from_numpy(a, kind=None):
+    """helper for drivers: numpy array -> FArr (column-major copy)"""
+    a = np.asarray(a)
+    if kind is None:
+        kind = "i" if a.dtype.kind in "iu" else "d"
+    return FArr(np.array(a, dtype=_DT[kind], order="F", copy=True))

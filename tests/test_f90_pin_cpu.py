@@ -1,0 +1,133 @@
+"""The oracle against the reference's OWN source, executed.
+
+`tests/golden/f90_exec/*.npz` were produced by `tests/golden/make_f90_vectors.py`: the reference's Fortran files (RRMODEL/
+dyna_*.f90, DTA/dta_route_processing.f90), translated statement by statement by `oracle/f90_translate.py` and run with
+Fortran arithmetic semantics on small synthetic catchments -- RANMAR and genpar, param_setup, init_satzone (every exit of
+its search), Topmod with its three zones, dynamic_dist, river / route_process_run_step, results_ts, write_output.  The C++
+oracle has to reproduce every flow, total, parameter and flag BIT FOR BIT; the GPU kernels are then held to the oracle
+(tests/test_gpu_*.py) and to these vectors directly (tests/test_gpu_f90_pin.py).
+
+When the reference sources are present (this container, not the GPU box) one case is regenerated live, which keeps the
+generator and the committed files honest.
+"""
+import ast
+import os
+import sys
+
+import numpy as np
+import pytest
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+import f90_cases  # noqa: E402
+from decipher_b200 import capi, synth  # noqa: E402
+from oracle_binding import oracle_build_hist, oracle_genpar, oracle_ranmar, oracle_route_timeseries, oracle_run  # noqa: E402
+
+VEC = os.path.join(HERE, "golden", "f90_exec")
+
+
+def bits(a):
+    return np.ascontiguousarray(np.asarray(a, dtype=np.float64)).view(np.uint64)
+
+
+def same_bits(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return a.shape == b.shape and np.array_equal(bits(a), bits(b))
+
+
+def load(name):
+    return np.load(os.path.join(VEC, name + ".npz"), allow_pickle=False)
+
+
+def test_ranmar_stream_of_the_executed_source():
+    """ranin(5, 2000) + ranaru (RRMODEL/dyna_random.f90), the seeds of RRMODEL_EXAMPLE_FILES/params.dat"""
+    u = load("ranmar_5_2000")["u"]
+    assert same_bits(oracle_ranmar(5, 2000, 0, 200), u)
+    assert 0.0 <= u.min() and u.max() < 1.0
+
+
+@pytest.mark.parametrize("name", sorted(f90_cases.CASES))
+def test_oracle_reproduces_the_executed_reference(name):
+    case = f90_cases.CASES[name]
+    v = load(name)
+    cat, explicit = f90_cases.build(name)
+    mc_in = v["mcpar_in"]
+    if explicit is None:                                           # sampled by the reference's genpar: bit-exact parameter sets
+        ll, ul = synth.example_bounds(case["raw"]["npt"])
+        assert same_bits(oracle_genpar(case["seeds"][0], case["seeds"][1], ll, ul, case["members"]), mc_in)
+    else:
+        assert same_bits(explicit, mc_in)
+    M = mc_in.shape[2]
+    ref = oracle_run(cat, np.asfortranarray(mc_in).copy(order="F"), flags=capi.OPT_CHECK_BALANCE)
+    stop = [str(s) for s in v["stop"]]
+    warn = ast.literal_eval(str(v["warnings"]))
+    for m in range(M):
+        st = int(ref["status"][m])
+        assert (st & capi.ST_SOLFLAG_MASK) == int(v["sol_flag"][m]), (m, st)
+        # the three numbers init_satzone writes to the .res file (x 1000, dyna_init_satzone.f90:188-190)
+        assert same_bits(ref["init_diag"][:, m] * 1000, v["init"][:, m]), (m, ref["init_diag"][:, m] * 1000, v["init"][:, m])
+        rz = "dyna_root_zone1" in stop[m]
+        ts = "dyna_results_ts" in stop[m]
+        assert bool(st & capi.ST_RZ_BALANCE) == rz, (m, st, stop[m])
+        assert bool(st & (capi.ST_TS_OUTSUM | capi.ST_TS_WBAL)) == ts, (m, st, stop[m])
+        assert (" Storebal SRZ wrong " in warn[m]) == rz
+        if stop[m]:
+            continue                                               # the reference program ends there: nothing was written
+        assert same_bits(ref["q"][:, :, m], v["q"][:, :, m]), (m, np.abs(ref["q"][:, :, m] - v["q"][:, :, m]).max())
+        assert same_bits(ref["reach_totals"][:, :, m], v["totals"][:, :, m]), m
+        assert same_bits(ref["mcpar"][:, :, m], v["mcpar_written"][:, :, m]), m       # after the srinit clip
+        assert np.isfinite(v["q"][:, :, m]).all() == (not (st & capi.ST_NONFINITE))
+
+
+def test_branches_the_vectors_reach():
+    """the explicit parameter sets exist to drive the reference into its rare branches: make sure they still do"""
+    d = load("d_init_branches")
+    assert sorted(set(d["sol_flag"].tolist())) == [0, 1, 2]
+    assert d["mcpar_written"][0, 3, 0] == d["mcpar_written"][0, 2, 0] != d["mcpar_in"][0, 3, 0]      # srinit clipped to srmax
+    assert "dyna_root_zone1.f90" in str(load("f_huge_rain")["stop"][0])
+    assert str(load("g_negative_rain")["stop"][0]) == ""            # `.lt. - 0000000001` is the integer -1
+    w = ast.literal_eval(str(load("b_tree_ntt2")["warnings"]))
+    assert all(x.get(" Storebal SD wrong KINEMATIC ", 0) > 0 for x in w)      # the reference's own check misfires for ntt = 2
+
+
+def test_routing_of_the_executed_source():
+    """hist_add_value on the inputs of the reference's add_accumulation_test (dta_route_processing.f90:444-468),
+    route_processing_build_hist at the four velocities of build_hist_test (:470-534) and route_process_run_timeseries"""
+    v = load("routing")
+    acc = v["accumulation"]
+    # the reference's own comment (:392-397) describes the split: first cell (1 - fraction), full middle cells, last cell
+    assert same_bits(acc[0], [0, 0, 1.0 * (2.4 - 2.2), 0, 0, 0])
+    assert same_bits(acc[1], [0, 0, 1 - (2.2 - 3 + 1), 3.1 - 4 + 1, 0, 0])
+    assert same_bits(acc[2], [0, 0, 1 - (2.2 - 3 + 1), 1.0, 4.2 - 5 + 1, 0])
+    assert same_bits(acc[3], [0, 0, 1 - (2.2 - 3 + 1), 1.0, 1.0, 5.2 - 6 + 1])
+    raw = synth.make_raw(nac=10, nriv=4, npt=1, ngp=1, nge=1, nstep=96, kW=3, seed=int(v["route_seed"][0]), tree=True)
+    cat = synth.assemble(raw)
+    inflow = v["inflow"]                                            # (timestep, series)
+    for k, vel in enumerate(v["velocity"]):
+        rc, hist, idx, T = oracle_build_hist(cat, float(vel))
+        assert rc == 0 and T == int(v["hist_len"][k])
+        assert same_bits(hist, v[f"hist_{k}"])
+        assert np.array_equal(idx, v["hist_idx"][k])
+        routed, st = oracle_route_timeseries(cat, np.array([vel]), np.asfortranarray(inflow.T[:, :, None]))
+        assert same_bits(routed[:, :, 0], v["routed"][k].T) and st[0] == 0
+
+
+def _reference_present():
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    import make_f90_vectors
+    return make_f90_vectors.reference_available()
+
+
+@pytest.mark.skipif(not _reference_present(), reason="reference sources are not on this machine (GPU box)")
+def test_live_translation_reproduces_the_committed_vectors():
+    import make_f90_vectors as mk
+    ns = mk.load_reference()
+    assert not [p for p in mk.NEEDED if p in ns["_NOT_TRANSLATED"]]
+    for name in ("a_two_reaches", "d_init_branches"):
+        v = load(name)
+        cat, mc, res = mk.make_case(ns, name)
+        assert same_bits(mc, v["mcpar_in"])
+        for m, r in enumerate(res):
+            assert same_bits(r["q"], v["q"][:, :, m]) and same_bits(r["totals"], v["totals"][:, :, m])
+            assert r["sol_flag"] == int(v["sol_flag"][m])
