@@ -4,12 +4,15 @@
 // __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this
 // library, and only as the checker or the timed CPU baseline.
 //
-// PARITY UNPINNED UPSTREAM: the reference ships no tests, fixtures or golden vectors for this
-// path and no Fortran compiler exists in this environment, so this restatement cannot be checked
-// against outputs of the reference itself.  What IS pinned: the RANMAR generator against its
-// published known-answer test (James 1990; tests/test_oracle_cpu.py) and the run-time invariants
-// the reference enforces with STOP (water balance, histogram rows sum to 1).  An independent
-// NumPy restatement (oracle/oracle_np.py) cross-checks this file on small cases.
+// PARITY PIN: no Fortran compiler exists in this environment and the reference ships no fixtures for
+// this path, so the reference cannot be built.  Its SOURCE is executed instead: oracle/f90_translate.py
+// translates the reference's own .f90 files statement by statement, oracle/f90_runtime.py runs them
+// with Fortran arithmetic semantics, tests/golden/make_f90_vectors.py commits the outputs
+// (tests/golden/f90_exec/), and tests/test_f90_pin_cpu.py requires this file to reproduce them BIT FOR
+// BIT (flows, reach totals, init block, parameter tables, flags, RANMAR stream, routing histograms).
+// Not pinned: one compiler's code generation (FMA contraction, x87, -ffast-math).  Also pinned: RANMAR
+// against its published known-answer test (James 1990; tests/test_oracle_cpu.py) and an independent
+// NumPy restatement (oracle/oracle_np.py).
 //
 // Every routine follows the reference statement by statement: IEEE FP64, strict left-to-right
 // evaluation, no FMA contraction (build with -ffp-contract=off), default-real literals taken as
@@ -20,7 +23,8 @@
 //   * `sumeout` (RRMODEL/dyna_results_ts.f90:28,68) and `tot_reach_ppt`
 //     (RRMODEL/dyna_write_output.f90:55-57,63) are used uninitialised upstream; both start at 0 here.
 //   * STOP conditions become per-member status bits; the member keeps running.
-//   * the init search loop is capped at DCP_INIT_MAX_ITER iterations (hang guard).
+//   * the init search loop is capped at DCP_INIT_MAX_ITER = 2e6 iterations (hang guard; the executed
+//     reference needs up to ~3e4 on the test catchments).
 //   * NSE / log-NSE do not exist upstream; they are defined in objective() below.
 
 #include "../include/decipher_b200.h"
