@@ -460,3 +460,202 @@ def from_numpy(a, kind=None):
     if kind is None:
         kind = "i" if a.dtype.kind in "iu" else "d"
     return FArr(np.array(a, dtype=_DT[kind], order="F", copy=True))
+
+
+# ------------------------------------------------------------------------------------------------ array predicates
+def _cmp(op):
+    def f(self, o):
+        return FArr(op(self.a, FArr._u(o)))
+    return f
+
+
+FArr.__eq__ = _cmp(np.equal)
+FArr.__ne__ = _cmp(np.not_equal)
+FArr.__lt__ = _cmp(np.less)
+FArr.__le__ = _cmp(np.less_equal)
+FArr.__gt__ = _cmp(np.greater)
+FArr.__ge__ = _cmp(np.greater_equal)
+FArr.__hash__ = None
+
+
+def i_count(mask):
+    return int(np.count_nonzero(mask.a))
+
+
+def _i_sum_masked(x, mask=None):
+    flat = x.a.reshape(-1, order="F")
+    if mask is None:
+        if x.isint:
+            return int(flat.sum())
+        s = flat.dtype.type(0)
+        for v in flat:
+            s = s + v
+        return s
+    mk = mask.a.reshape(-1, order="F")
+    if x.isint:
+        return int(flat[mk].sum())
+    s = flat.dtype.type(0)
+    for v, keep in zip(flat, mk):
+        if keep:
+            s = s + v
+    return s
+
+
+i_sum = _i_sum_masked
+_scalar_int = i_int
+
+
+def i_int(x, kind=None):
+    if isinstance(x, FArr):
+        return FArr(np.trunc(x.a).astype(np.int64), x.lb)
+    return _scalar_int(x)
+
+
+def f_case(sel, *vals):
+    """SELECT CASE match; character selectors compare without trailing blanks"""
+    if isinstance(sel, str):
+        return any(sel.rstrip() == str(v).rstrip() for v in vals)
+    return any(sel == v for v in vals)
+
+
+# ------------------------------------------------------------------------------------------------ sequential formatted input
+class Unit:
+    def __init__(self, path):
+        with open(path, "r", errors="replace") as f:
+            self.lines = f.read().split("\n")
+        if self.lines and self.lines[-1] == "":
+            self.lines.pop()
+        self.pos = 0
+        self.path = path
+
+
+UNITS = {}
+
+
+class FEndOfFile(Exception):
+    pass
+
+
+def open_unit(unit, path):
+    UNITS[int(unit)] = Unit(path)
+
+
+def f_open(where, unit, **kw):
+    if kw.get("action", "").strip().lower() == "write" or kw.get("status", "").strip().lower() in ("unknown", "replace", "new"):
+        return                                          # output files are not produced
+    open_unit(unit, str(kw["file"]).strip())
+
+
+def f_close(unit):
+    UNITS.pop(int(unit), None)
+
+
+def f_rewind(unit):
+    UNITS[int(unit)].pos = 0
+
+
+def _tokens(line):
+    """list-directed values of one record: blank / comma / tab separated, quoted strings kept whole, '/' ends the record"""
+    out = []
+    i, n = 0, len(line)
+    slash = False
+    while i < n:
+        ch = line[i]
+        if ch in " \t\r":
+            i += 1
+        elif ch == ",":
+            i += 1
+        elif ch == "/":
+            slash = True
+            break
+        elif ch in "'\"":
+            j = i + 1
+            buf = []
+            while j < n:
+                if line[j] == ch:
+                    if j + 1 < n and line[j + 1] == ch:
+                        buf.append(ch)
+                        j += 2
+                        continue
+                    break
+                buf.append(line[j])
+                j += 1
+            out.append("".join(buf))
+            i = j + 1
+        else:
+            j = i
+            while j < n and line[j] not in " \t\r,":
+                j += 1
+            out.append(line[i:j])
+            i = j
+    return out, slash
+
+
+def _convert(tok, base, where):
+    if base == "c":
+        return tok
+    t = tok.strip().lower()
+    try:
+        if base == "i":
+            return int(t)
+        v = float(t.replace("d", "e"))
+        return F64(v) if base == "d" else F32(v)
+    except ValueError:
+        raise FStop(f"{where}: bad {base} value {tok!r} in list-directed input") from None
+
+
+def f_read(where, unit, fmt, spec, iostat=False):
+    """READ(unit, fmt) of the items described by spec = [(base, count or None)]; returns (io, [values]) where an array
+    item's value is a list.  fmt: '*' (list directed) or '(a)' (one whole record into a character item).  Every READ
+    starts a new record and abandons the rest of the last record it touched (Fortran sequential formatted input)."""
+    u = UNITS.get(int(unit))
+    if u is None:
+        raise FStop(f"{where}: unit {unit} is not connected")
+    need = sum(1 if c is None else int(c) for _, c in spec)
+    flat = []
+    try:
+        if fmt != "*":
+            if fmt.replace(" ", "").lower() != "(a)":
+                raise FUnsupported(f"{where}: format {fmt}")
+            if u.pos >= len(u.lines):
+                raise FEndOfFile
+            flat = [u.lines[u.pos]] * max(need, 0)
+            u.pos += 1
+        elif need == 0:
+            if u.pos >= len(u.lines):
+                raise FEndOfFile
+            u.pos += 1
+        else:
+            while len(flat) < need:
+                if u.pos >= len(u.lines):
+                    raise FEndOfFile
+                toks, slash = _tokens(u.lines[u.pos])
+                u.pos += 1
+                flat.extend(toks)
+                if slash:
+                    break
+            if len(flat) < need:
+                raise FUnsupported(f"{where}: '/' terminated input")
+    except FEndOfFile:
+        if iostat:
+            return -1, None
+        raise FStop(f"{where}: end of file on unit {unit} ({u.path})") from None
+    vals = []
+    k = 0
+    for base, c in spec:
+        if c is None:
+            vals.append(_convert(flat[k], base, where))
+            k += 1
+        else:
+            vals.append([_convert(t, base, where) for t in flat[k:k + int(c)]])
+            k += int(c)
+    return 0, vals
+
+
+def f_store(dst, values, base):
+    """whole-array / section target of a READ"""
+    a = np.array(values, dtype=_DT[base] if base != "c" else object)
+    if isinstance(dst, FArr):
+        dst.a[...] = a.reshape(dst.a.shape, order="F")
+        return dst
+    raise FUnsupported("READ into an unallocated array")

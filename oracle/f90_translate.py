@@ -514,6 +514,7 @@ class Proc:
         self.body = []           # [(line, label, text)]
         self.copy_out = []       # positions of dummies returned to the caller
         self.uses = []
+        self.broken = None
 
 
 class Program:
@@ -545,10 +546,13 @@ class Program:
                 if re.match(r"^end\s*type\b", s):
                     cur_type = None
                     continue
-                toks = tokenize(s)
-                if is_declaration(toks):
-                    for d in parse_declaration(toks):
-                        cur_type.comps[d.name] = d
+                try:
+                    toks = tokenize(s)
+                    if is_declaration(toks):
+                        for d in parse_declaration(toks):
+                            cur_type.comps[d.name] = d
+                except SyntaxError as e:
+                    self.warnings.append(f"{src}:{ln}: component outside the subset: {e}")
                 continue
             if cur_iface is not None:
                 if re.match(r"^end\s*interface\b", s):
@@ -570,10 +574,14 @@ class Program:
                     if m:
                         cur_proc.uses.append(m.group(1))
                         continue
-                    toks = tokenize(s)
-                    if is_declaration(toks):
-                        for d in parse_declaration(toks):
-                            cur_proc.decls[d.name] = d
+                    try:
+                        toks = tokenize(s)
+                        if is_declaration(toks):
+                            for d in parse_declaration(toks):
+                                cur_proc.decls[d.name] = d
+                            continue
+                    except SyntaxError as e:
+                        cur_proc.broken = f"declaration outside the subset: {s[:60]}"
                         continue
                     in_exec = True
                 cur_proc.body.append((ln, label, s))
@@ -608,12 +616,16 @@ class Program:
                 cur_proc = Proc("fun", m.group(1), args, m.group(3) or m.group(1), module, src)
                 in_exec = False
                 continue
-            toks = tokenize(s)
-            if is_declaration(toks):
-                for d in parse_declaration(toks):
-                    d.modvar = True
-                    self.modvars[d.name] = d
-                    self.modvar_order.append(d.name)
+            try:
+                toks = tokenize(s)
+                if is_declaration(toks):
+                    for d in parse_declaration(toks):
+                        d.modvar = True
+                        self.modvars[d.name] = d
+                        self.modvar_order.append(d.name)
+                    continue
+            except SyntaxError as e:
+                self.warnings.append(f"{src}:{ln}: module entity outside the subset: {s[:60]}")
                 continue
             self.warnings.append(f"{src}:{ln}: ignored at module level: {s}")
 
@@ -644,14 +656,19 @@ class Program:
         g = Gen(self, None)
         for name in self.modvar_order:
             d = self.modvars[name]
-            out.append(f"_M.{pyname(name)} = {g.initial_value(d)}")
+            try:
+                out.append(f"_M.{pyname(name)} = {g.initial_value(d)}")
+            except (SyntaxError, NotImplementedError, KeyError) as e:
+                self.warnings.append(f"module entity {name} outside the subset: {e}")
         out.append("")
         for p in self.procs.values():
             if only is not None and p.name not in only:
                 continue
             try:
+                if p.broken:
+                    raise NotImplementedError(p.broken)
                 out += Gen(self, p).gen_proc()
-            except (SyntaxError, NotImplementedError, KeyError) as e:
+            except (SyntaxError, NotImplementedError, KeyError, AssertionError) as e:
                 msg = f"{type(e).__name__}: {e}"
                 out.append(f"def f_{p.name}(*a, **k):")
                 out.append(f"    raise FUnsupported({('procedure ' + p.name + ' is outside the translated subset: ' + msg)!r})")
@@ -696,7 +713,7 @@ _CV = {"i": "cv_i", "r": "cv_r", "d": "cv_d", "l": "cv_l", "c": "cv_c", "t": "cv
 
 _INTRINSICS = {"exp", "log", "cos", "sin", "tan", "atan", "sqrt", "abs", "min", "max", "dble", "real", "int", "nint", "floor",
                "ceiling", "mod", "sign", "size", "allocated", "sum", "minval", "maxval", "cshift", "trim", "len_trim",
-               "adjustl", "huge", "isnan"}
+               "adjustl", "huge", "isnan", "count"}
 
 
 class Gen:
@@ -914,6 +931,76 @@ class Gen:
             vals = []
         self.emit(f"f_io({self.where!r}, {txt!r}, [{', '.join(vals)}])")
 
+    def read(self, toks):
+        """READ (unit, fmt [, iostat = v]) items -- list-directed or '(A)'; items: variables, array elements, whole arrays,
+        sections, one-level implied DO"""
+        grp, j = _group(toks, 1)
+        ctl = _split_commas(grp)
+        unit = self.expr(Parser(ctl[0]).p_arg())
+        fmt = "*"
+        iostat = None
+        for k, part in enumerate(ctl[1:]):
+            a = Parser(part).p_arg()
+            if isinstance(a, tuple) and a[0] == "kw":
+                if a[1] == "iostat":
+                    iostat = self.ref(a[2][1], lvalue=True)[0]
+                elif a[1] == "fmt":
+                    a = a[2]
+                else:
+                    raise NotImplementedError(f"read control {a[1]}")
+            if k == 0 and not (isinstance(a, tuple) and a[0] == "kw"):
+                if a == ("star",):
+                    fmt = "*"
+                elif a[0] == "str":
+                    fmt = a[1]
+                else:
+                    raise NotImplementedError("read with a format label")
+        spec, stores = [], []
+        items = _split_commas(toks[j:]) if j < len(toks) else []
+        for part in items:
+            if not part:
+                continue
+            n = len(spec)
+            if part[0].k == "op" and part[0].v == "(" and any(t.k == "op" and t.v == "=" for t in part):
+                inner, _ = _group(part, 0)                          # implied DO: (a(i), b(i), i = lo, hi)
+                pieces = _split_commas(inner)
+                eq = next(i for i, pc in enumerate(pieces) if len(pc) > 1 and pc[1].k == "op" and pc[1].v == "=")
+                var = self.lookup(pieces[eq][0].v)
+                lo = self.expr(Parser(pieces[eq][2:]).expr())
+                hi = self.expr(Parser(pieces[eq + 1]).expr())
+                targets = [self.ref(Parser(pc).p_ref()[1], lvalue=True) for pc in pieces[:eq]]
+                bases = {t[1][0] for t in targets}
+                if len(bases) != 1 or any(t[1][3] != "scalar" for t in targets):
+                    raise NotImplementedError("implied DO over mixed or array items")
+                base = bases.pop()
+                spec.append(f"({base!r}, len(f_range({lo}, {hi})) * {len(targets)})")
+                body = [f"_it = iter(_v[{n}])", f"for {self.var_code(var)} in f_range({lo}, {hi}):"]
+                for code, (b, tn, rk, kd) in targets:
+                    body.append(f"    {code} = " + (f"next(_it)" if code.endswith("]") else f"{_CV[b]}(next(_it))"))
+                stores.append(body)
+                continue
+            code, (base, tname, rank, kind) = self.ref(Parser(part).p_ref()[1], lvalue=True)
+            if kind == "scalar":
+                spec.append(f"({base!r}, None)")
+                stores.append([f"{code} = _v[{n}]" if code.endswith("]") else f"{code} = {_CV[base]}(_v[{n}])"])
+            elif kind in ("array", "section"):
+                spec.append(f"({base!r}, i_size({code}))")
+                stores.append([f"f_store({code}, _v[{n}], {base!r})"])
+            else:
+                raise NotImplementedError("read into a component of an array of derived type")
+        self.emit(f"_io, _v = f_read({self.where!r}, {unit}, {fmt!r}, [{', '.join(spec)}], {iostat is not None})")
+        if iostat is not None:
+            self.emit(f"{iostat} = _io")
+            self.emit("if _io == 0:")
+            self.ind += 1
+        for body in stores:
+            for line in body:
+                self.emit(line)
+        if iostat is not None:
+            if not stores:
+                self.emit("pass")
+            self.ind -= 1
+
     def stmt(self, s, stack, label=None):
         try:
             toks = tokenize(s)
@@ -939,6 +1026,12 @@ class Gen:
                     return                                     # closed by the label logic in gen_proc
                 stack.pop()
                 self.ind -= 1
+                return
+            if what == "select":
+                assert stack and stack[-1][0] == "select", f"{self.where}: end select without select"
+                if stack[-1][2]:
+                    self.ind -= 1
+                stack.pop()
                 return
             raise NotImplementedError(f"end {what}")
         if is_assign is None:
@@ -1042,7 +1135,63 @@ class Gen:
             if w in ("print", "write"):
                 self.io(toks)
                 return
-            if w in ("read", "open", "close", "rewind", "backspace", "inquire", "format", "flush"):
+            if w == "select" and nxt is not None and nxt.v == "case":
+                grp, _ = _group(toks, 2)
+                self.sel_n = getattr(self, "sel_n", 0) + 1
+                var = f"_sel{self.sel_n}"
+                self.emit(f"{var} = {self.expr(Parser(grp).expr())}")
+                stack.append(["select", var, False])
+                return
+            if w == "case":
+                assert stack and stack[-1][0] == "select", f"{self.where}: case outside select"
+                top = stack[-1]
+                if top[2]:
+                    self.ind -= 1
+                if nxt is not None and nxt.k == "id" and nxt.v == "default":
+                    self.emit("else:" if top[2] else "if True:")
+                else:
+                    grp, _ = _group(toks, 1)
+                    vals = []
+                    for part in _split_commas(grp):
+                        a = Parser(part).p_arg()
+                        if isinstance(a, tuple) and a[0] == "range":
+                            raise NotImplementedError("case range")
+                        vals.append(self.expr(a))
+                    self.emit(f"{'elif' if top[2] else 'if'} f_case({top[1]}, {', '.join(vals)}):")
+                top[2] = True
+                self.ind += 1
+                self.emit("pass")
+                return
+            if w == "read":
+                self.read(toks)
+                return
+            if w == "open":
+                grp, _ = _group(toks, 1)
+                pos, kws = [], []
+                for part in _split_commas(grp):
+                    a = Parser(part).p_arg()
+                    if isinstance(a, tuple) and a[0] == "kw":
+                        if a[1] in ("iostat",):
+                            code, _ = self.ref(a[2][1], lvalue=True)
+                            self.emit(f"{code} = 0")
+                        elif a[1] == "unit":
+                            pos.append(self.expr(a[2]))
+                        else:
+                            kws.append(f"{a[1]}={self.expr(a[2])}")
+                    else:
+                        pos.append(self.expr(a))
+                self.emit(f"f_open({self.where!r}, {pos[0]}{''.join(', ' + k for k in kws)})")
+                return
+            if w in ("close", "rewind"):
+                if nxt is not None and nxt.k == "op" and nxt.v == "(":
+                    grp, _ = _group(toks, 1)
+                    a = Parser(_split_commas(grp)[0]).p_arg()
+                    u = self.expr(a[2] if isinstance(a, tuple) and a[0] == "kw" else a)
+                else:
+                    u = self.expr(Parser(toks, 1).expr())
+                self.emit(f"f_{w}({u})")
+                return
+            if w in ("backspace", "inquire", "format", "flush"):
                 self.emit(f"f_unsupported({self.where!r}, {w!r})")
                 return
             raise NotImplementedError(f"statement {s!r}")
@@ -1135,12 +1284,14 @@ class Gen:
 
     def resolve_generic(self, name, args):
         a0 = args[0]
-        d = self.lookup(a0[1][0][0]) if a0[0] == "ref" and len(a0[1]) == 1 else None
+        base = rank = None
+        if a0[0] == "ref" and self.lookup(a0[1][0][0]) is not None:
+            _, (base, _, rank, _) = self.ref(a0[1], lvalue=True)
         for cand in self.prog.generics[name]:
             c = self.prog.procs.get(cand)
             if c is None or len(c.args) != len(args):
                 continue
             cd = c.decls.get(c.args[0])
-            if d is None or (cd.base == d.base and cd.rank == d.rank):
+            if base is None or (cd.base == base and cd.rank == rank):
                 return cand
         raise KeyError(f"no specific procedure of {name} matches")

@@ -66,3 +66,39 @@ def build(name):
         for m, s in enumerate(c["sets"]):
             mc[:, :, m] = np.asarray(s, dtype=np.float64).reshape(npt, 7)
     return cat, mc
+
+
+# ---------------------------------------------------------------------------------------------------- whole projects
+# Projects in the reference's FILE formats (decipher_b200.formats.write_project): the reference's readers (Tread_dyna, Inputs,
+# mc_setup, modelstruct_setup, read_routingdata with riv_tree_read_impl / read_numeric_list_fid) are executed on the files, then
+# ranin / genpar / mainloop for `numsim` members -- `program main` (dyna_main.f90:95-206) without the path handling of `project`.
+PROJECTS = {
+    "p_tree": dict(raw=dict(nac=14, nriv=3, npt=2, ngp=2, nge=2, nstep=50, kW=4, seed=77, tree=True), numsim=3, seeds=(11, 222)),
+    # observed flow: gauge 1 misses its first value (start = mean of the valid ones, dyna_inputs.f90:96-99), gauge 2 has no valid
+    # value at all (start = (0.001/24)*dt, the quotient taken in SINGLE precision, :94)
+    "p_missing_flow": dict(raw=dict(nac=10, nriv=2, npt=1, ngp=1, nge=1, nstep=40, kW=3, seed=78), numsim=2, seeds=(5, 2000),
+                           tweak="missing_flow"),
+}
+
+
+def write_project(name, root):
+    """writes the project files under root; -> raw dict"""
+    from decipher_b200 import formats
+    c = PROJECTS[name]
+    raw = synth.make_raw(**c["raw"])
+    if c.get("tweak") == "missing_flow":
+        raw["qobs"] = np.asfortranarray(raw["qobs"].copy())
+        raw["qobs"][0, 0] = raw["flow_err"]
+        raw["qobs"][1, :] = raw["flow_err"]
+    ll, ul = synth.example_bounds(c["raw"]["npt"])
+    formats.write_project(raw, root, ll, ul, numsim=c["numsim"], seeds=c["seeds"])
+    return raw
+
+
+def project_units(root, name="Catch1"):
+    """unit number -> file, as `project` connects them (dyna_project.f90:247-320)"""
+    import os
+    inp, st = os.path.join(root, "INPUTS"), os.path.join(root, "SETTINGS")
+    return {12: f"{st}/params.dat", 11: f"{st}/model_structure.dat", 13: f"{inp}/{name}_dyna_hru.dat", 17: f"{inp}/{name}_hru_meta.dat",
+            501: f"{inp}/{name}_flow_conn.dat", 502: f"{inp}/{name}_riv_data.dat", 503: f"{inp}/{name}_flow_point.dat",
+            14: f"{inp}/{name}_obsq.dat", 15: f"{inp}/{name}_PET.dat", 16: f"{inp}/{name}_rain.dat"}

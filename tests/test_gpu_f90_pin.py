@@ -46,3 +46,30 @@ def test_cuda_reproduces_the_executed_reference(name, kernel, flags):
         else:
             compare_flows(out["q"][:, :, m:m + 1], qr, floor=1e-2 if name.startswith(("h_", "d_")) else 1e-3)
         compare_close(out["reach_totals"][:, :, m], v["totals"][:, :, m], what="reach totals")
+
+
+@pytest.mark.parametrize("name", sorted(f90_cases.PROJECTS))
+@pytest.mark.parametrize("fast", [False, True])
+def test_cli_on_project_files_reproduces_the_executed_program(name, fast, tmp_path):
+    """The whole drop-in (decipher_b200_run: C++ readers + RANMAR/genpar + C ABI + CUDA) on a project directory against
+    `program main` of the reference executed on the same files (tests/golden/f90_exec/p_*.npz)."""
+    import subprocess
+    from decipher_b200 import formats, host
+    exe = os.path.join(os.path.dirname(HERE), "decipher_b200", "csrc", "build", "decipher_b200_run")
+    v = np.load(os.path.join(VEC, name + ".npz"), allow_pickle=False)
+    root = str(tmp_path)
+    f90_cases.write_project(name, root)
+    n = int(v["numsim"])
+    cmd = [exe, "-dir", root, "-ids", "1", "1", "1", "-write-members", f"1:{n}", "-flow-bin"] + (["-fast"] if fast else [])
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    p = host.Project(root)
+    ft = formats.read_flow_table(p.out_prefix + "ensemble_flow.bin")
+    assert ft["members"].tolist() == list(range(1, n + 1))
+    compare_flows(ft["q"], v["q"])
+    flow = np.loadtxt(p.out_prefix + f"mc_id_{n:08d}.flow", ndmin=2).T                     # the reference's own text format
+    assert np.abs(flow - v["q"][:, :, n - 1]).max() <= 0.5e-8 + 1e-12
+    tab = formats.read_perf_table(p.out_prefix + "ensemble_perf.bin")
+    unclipped = tab["mcpar"][:, 3, :] == v["mcpar"][:, 3, :]                                # srinit may be clipped to srmax afterwards
+    assert np.array_equal(np.delete(tab["mcpar"], 3, axis=1), np.delete(v["mcpar"], 3, axis=1)) and unclipped.mean() > 0.5
+    p.close()
