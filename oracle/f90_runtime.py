@@ -604,6 +604,31 @@ def _convert(tok, base, where):
         raise FStop(f"{where}: bad {base} value {tok!r} in list-directed input") from None
 
 
+def _formatted_fields(line, fmt, need, where):
+    """fields of one record under a format of A / Aw / Iw / nX descriptors (dyna_project.f90:330-331: a13,1X,a700 and
+    a13,1X,i4); a record shorter than the format is padded with blanks, as Fortran does"""
+    body = fmt.strip().lower()
+    if not (body.startswith("(") and body.endswith(")")):
+        raise FUnsupported(f"{where}: format {fmt}")
+    out = []
+    col = 0
+    for d in [x.strip() for x in body[1:-1].split(",")]:
+        if d == "a":
+            out.append(line[col:])
+            col = len(line)
+        elif d[0] in "ai" and d[1:].isdigit():
+            w = int(d[1:])
+            out.append(line[col:col + w].ljust(w) if d[0] == "a" else (line[col:col + w].strip() or "0"))
+            col += w
+        elif d.endswith("x") and d[:-1].isdigit():
+            col += int(d[:-1])
+        else:
+            raise FUnsupported(f"{where}: edit descriptor {d!r}")
+    if len(out) < need:
+        raise FUnsupported(f"{where}: format {fmt} holds fewer items than the list")
+    return out
+
+
 def f_read(where, unit, fmt, spec, iostat=False):
     """READ(unit, fmt) of the items described by spec = [(base, count or None)]; returns (io, [values]) where an array
     item's value is a list.  fmt: '*' (list directed) or '(a)' (one whole record into a character item).  Every READ
@@ -615,11 +640,9 @@ def f_read(where, unit, fmt, spec, iostat=False):
     flat = []
     try:
         if fmt != "*":
-            if fmt.replace(" ", "").lower() != "(a)":
-                raise FUnsupported(f"{where}: format {fmt}")
             if u.pos >= len(u.lines):
                 raise FEndOfFile
-            flat = [u.lines[u.pos]] * max(need, 0)
+            flat = _formatted_fields(u.lines[u.pos], fmt, need, where)
             u.pos += 1
         elif need == 0:
             if u.pos >= len(u.lines):

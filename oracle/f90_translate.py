@@ -515,6 +515,7 @@ class Proc:
         self.copy_out = []       # positions of dummies returned to the caller
         self.uses = []
         self.broken = None
+        self.formats = {}        # statement label -> format text
 
 
 class Program:
@@ -567,8 +568,21 @@ class Program:
                     self.procs[cur_proc.name] = cur_proc
                     cur_proc = None
                     continue
+                if label is not None and re.match(r"^format\s*\(", s):
+                    cur_proc.formats[label] = s[s.index("("):]
+                    continue
                 if not in_exec:
                     if re.match(r"^(implicit|private|public|intrinsic|external|save)\b", s):
+                        continue
+                    m = re.match(r"^parameter\s*\((.*)\)$", s)
+                    if m:
+                        try:
+                            for part in _split_commas(tokenize(m.group(1))):
+                                d = cur_proc.decls[part[0].v]
+                                d.param = True
+                                d.init = Parser(part, 2).expr()
+                        except (SyntaxError, KeyError):
+                            cur_proc.broken = f"parameter statement outside the subset: {s[:60]}"
                         continue
                     m = re.match(r"^use\s+(\w+)", s)
                     if m:
@@ -936,7 +950,11 @@ class Gen:
         sections, one-level implied DO"""
         grp, j = _group(toks, 1)
         ctl = _split_commas(grp)
-        unit = self.expr(Parser(ctl[0]).p_arg())
+        u0 = Parser(ctl[0]).p_arg()
+        if u0 == ("star",):
+            self.emit(f"f_unsupported({self.where!r}, 'read from standard input')")
+            return
+        unit = self.expr(u0)
         fmt = "*"
         iostat = None
         for k, part in enumerate(ctl[1:]):
@@ -953,8 +971,10 @@ class Gen:
                     fmt = "*"
                 elif a[0] == "str":
                     fmt = a[1]
+                elif a[0] == "num" and a[2] in self.p.formats:
+                    fmt = self.p.formats[a[2]]
                 else:
-                    raise NotImplementedError("read with a format label")
+                    raise NotImplementedError("read with a format held in a variable")
         spec, stores = [], []
         items = _split_commas(toks[j:]) if j < len(toks) else []
         for part in items:

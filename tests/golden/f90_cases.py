@@ -71,7 +71,7 @@ def build(name):
 # ---------------------------------------------------------------------------------------------------- whole projects
 # Projects in the reference's FILE formats (decipher_b200.formats.write_project): the reference's readers (Tread_dyna, Inputs,
 # mc_setup, modelstruct_setup, read_routingdata with riv_tree_read_impl / read_numeric_list_fid) are executed on the files, then
-# ranin / genpar / mainloop for `numsim` members -- `program main` (dyna_main.f90:95-206) without the path handling of `project`.
+# ranin / genpar / mainloop for `numsim` members -- `program main` (dyna_main.f90:95-206), `project` included.
 PROJECTS = {
     "p_tree": dict(raw=dict(nac=14, nriv=3, npt=2, ngp=2, nge=2, nstep=50, kW=4, seed=77, tree=True), numsim=3, seeds=(11, 222)),
     # observed flow: gauge 1 misses its first value (start = mean of the valid ones, dyna_inputs.f90:96-99), gauge 2 has no valid
@@ -102,3 +102,51 @@ def project_units(root, name="Catch1"):
     return {12: f"{st}/params.dat", 11: f"{st}/model_structure.dat", 13: f"{inp}/{name}_dyna_hru.dat", 17: f"{inp}/{name}_hru_meta.dat",
             501: f"{inp}/{name}_flow_conn.dat", 502: f"{inp}/{name}_riv_data.dat", 503: f"{inp}/{name}_flow_point.dat",
             14: f"{inp}/{name}_obsq.dat", 15: f"{inp}/{name}_PET.dat", 16: f"{inp}/{name}_rain.dat"}
+
+
+# ---------------------------------------------------------------------------------------------------- the reference's own control files
+REF_EXAMPLE_IDS = [(1, 1, 1), (2, 3, 2)]          # (project, catchment setup, input setup) triples that are executed
+
+
+def stage_reference_example(work, gold):
+    """work/project.dat (the reference's text, its two absolute project_dir values pointed at work/CatchmentN/) plus, per
+    project, SETTINGS/ holding the reference's params.dat, model_structure.dat and settings.dat BYTE FOR BYTE (copies under
+    `gold` = tests/golden/ref_example) and INPUTS/ with synthetic data under exactly the names settings.dat lists (the data
+    files are not shipped upstream).  -> (dirs, raws)"""
+    import os
+    import shutil
+    from decipher_b200 import formats
+    ll, ul = synth.example_bounds(3)
+    dirs = []
+    raws = {}
+    for ic, cname in enumerate(["Catchment1", "Catchment2"]):
+        root = os.path.join(work, cname)
+        # three different HRU discretisations and three forcing sets, as settings.dat describes
+        for k in range(3):
+            raw = synth.make_raw(nac=12 + 6 * k + ic, nriv=2, npt=3, ngp=2, nge=1, nstep=120 + 24 * k, kW=3, seed=77 + 10 * ic + k)
+            raws[(ic, k)] = raw
+            tmp = os.path.join(work, f"tmp_{ic}_{k}")
+            formats.write_project(raw, tmp, ll, ul, name="X")
+            os.makedirs(os.path.join(root, "INPUTS"), exist_ok=True)
+            inp = os.path.join(tmp, "INPUTS")
+            shutil.copy(os.path.join(inp, "X_dyna_hru.dat"), os.path.join(root, "INPUTS", f"Catch1_HRU{k + 1}_dyna_hru.dat"))
+            shutil.copy(os.path.join(inp, "X_hru_meta.dat"), os.path.join(root, "INPUTS", f"Catch1_HRU{k + 1}_hru_meta.dat"))
+            if k == 0:      # the three catchment setups share one river network (settings.dat:14-16, 21-23, 28-30)
+                for n in ("flow_conn", "riv_data", "flow_point"):
+                    shutil.copy(os.path.join(inp, f"X_{n}.dat"), os.path.join(root, "INPUTS", f"Catch1_{n}.dat"))
+            tag = ["10k", "lump", "lump95"][k]
+            shutil.copy(os.path.join(inp, "X_obsq.dat"), os.path.join(root, "INPUTS", f"Catch1_{tag}_obsq.dat"))
+            shutil.copy(os.path.join(inp, "X_rain.dat"), os.path.join(root, "INPUTS", f"Catch1_{tag}_rain.dat"))
+            shutil.copy(os.path.join(inp, "X_PET.dat"), os.path.join(root, "INPUTS", f"Catch1_{tag}_PET.dat"))
+            shutil.rmtree(tmp)
+        os.makedirs(os.path.join(root, "SETTINGS"), exist_ok=True)
+        os.makedirs(os.path.join(root, "OUTPUT"), exist_ok=True)
+        for f in ("params.dat", "model_structure.dat", "settings.dat"):
+            shutil.copyfile(os.path.join(gold, f), os.path.join(root, "SETTINGS", f))          # verbatim
+        dirs.append(root + "/")
+    text = open(os.path.join(gold, "project.dat")).read()
+    assert "/data/MODEL/Catchment1/" in text and "/data/MODEL/Catchment2/" in text
+    text = text.replace("/data/MODEL/Catchment1/", dirs[0]).replace("/data/MODEL/Catchment2/", dirs[1])
+    with open(os.path.join(work, "project.dat"), "w") as f:
+        f.write(text)
+    return dirs, raws

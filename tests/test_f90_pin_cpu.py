@@ -113,16 +113,8 @@ def test_routing_of_the_executed_source():
         assert same_bits(routed[:, :, 0], v["routed"][k].T) and st[0] == 0
 
 
-@pytest.mark.parametrize("name", sorted(f90_cases.PROJECTS))
-def test_host_reader_sampler_and_oracle_reproduce_the_executed_program(name, tmp_path):
-    """`program main` of the reference executed on project FILES (its own readers: Tread_dyna, Inputs, mc_setup,
-    modelstruct_setup, read_routingdata / riv_tree_read_impl) against the drop-in chain on the same files: the C++ host
-    reader, its RANMAR / genpar and the oracle.  Every array the readers leave behind and every flow: bit for bit."""
-    from decipher_b200 import host
-    v = load(name)
-    root = str(tmp_path)
-    f90_cases.write_project(name, root)
-    p = host.Project(root)
+def _check_against_executed_program(p, v, work):
+    """p: host.Project (C++ reader + sampler); v: what `program main` of the reference produced on the same files"""
     cat = p.catchment()
     assert (cat.nac, cat.nriv, cat.nstep, cat.npt, cat.ntt) == tuple(int(v[k]) for k in ("nac", "nriv", "nstep", "npt", "ntt"))
     assert cat.dt == float(v["dt"]) and p.numsim == int(v["numsim"]) and tuple(p.seeds) == tuple(v["seeds"])
@@ -133,14 +125,53 @@ def test_host_reader_sampler_and_oracle_reproduce_the_executed_program(name, tmp
         assert np.array_equal(getattr(cat, k), v[k]), k
     assert np.array_equal(cat.node_to_flow_mapping, v["mapping"])
     assert same_bits(p.ll, v["ll"]) and same_bits(p.ul, v["ul"])
+    # `project` itself (dyna_project.f90): the output prefix and the files it connects to units 11-17 and 501-503
+    assert os.path.normpath(p.out_prefix) == os.path.normpath(os.path.join(work, str(v["out_dir_path"]).replace("<work>", work)))
     mc = p.genpar(p.numsim)
     assert same_bits(mc, v["mcpar"])
     ref = oracle_run(cat, mc.copy(order="F"))
     assert same_bits(ref["q"], v["q"]) and same_bits(ref["reach_totals"], v["totals"])
+    return cat
+
+
+@pytest.mark.parametrize("name", sorted(f90_cases.PROJECTS))
+def test_host_reader_sampler_and_oracle_reproduce_the_executed_program(name, tmp_path):
+    """`program main` of the reference executed on project FILES (its own `project`, Tread_dyna, Inputs, mc_setup,
+    modelstruct_setup, read_routingdata / riv_tree_read_impl, then ranin / genpar / mainloop) against the drop-in chain on
+    the same files: the C++ host reader, its RANMAR / genpar and the oracle.  Every array the readers leave behind and every
+    flow: bit for bit."""
+    from decipher_b200 import host
+    v = load(name)
+    root = str(tmp_path)
+    f90_cases.write_project(name, root)
+    p = host.Project(root)
+    _check_against_executed_program(p, v, root)
     p.close()
+    want = f90_cases.project_units(root)
+    got = dict(zip(v["unit_numbers"].tolist(), [str(x) for x in v["unit_files"]]))
+    assert {u: os.path.normpath(os.path.join(root, f)) for u, f in got.items() if u != 10} == {u: os.path.normpath(f) for u, f in want.items()}
     if name == "p_missing_flow":
         # (0.001/24) is a single-precision quotient (dyna_inputs.f90:94): not 0.001/24 in double
         assert v["qobs_start"][1] == float(np.float32(0.001) / np.float32(24)) * float(v["dt"]) != (0.001 / 24) * float(v["dt"])
+
+
+@pytest.mark.parametrize("ids", f90_cases.REF_EXAMPLE_IDS)
+def test_the_references_own_control_files_executed_by_its_own_source(ids, tmp_path):
+    """RRMODEL_EXAMPLE_FILES/{project,settings,params,model_structure}.dat -- the only fixtures the reference ships for this
+    path, staged verbatim (tests/golden/ref_example/) -- read by the reference's own `project` / `mc_setup` /
+    `modelstruct_setup` ... executed from source, then 10 members through `mainloop`; the C++ host on the same staging must
+    arrive at the same setup selection, bounds, seeds, sampled parameter sets and flows."""
+    from decipher_b200 import host
+    v = load("x_ref_example_%d_%d_%d" % tuple(ids))
+    work = str(tmp_path)
+    f90_cases.stage_reference_example(work, os.path.join(HERE, "golden", "ref_example"))
+    p = host.Project(work, *ids)
+    _check_against_executed_program(p, v, work)
+    assert p.numsim == 10 and tuple(p.seeds) == (5, 2000)            # params.dat:1-2 as the reference itself parsed them
+    files = [str(x) for x in v["unit_files"]]
+    assert any(f.endswith("Catch1_HRU%d_dyna_hru.dat" % ids[1]) for f in files)        # settings.dat's setup selection
+    assert any(f.endswith("Catch1_%s_obsq.dat" % ["10k", "lump", "lump95"][ids[2] - 1]) for f in files)
+    p.close()
 
 
 def _reference_present():

@@ -12,7 +12,7 @@ the 3 x 14 bounds, the model-structure table (dyna_modelstruct_setup.f90:30-111)
 """
 import filecmp
 import os
-import shutil
+import sys
 
 import numpy as np
 import pytest
@@ -20,6 +20,9 @@ import pytest
 from decipher_b200 import formats, host, synth
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+import f90_cases  # noqa: E402
+
 GOLD = os.path.join(HERE, "golden", "ref_example")
 REF = "/root/reference/RRMODEL_EXAMPLE_FILES"
 FILES = ["params.dat", "model_structure.dat", "settings.dat", "project.dat"]
@@ -42,39 +45,7 @@ def staged(tmp_path_factory):
     """work/project.dat (reference text, project_dir substituted) + Catchment1/, Catchment2/ holding the verbatim
     SETTINGS files and synthetic INPUTS under the names settings.dat lists."""
     work = str(tmp_path_factory.mktemp("refproj"))
-    ll, ul = synth.example_bounds(3)
-    dirs = []
-    raws = {}
-    for ic, cname in enumerate(["Catchment1", "Catchment2"]):
-        root = os.path.join(work, cname)
-        # three different HRU discretisations and three forcing sets, as settings.dat describes
-        for k in range(3):
-            raw = synth.make_raw(nac=12 + 6 * k + ic, nriv=2, npt=3, ngp=2, nge=1, nstep=120 + 24 * k, kW=3, seed=77 + 10 * ic + k)
-            raws[(ic, k)] = raw
-            tmp = os.path.join(work, f"tmp_{ic}_{k}")
-            formats.write_project(raw, tmp, ll, ul, name="X")
-            os.makedirs(os.path.join(root, "INPUTS"), exist_ok=True)
-            inp = os.path.join(tmp, "INPUTS")
-            shutil.copy(os.path.join(inp, "X_dyna_hru.dat"), os.path.join(root, "INPUTS", f"Catch1_HRU{k + 1}_dyna_hru.dat"))
-            shutil.copy(os.path.join(inp, "X_hru_meta.dat"), os.path.join(root, "INPUTS", f"Catch1_HRU{k + 1}_hru_meta.dat"))
-            if k == 0:      # the three catchment setups share one river network (settings.dat:14-16, 21-23, 28-30)
-                for n in ("flow_conn", "riv_data", "flow_point"):
-                    shutil.copy(os.path.join(inp, f"X_{n}.dat"), os.path.join(root, "INPUTS", f"Catch1_{n}.dat"))
-            tag = ["10k", "lump", "lump95"][k]
-            shutil.copy(os.path.join(inp, "X_obsq.dat"), os.path.join(root, "INPUTS", f"Catch1_{tag}_obsq.dat"))
-            shutil.copy(os.path.join(inp, "X_rain.dat"), os.path.join(root, "INPUTS", f"Catch1_{tag}_rain.dat"))
-            shutil.copy(os.path.join(inp, "X_PET.dat"), os.path.join(root, "INPUTS", f"Catch1_{tag}_PET.dat"))
-            shutil.rmtree(tmp)
-        os.makedirs(os.path.join(root, "SETTINGS"), exist_ok=True)
-        os.makedirs(os.path.join(root, "OUTPUT"), exist_ok=True)
-        for f in ("params.dat", "model_structure.dat", "settings.dat"):
-            shutil.copyfile(os.path.join(GOLD, f), os.path.join(root, "SETTINGS", f))          # verbatim
-        dirs.append(root + "/")
-    text = open(os.path.join(GOLD, "project.dat")).read()
-    assert "/data/MODEL/Catchment1/" in text and "/data/MODEL/Catchment2/" in text
-    text = text.replace("/data/MODEL/Catchment1/", dirs[0]).replace("/data/MODEL/Catchment2/", dirs[1])
-    with open(os.path.join(work, "project.dat"), "w") as f:
-        f.write(text)
+    dirs, raws = f90_cases.stage_reference_example(work, GOLD)
     return work, dirs, raws
 
 
