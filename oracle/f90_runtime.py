@@ -358,6 +358,8 @@ def i_real(x, kind=None):
 
 
 def i_int(x, kind=None):
+    if isinstance(x, FArr):
+        return FArr(np.trunc(x.a).astype(np.int64), x.lb)
     return int(x)
 
 
@@ -398,13 +400,20 @@ def i_allocated(x):
     return x is not None
 
 
-def i_sum(x):
+def i_sum(x, mask=None):
+    """SUM(array [, mask]): left to right in array element order"""
     flat = x.a.reshape(-1, order="F")
+    mk = None if mask is None else mask.a.reshape(-1, order="F")
     if x.isint:
-        return int(flat.sum())
+        return int(flat.sum() if mk is None else flat[mk].sum())
     s = flat.dtype.type(0)
-    for v in flat:
-        s = s + v
+    if mk is None:
+        for v in flat:
+            s = s + v
+    else:
+        for v, keep in zip(flat, mk):
+            if keep:
+                s = s + v
     return s
 
 
@@ -480,35 +489,6 @@ FArr.__hash__ = None
 
 def i_count(mask):
     return int(np.count_nonzero(mask.a))
-
-
-def _i_sum_masked(x, mask=None):
-    flat = x.a.reshape(-1, order="F")
-    if mask is None:
-        if x.isint:
-            return int(flat.sum())
-        s = flat.dtype.type(0)
-        for v in flat:
-            s = s + v
-        return s
-    mk = mask.a.reshape(-1, order="F")
-    if x.isint:
-        return int(flat[mk].sum())
-    s = flat.dtype.type(0)
-    for v, keep in zip(flat, mk):
-        if keep:
-            s = s + v
-    return s
-
-
-i_sum = _i_sum_masked
-_scalar_int = i_int
-
-
-def i_int(x, kind=None):
-    if isinstance(x, FArr):
-        return FArr(np.trunc(x.a).astype(np.int64), x.lb)
-    return _scalar_int(x)
 
 
 def f_case(sel, *vals):
