@@ -15,6 +15,7 @@ files.  It fixes the semantics the translated statements rely on:
 """
 import copy
 import math
+import os
 
 import numpy as np
 
@@ -510,6 +511,7 @@ class Unit:
 
 
 UNITS = {}
+OUTPUT_FILES = []      # (unit, name) of every file opened for writing
 
 
 class FEndOfFile(Exception):
@@ -520,10 +522,18 @@ def open_unit(unit, path):
     UNITS[int(unit)] = Unit(path)
 
 
-def f_open(where, unit, **kw):
+def f_open(where, unit, iostat=False, **kw):
+    """-> the IOSTAT value.  Output files are not produced (their WRITEs are logged instead)."""
     if kw.get("action", "").strip().lower() == "write" or kw.get("status", "").strip().lower() in ("unknown", "replace", "new"):
-        return                                          # output files are not produced
-    open_unit(unit, str(kw["file"]).strip())
+        OUTPUT_FILES.append((int(unit), str(kw.get("file", "")).strip()))
+        return 0
+    path = str(kw["file"]).strip()
+    if not os.path.isfile(path):
+        if iostat:
+            return 2
+        raise FStop(f"{where}: cannot open {path!r}")
+    open_unit(unit, path)
+    return 0
 
 
 def f_close(unit):
@@ -662,3 +672,108 @@ def f_store(dst, values, base):
         dst.a[...] = a.reshape(dst.a.shape, order="F")
         return dst
     raise FUnsupported("READ into an unallocated array")
+
+
+def f_backspace(unit):
+    u = UNITS[int(unit)]
+    u.pos = max(u.pos - 1, 0)
+
+
+# ------------------------------------------------------------------------------------------------ characters, command line
+ARGV = []          # argument 0 is the program name, as GET_COMMAND_ARGUMENT numbers them
+
+
+def f_get_command_argument(number):
+    n = int(number)
+    return ARGV[n] if 0 <= n < len(ARGV) else ""
+
+
+def f_substr(s, lo, hi):
+    lo = 1 if lo is None else int(lo)
+    hi = len(s) if hi is None else int(hi)
+    return s[lo - 1:hi].ljust(max(hi - lo + 1, 0)) if hi >= lo else ""
+
+
+def f_setsub(s, lo, hi, value):
+    lo = 1 if lo is None else int(lo)
+    hi = len(s) if hi is None else int(hi)
+    s = s.ljust(hi)
+    w = hi - lo + 1
+    return s[:lo - 1] + str(value)[:w].ljust(w) + s[hi:]
+
+
+def i_len(s):
+    return len(s)
+
+
+def i_index(s, sub):
+    return s.find(sub) + 1
+
+
+def i_iachar(c):
+    return ord(c[0]) if c else 32
+
+
+i_ichar = i_iachar
+
+
+def i_achar(k):
+    return chr(int(k))
+
+
+i_char = i_achar
+
+
+def f_fmt(where, fmt, values):
+    """internal WRITE under a format of character-literal, A / Aw, I0 / Iw / Iw.m and nX descriptors (no reversion)"""
+    body = str(fmt).strip()
+    if not (body.startswith("(") and body.endswith(")")):
+        raise FUnsupported(f"{where}: format {fmt!r}")
+    body = body[1:-1]
+    parts, cur, q = [], [], None
+    for ch in body:
+        if q:
+            cur.append(ch)
+            if ch == q:
+                q = None
+        elif ch in "'\"":
+            q = ch
+            cur.append(ch)
+        elif ch == ",":
+            parts.append("".join(cur).strip())
+            cur = []
+        else:
+            cur.append(ch)
+    parts.append("".join(cur).strip())
+    out = []
+    vals = list(values)
+    for d in parts:
+        if not d:
+            continue
+        if d[0] in "'\"":
+            out.append(d[1:-1].replace(d[0] * 2, d[0]))
+            continue
+        dl = d.lower()
+        if dl.endswith("x") and dl[:-1].isdigit():
+            out.append(" " * int(dl[:-1]))
+        elif dl == "a":
+            out.append(str(vals.pop(0)))
+        elif dl[0] == "a" and dl[1:].isdigit():
+            w = int(dl[1:])
+            v = str(vals.pop(0))
+            out.append(v[:w] if len(v) >= w else v.rjust(w))
+        elif dl[0] == "i":
+            w, _, m = dl[1:].partition(".")
+            v = int(vals.pop(0))
+            txt = str(abs(v)).rjust(int(m), "0") if m else str(abs(v))
+            if v < 0:
+                txt = "-" + txt
+            w = int(w)
+            if w and len(txt) > w:
+                txt = "*" * w
+            out.append(txt.rjust(w) if w else txt)
+        else:
+            raise FUnsupported(f"{where}: edit descriptor {d!r}")
+    if vals:
+        raise FUnsupported(f"{where}: format {fmt!r} has fewer descriptors than items")
+    return "".join(out)

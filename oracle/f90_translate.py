@@ -564,7 +564,7 @@ class Program:
                     self.generics.setdefault(cur_iface, []).extend(x.strip() for x in m.group(1).split(","))
                 continue
             if cur_proc is not None:
-                if re.match(r"^end\s*(subroutine|function)\b", s) or s == "end":
+                if re.match(r"^end\s*(subroutine|function|program)\b", s) or s == "end":
                     self.procs[cur_proc.name] = cur_proc
                     cur_proc = None
                     continue
@@ -607,7 +607,12 @@ class Program:
                 continue
             if re.match(r"^end\s*(module|program)?\b", s) and not re.match(r"^end\s*(if|do)", s):
                 continue
-            if s == "contains" or re.match(r"^(implicit|private|public|use|program)\b", s):
+            m = re.match(r"^program\s+(\w+)$", s)
+            if m:                                                  # a main program: a procedure without arguments
+                cur_proc = Proc("sub", m.group(1), [], None, module, src)
+                in_exec = False
+                continue
+            if s == "contains" or re.match(r"^(implicit|private|public|use)\b", s):
                 continue
             m = re.match(r"^interface\s*(\w+)?$", s)
             if m:
@@ -727,7 +732,7 @@ _CV = {"i": "cv_i", "r": "cv_r", "d": "cv_d", "l": "cv_l", "c": "cv_c", "t": "cv
 
 _INTRINSICS = {"exp", "log", "cos", "sin", "tan", "atan", "sqrt", "abs", "min", "max", "dble", "real", "int", "nint", "floor",
                "ceiling", "mod", "sign", "size", "allocated", "sum", "minval", "maxval", "cshift", "trim", "len_trim",
-               "adjustl", "huge", "isnan", "count"}
+               "adjustl", "huge", "isnan", "count", "len", "index", "iachar", "ichar", "achar", "char"}
 
 
 class Gen:
@@ -871,8 +876,14 @@ class Gen:
                 if kind == "gather":
                     raise NotImplementedError("subscript after array component reference")
                 if not rank:
+                    if base == "c" and len(ar) == 1 and isinstance(ar[0], tuple) and ar[0][0] == "range" and idx == len(chain) - 1:
+                        lo = self.expr(ar[0][1]) if ar[0][1] is not None else "None"
+                        hi = self.expr(ar[0][2]) if ar[0][2] is not None else "None"
+                        if lvalue:
+                            return (code, lo, hi), (base, tname, 0, "substr")
+                        return f"f_substr({code}, {lo}, {hi})", (base, tname, 0, "scalar")
                     if base == "c":
-                        raise NotImplementedError("substring")
+                        raise NotImplementedError("substring of an array element")
                     raise SyntaxError(f"subscript on scalar {nm}")
                 subs = [self.sub(a) for a in ar]
                 nsec = sum(1 for a in ar if isinstance(a, tuple) and a[0] == "range")
@@ -924,9 +935,23 @@ class Gen:
     def io(self, toks):
         """print / write: the first string literal of the list names the event, the values of the other list items are
         recorded (arrays as copies); a list outside the subset (implied DO, array constructor) is recorded without values"""
+        internal = None
         if toks[0].v == "write":
-            _, j = _group(toks, 1)
+            grp, j = _group(toks, 1)
             items = toks[j:]
+            ctl = _split_commas(grp)
+            first = ctl[0]
+            if first and first[0].k == "id" and len(ctl) > 1:
+                d = self.lookup(first[0].v)
+                if d is not None and d.base in ("c", "t"):
+                    try:
+                        code, (base, _, rank, kind) = self.ref(Parser(first).p_ref()[1], lvalue=True)
+                        if base == "c" and kind == "scalar":
+                            a = Parser(ctl[1]).p_arg()
+                            if not (isinstance(a, tuple) and a[0] in ("star", "kw", "num")):
+                                internal = (code, self.expr(a))
+                    except (SyntaxError, NotImplementedError, KeyError):
+                        internal = None
         else:
             parts = _split_commas(toks[1:])
             items = [t for part in parts[1:] for t in part + [Tok("op", ",", 0, 0)]][:-1] if len(parts) > 1 else []
@@ -943,6 +968,14 @@ class Gen:
                 vals.append(self.expr(e))
         except (SyntaxError, NotImplementedError, KeyError):
             vals = []
+        if internal is not None and (vals or not items):
+            # WRITE to a character variable: formatted for the integer / character descriptors (names of output files, headers)
+            allv = []
+            for part in _split_commas(items) if items else []:
+                if part:
+                    allv.append(self.expr(Parser(part).expr()))
+            self.emit(f"{internal[0]} = f_fmt({self.where!r}, {internal[1]}, [{', '.join(allv)}])")
+            return
         self.emit(f"f_io({self.where!r}, {txt!r}, [{', '.join(vals)}])")
 
     def read(self, toks):
@@ -1188,21 +1221,22 @@ class Gen:
             if w == "open":
                 grp, _ = _group(toks, 1)
                 pos, kws = [], []
+                ios = None
                 for part in _split_commas(grp):
                     a = Parser(part).p_arg()
                     if isinstance(a, tuple) and a[0] == "kw":
                         if a[1] in ("iostat",):
-                            code, _ = self.ref(a[2][1], lvalue=True)
-                            self.emit(f"{code} = 0")
+                            ios, _ = self.ref(a[2][1], lvalue=True)
+                            kws.append("iostat=True")
                         elif a[1] == "unit":
                             pos.append(self.expr(a[2]))
                         else:
                             kws.append(f"{a[1]}={self.expr(a[2])}")
                     else:
                         pos.append(self.expr(a))
-                self.emit(f"f_open({self.where!r}, {pos[0]}{''.join(', ' + k for k in kws)})")
+                self.emit(f"{ios + ' = ' if ios else ''}f_open({self.where!r}, {pos[0]}{''.join(', ' + k for k in kws)})")
                 return
-            if w in ("close", "rewind"):
+            if w in ("close", "rewind", "backspace"):
                 if nxt is not None and nxt.k == "op" and nxt.v == "(":
                     grp, _ = _group(toks, 1)
                     a = Parser(_split_commas(grp)[0]).p_arg()
@@ -1211,7 +1245,7 @@ class Gen:
                     u = self.expr(Parser(toks, 1).expr())
                 self.emit(f"f_{w}({u})")
                 return
-            if w in ("backspace", "inquire", "format", "flush"):
+            if w in ("inquire", "format", "flush"):
                 self.emit(f"f_unsupported({self.where!r}, {w!r})")
                 return
             raise NotImplementedError(f"statement {s!r}")
@@ -1223,7 +1257,9 @@ class Gen:
             raise SyntaxError(f"trailing tokens in {s!r}")
         code, (base, tname, rank, kind) = self.ref(lhs[1], lvalue=True)
         r = self.expr(rhs)
-        if kind == "gather":
+        if kind == "substr":
+            self.emit(f"{code[0]} = f_setsub({code[0]}, {code[1]}, {code[2]}, {r})")
+        elif kind == "gather":
             self.emit(f"f_scatter({code[0]}, {pyname(code[1])!r}, {r}, {_CV[base]})")
         elif kind == "array":
             self.emit(f"{code} = f_aassign({code}, {r})")
@@ -1263,6 +1299,10 @@ class Gen:
         args = []
         if len(toks) > 2:
             args = Parser(toks, 2).p_args()
+        if name == "get_command_argument":
+            dst, _ = self.ref(args[1][1], lvalue=True)
+            self.emit(f"{dst} = f_get_command_argument({self.expr(args[0])})")
+            return
         if name == "move_alloc":
             src, _ = self.ref(args[0][1], lvalue=True)
             dst, _ = self.ref(args[1][1], lvalue=True)

@@ -150,3 +150,47 @@ def stage_reference_example(work, gold):
     with open(os.path.join(work, "project.dat"), "w") as f:
         f.write(text)
     return dirs, raws
+
+
+# ---------------------------------------------------------------------------------------------------- standalone router program
+# DTA/route_run_standalone.f90 executed on the file set it reads (decipher_b200.formats.write_router_inputs).  Its velocity is
+# hard-wired (v_param(1) = 0.133 per timestep, :53), so the synthetic reaches are metres long to keep the delays within the series.
+ROUTER_VELOCITY = 0.133
+
+
+def router_network(sea):
+    """-> (Catchment describing the river network, inflow (n_points, nstep))"""
+    import dataclasses
+    cat = synth.synth_catchment(nac=24, nriv=4, npt=1, nstep=90, tree=True, seed=4401, reach_km=(0.002, 0.012), cell_m=0.05)
+    if sea:                       # an ungauged sea outlet as first node (DTA/route_run_standalone.f90:139-151): one input column less than nodes
+        reach_m, cell_m = 3.0, 0.05
+        down_old = np.asarray(cat.meta["down"])
+        down = np.concatenate([[0], np.where(down_old > 0, down_old + 1, 1)]).astype(np.int32)
+        _, tree = synth.full_upstream(down)
+        nc = int(round(reach_m / cell_m))
+        rd = cat.river_data.copy()
+        rd[:, 2] += reach_m
+        rd[:, 6] += reach_m
+        seac = np.zeros((nc, 8))
+        seac[:, 0] = 900.0
+        seac[:, 1] = 2500.0
+        seac[:, 6] = np.arange(nc) * cell_m
+        seac[:, 2] = seac[:, 6] + cell_m
+        seac[:, 3] = np.arange(nc) * cell_m
+        seac[:, 5] = 0.002
+        cat = dataclasses.replace(
+            cat, node_gauge_id=np.concatenate([[900], cat.node_gauge_id]).astype(np.int32),
+            node_type=np.concatenate([[1], cat.node_type]).astype(np.int32),
+            uptree_count=np.array([len(t) for t in tree], dtype=np.int32),
+            uptree_index=np.array([u for t in tree for u in t], dtype=np.int32),
+            frac_sub_area=np.concatenate([[1.0], cat.frac_sub_area]),
+            river_data=np.asfortranarray(np.round(np.vstack([seac, rd]), 3)),
+            node_to_flow_mapping=(np.arange(cat.nriv) + 2).astype(np.int32), meta=dict(down=down))
+    else:
+        cat = dataclasses.replace(cat, river_data=np.asfortranarray(np.round(cat.river_data, 3)))
+    rd = cat.river_data.copy()
+    rd[:, 1] = 20.0 + (np.arange(rd.shape[0]) % 7)         # cell areas (the 5 cm cells of this toy network round to 0 otherwise)
+    cat = dataclasses.replace(cat, river_data=np.asfortranarray(rd))
+    rng = np.random.default_rng(4402)
+    x = rng.exponential(1e-1, size=(cat.nriv, cat.nstep)) * (rng.random((cat.nriv, cat.nstep)) < 0.3)
+    return cat, np.asfortranarray(x)

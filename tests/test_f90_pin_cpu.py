@@ -174,6 +174,32 @@ def test_the_references_own_control_files_executed_by_its_own_source(ids, tmp_pa
     p.close()
 
 
+@pytest.mark.parametrize("sea", [False, True])
+def test_router_front_end_against_the_executed_router_program(sea, tmp_path):
+    """The main program DTA/route_run_standalone.f90 executed from source on the file set it reads (tree, river data, ASCII-grid
+    series; with and without an ungauged sea outlet as first node) against the C++ front end + the oracle's router: the
+    column -> node mapping, the headers of the output file, its name, and every routed value bit for bit."""
+    from decipher_b200 import formats, host
+    v = load("r_router_program_%s" % ("sea" if sea else "plain"))
+    cat, x = f90_cases.router_network(sea)
+    paths = formats.write_router_inputs(cat, x, str(tmp_path))
+    r = host.RouterInputs(paths["river_data"], paths["flow_conn"], paths["timeseries"])
+    net = r.network()
+    assert np.array_equal(net["node_to_flow_mapping"], np.arange(cat.nriv) + (2 if sea else 1))      # route_run_standalone.f90:139-151
+    assert same_bits(r.inflow, x)
+    routed, st = oracle_route_timeseries(cat, np.array([f90_cases.ROUTER_VELOCITY]), np.asfortranarray(r.inflow[:, :, None]))
+    assert st[0] == 0 and same_bits(routed[:, :, 0].T, v["routed"])
+    assert int(v["precision"]) == 6 and str(v["out_file"]) == "net_flow_routed.txt"
+    out = str(tmp_path / "routed.txt")
+    r.write_routed(routed[:, :, 0], out)
+    assert open(out).readline().rstrip("\n").split("\t") == [str(h) for h in v["headers"]]
+    if sea:
+        # the reference stores the COUNTER in flow_output_indexes (dta_route_processing.f90:141-148): column k reads node k,
+        # so the first column is the SEA node's flow under the first gauge's header -- reproduced, not corrected
+        assert int(cat.node_type[0]) == 1 and [str(h) for h in v["headers"]] == [str(g) for g in cat.node_gauge_id[1:]]
+    r.close()
+
+
 def _reference_present():
     sys.path.insert(0, os.path.join(HERE, "golden"))
     import make_f90_vectors
@@ -192,6 +218,11 @@ def test_live_translation_reproduces_the_committed_vectors():
         v = load("p_tree")
         for k in ("ac", "wtrans", "qobs_start", "frac_sub_area", "mcpar", "q", "totals"):
             assert same_bits(r[k], v[k]), k
+    from decipher_b200 import formats
+    with tempfile.TemporaryDirectory() as root:
+        cat, x = f90_cases.router_network(True)
+        r = mk.run_router_program(ns, root, formats.write_router_inputs(cat, x, root))
+        assert same_bits(r["routed"], load("r_router_program_sea")["routed"])
     for name in ("a_two_reaches", "d_init_branches"):
         v = load(name)
         cat, mc, res = mk.make_case(ns, name)

@@ -73,3 +73,23 @@ def test_cli_on_project_files_reproduces_the_executed_program(name, fast, tmp_pa
     unclipped = tab["mcpar"][:, 3, :] == v["mcpar"][:, 3, :]                                # srinit may be clipped to srmax afterwards
     assert np.array_equal(np.delete(tab["mcpar"], 3, axis=1), np.delete(v["mcpar"], 3, axis=1)) and unclipped.mean() > 0.5
     p.close()
+
+
+@pytest.mark.parametrize("sea", [False, True])
+def test_router_cli_reproduces_the_executed_router_program(sea, tmp_path):
+    """decipher_route_run (files -> C++ front end -> GPU router -> <series>_routed.txt) against the reference's main program
+    route_run_standalone executed from source on the same files (its velocity is hard-wired to 0.133)."""
+    import subprocess
+    from decipher_b200 import formats
+    exe = os.path.join(os.path.dirname(HERE), "decipher_b200", "csrc", "build", "decipher_route_run")
+    v = np.load(os.path.join(VEC, "r_router_program_%s.npz" % ("sea" if sea else "plain")), allow_pickle=False)
+    cat, x = f90_cases.router_network(sea)
+    paths = formats.write_router_inputs(cat, x, str(tmp_path))
+    r = subprocess.run([exe, "-river_data", paths["river_data"], "-tree", paths["flow_conn"], "-timeseries_in", paths["timeseries"],
+                        "-velocity", repr(f90_cases.ROUTER_VELOCITY)], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = os.path.join(str(tmp_path), str(v["out_file"]))                         # the name the reference derives (:191)
+    lines = open(out).read().splitlines()
+    assert lines[0].split("\t") == [str(h) for h in v["headers"]]
+    vals = np.array([[float(a) for a in ln.split(" ")] for ln in lines[1:]])
+    assert vals.shape == v["routed"].shape and np.abs(vals - v["routed"]).max() <= 0.5e-6 + 1e-12       # F0.6 text
