@@ -127,6 +127,11 @@ def _check_against_executed_program(p, v, work):
     assert same_bits(p.ll, v["ll"]) and same_bits(p.ul, v["ul"])
     # `project` itself (dyna_project.f90): the output prefix and the files it connects to units 11-17 and 501-503
     assert os.path.normpath(p.out_prefix) == os.path.normpath(os.path.join(work, str(v["out_dir_path"]).replace("<work>", work)))
+    # names of the per-member output files (dyna_file_open.f90: "('mc_id_',I8.8)")
+    for m in range(p.numsim):
+        for ext, key in ((".res", "res_files"), (".flow", "flow_files")):
+            want = os.path.join(work, str(v[key][m]).replace("<work>", work))
+            assert os.path.normpath(p.out_prefix + "mc_id_%08d%s" % (m + 1, ext)) == os.path.normpath(want)
     mc = p.genpar(p.numsim)
     assert same_bits(mc, v["mcpar"])
     ref = oracle_run(cat, mc.copy(order="F"))
