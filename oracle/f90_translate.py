@@ -529,6 +529,7 @@ class Program:
         self.modvars = {}        # name -> Decl (parameters and module variables)
         self.modvar_order = []
         self.warnings = []
+        self.linemap = {}        # line of the generated text -> (procedure, "file.f90:line") of the reference statement
 
     # ---------------------------------------------------------------------------------------------- parsing
     def add_source(self, text, src="<text>"):
@@ -686,7 +687,12 @@ class Program:
             try:
                 if p.broken:
                     raise NotImplementedError(p.broken)
-                out += Gen(self, p).gen_proc()
+                g = Gen(self, p)
+                lines = g.gen_proc()
+                for k, w in enumerate(g.origin):
+                    if w:
+                        self.linemap[len(out) + k + 1] = (p.name, w)
+                out += lines
             except (SyntaxError, NotImplementedError, KeyError, AssertionError) as e:
                 msg = f"{type(e).__name__}: {e}"
                 out.append(f"def f_{p.name}(*a, **k):")
@@ -719,6 +725,7 @@ class Program:
         code = self.generate(only)
         exec(compile(code, "<f90_translate>", "exec"), ns)
         ns["__source__"] = code
+        ns["__linemap__"] = dict(self.linemap)
         if extern:
             ns.update(extern)
         return ns
@@ -742,6 +749,7 @@ class Gen:
         self.prog = prog
         self.p = proc
         self.lines = []
+        self.origin = []         # per emitted line: "file.f90:line" of the statement it came from ("" for prologue lines)
         self.ind = 1
         self.where = ""
 
@@ -900,11 +908,13 @@ class Gen:
     # ---------------------------------------------------------------------------------------------- statements
     def emit(self, s):
         self.lines.append("    " * self.ind + s)
+        self.origin.append(self.where)
 
     def gen_proc(self):
         p = self.p
         args = ", ".join(f"v_{a}" for a in p.args)
         self.lines = [f"def f_{p.name}({args}):"]
+        self.origin = [""]
         self.ind = 1
         # locals
         for d in p.decls.values():
@@ -929,6 +939,7 @@ class Gen:
                 self.ind -= 1
         if stack:
             raise SyntaxError(f"{p.name}: unclosed block {stack}")
+        self.where = ""
         self.emit(self.ret)
         return self.lines
 

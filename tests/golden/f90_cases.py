@@ -39,7 +39,8 @@ CASES = {
                         sets=[[0.001, 1.0, 0.005, 0.0, 1000, 0.1, 3.0],
                               [0.03, 0.0, 0.05, 0.0, 1000, 10, 0.2],
                               [0.005, 2.0, 0.02, 0.0, 2000, 1.0, 0.2],
-                              [0.001, -2.0, 0.005, 0.0, 1000, 40, 0.2]]),
+                              [0.001, -2.0, 0.005, 0.0, 1000, 40, 0.2],
+                              [0.03, 1.2910231073712835, 0.05, 0.0, 1000, 10, 0.3]]),      # reaches tc > dtt (:90-91)
 }
 
 

@@ -235,3 +235,18 @@ def test_live_translation_reproduces_the_committed_vectors():
         for m, r in enumerate(res):
             assert same_bits(r["q"], v["q"][:, :, m]) and same_bits(r["totals"], v["totals"][:, :, m])
             assert r["sol_flag"] == int(v["sol_flag"][m])
+
+
+def test_statement_coverage_of_the_executed_source():
+    """coverage.json (make_f90_vectors.py --coverage): which statements of the reference the vectors run.  The process
+    equations must be covered completely; what is left are error exits and diagnostics."""
+    import json
+    with open(os.path.join(VEC, "coverage.json")) as f:
+        cov = json.load(f)
+    for proc in ("param_setup", "initialise_run", "init_satzone", "calculate_qb", "calculate_qbmax", "rain", "dynamic_dist",
+                 "root_zone1", "satzone_analyticalsolver", "river", "topmod", "mainloop", "write_output", "genpar", "ranin", "ranaru",
+                 "riv_node_full_upstream", "list_add_item_reserve", "read_routingdata", "read_numeric_list_fid"):
+        assert cov[proc]["statements"] > 0 and cov[proc]["not_executed"] == [], (proc, cov[proc]["not_executed"])
+    assert cov["unsat_zone1"]["not_executed"] == ["dyna_unsat_zone1.f90:85"]            # the " Storebal SUZ wrong " print
+    assert cov["results_ac"]["not_executed"] == ["dyna_results_ac.f90:31"]              # the " Problem with EX " print
+    assert cov["_total"]["executed"] >= 0.88 * cov["_total"]["statements"]
