@@ -41,6 +41,9 @@ CASES = {
                               [0.005, 2.0, 0.02, 0.0, 2000, 1.0, 0.2],
                               [0.001, -2.0, 0.005, 0.0, 1000, 40, 0.2],
                               [0.03, 1.2910231073712835, 0.05, 0.0, 1000, 10, 0.3]]),      # reaches tc > dtt (:90-91)
+    # model-structure switches other than 1 skip the zone (dyna_topmod.f90:146,161) and four sub-steps per step (ntt = 4)
+    "i_zones_off_ntt4": dict(raw=dict(nac=14, nriv=2, npt=2, ngp=2, nge=1, nstep=100, kW=4, seed=4110, ntt=4), tweak="zones_off",
+                             members=3, seeds=(5, 2000)),
 }
 
 
@@ -58,6 +61,11 @@ def build(name):
     elif tw == "huge_rain":
         cat.rain = np.asfortranarray(cat.rain.copy())
         cat.rain[0, 37] = 3.0e6
+    elif tw == "zones_off":
+        cat.ims_uz = cat.ims_uz.copy()
+        cat.ims_uz[::5] = 2
+        cat.ims_rz = cat.ims_rz.copy()
+        cat.ims_rz[3::7] = 0
     elif tw == "dry_start":
         cat.qobs_start = cat.qobs_start * 1e-11
     mc = None

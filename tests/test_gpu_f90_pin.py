@@ -12,7 +12,7 @@ sys.path.insert(0, os.path.join(HERE, "golden"))
 
 import f90_cases  # noqa: E402
 from decipher_b200.capi import (DeviceCatchment, KERNEL_RESIDENT, KERNEL_STREAMED, OPT_CHECK_BALANCE, OPT_FAST_MATH,
-                                ST_RZ_BALANCE, ST_SOLFLAG_MASK)  # noqa: E402
+                                ST_RZ_BALANCE, ST_SOLFLAG_MASK, ST_TS_OUTSUM, ST_TS_WBAL)  # noqa: E402
 from parity import compare_close, compare_flows  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -33,6 +33,7 @@ def test_cuda_reproduces_the_executed_reference(name, kernel, flags):
         st = int(out["status"][m])
         assert (st & ST_SOLFLAG_MASK) == int(v["sol_flag"][m]), (m, st)
         assert bool(st & ST_RZ_BALANCE) == ("dyna_root_zone1" in stop[m]), (m, st, stop[m])
+        assert bool(st & (ST_TS_OUTSUM | ST_TS_WBAL)) == ("dyna_results_ts" in stop[m]), (m, st, stop[m])
         if stop[m]:
             continue
         assert np.array_equal(out["mcpar"][:, :, m], v["mcpar_written"][:, :, m])
@@ -44,7 +45,7 @@ def test_cuda_reproduces_the_executed_reference(name, kernel, flags):
             # and a relative contract means nothing there -- such members are held to 1e-15 m per step absolutely
             assert np.abs(out["q"][:, :, m:m + 1] - qr).max() <= 1e-15
         else:
-            compare_flows(out["q"][:, :, m:m + 1], qr, floor=1e-2 if name.startswith(("h_", "d_")) else 1e-3)
+            compare_flows(out["q"][:, :, m:m + 1], qr, floor=1e-2 if name.startswith(("h_", "d_", "i_")) else 1e-3)
         compare_close(out["reach_totals"][:, :, m], v["totals"][:, :, m], what="reach totals")
 
 
