@@ -3,7 +3,8 @@
 ! NOT COMPILED IN THIS REPOSITORY'S CI: the build image has no Fortran compiler (gfortran, flang,
 ! nvfortran and ifort are all absent), so this module is shipped as source, written 1:1 against the C
 ! header.  Every derived-type component below has the same order, kind and meaning as the field of
-! the same name in `dcp_catchment_desc` / `dcp_run_opts`.
+! the same name in `dcp_catchment_desc` / `dcp_run_opts` / `dcp_run_stats` / `dcp_multi_stats`; tests/test_shim_consistency_cpu.py
+! checks that mechanically against include/decipher_b200.h, together with the argument lists of the interfaces.
 !
 ! Use: add this file and shim/dyna_main_gpu.f90 to RRMODEL's makefile sources, drop dyna_main.f90,
 ! link with -ldecipher_b200 -lcudart.  All the reference's setup routines (project, Tread_dyna,
@@ -18,6 +19,9 @@ module decipher_c_api
                                      DCP_ST_TS_WBAL = 16, DCP_ST_NONFINITE = 32, DCP_ST_INIT_ITERCAP = 64, &
                                      DCP_ST_HIST_DROPPED = 128
     integer(c_int), parameter :: DCP_NMEASURE = 5   ! NSE, log-NSE, KGE, PBIAS, RMSE
+    integer(c_int32_t), parameter :: DCP_PERF_NSE = 0, DCP_PERF_LOGNSE = 1, DCP_PERF_KGE = 2, DCP_PERF_PBIAS = 3, DCP_PERF_RMSE = 4
+    integer(c_int32_t), parameter :: DCP_OPT_SIGNATURES = 8
+    integer(c_int), parameter :: DCP_NSIG = 4, DCP_ABI_VERSION = 4
 
     type, bind(C) :: dcp_catchment_desc
         integer(c_int32_t) :: struct_size, nac, nriv, npt, nstep, ngp, nge, ntt
@@ -40,6 +44,23 @@ module decipher_c_api
         type(c_ptr) :: sig_out          ! DCP_OPT_SIGNATURES: (DCP_NSIG, nriv, n_member) flow-duration signatures, else c_null_ptr
     end type
 
+    integer(c_int), parameter :: DCP_MAX_RANKS = 16
+
+    ! timing of the last dcp_run_ensemble call on a handle (CUDA events, milliseconds)
+    type, bind(C) :: dcp_run_stats
+        real(c_double) :: ms_total, ms_init, ms_physics, ms_route, ms_h2d, ms_d2h
+        integer(c_int64_t) :: n_physics_launches, n_launches
+        integer(c_int32_t) :: kernel_used, hist_len
+    end type
+
+    ! what dcp_run_ensemble_multi reports about a run over several GPUs
+    type, bind(C) :: dcp_multi_stats
+        integer(c_int32_t) :: n_ranks, used_nccl, kernel_used, reserved
+        real(c_double) :: ms_wall, ms_gather, ms_busy_max, ms_busy_sum
+        real(c_double) :: ms_rank_device(DCP_MAX_RANKS)
+        real(c_double) :: ms_rank_wall(DCP_MAX_RANKS)
+    end type
+
     interface
         integer(c_int) function dcp_device_count() bind(C, name="dcp_device_count")
             import :: c_int
@@ -47,6 +68,10 @@ module decipher_c_api
         integer(c_int) function dcp_set_device(device) bind(C, name="dcp_set_device")
             import :: c_int
             integer(c_int), value :: device
+        end function
+        ! compare with DCP_ABI_VERSION before the first call
+        integer(c_int) function dcp_abi_version() bind(C, name="dcp_abi_version")
+            import :: c_int
         end function
         type(c_ptr) function dcp_last_error() bind(C, name="dcp_last_error")
             import :: c_ptr
@@ -81,6 +106,26 @@ module decipher_c_api
             type(c_ptr), value :: velocity, inflow, routed, status
             integer(c_int32_t), value :: flags
         end function
+        integer(c_int) function dcp_get_run_stats(handle, stats) bind(C, name="dcp_get_run_stats")
+            import :: c_int, c_ptr, dcp_run_stats
+            type(c_ptr), value :: handle
+            type(dcp_run_stats), intent(out) :: stats
+        end function
+        ! GLUE-style behavioural filter: perf(DCP_NMEASURE,nriv,n_member) -> index_out(n_member) (0-based members, ascending),
+        ! weight_out(n_member) or c_null_ptr, n_selected; gauge is 0-based, -1 = every gauge
+        integer(c_int) function dcp_select_behavioural(perf, n_member, nriv, measure, gauge, threshold, higher_is_better, &
+                                                       index_out, weight_out, n_selected, flags) &
+                                                       bind(C, name="dcp_select_behavioural")
+            import :: c_int, c_int32_t, c_int64_t, c_double, c_ptr
+            type(c_ptr), value :: perf
+            integer(c_int64_t), value :: n_member
+            integer(c_int32_t), value :: nriv, measure, gauge
+            real(c_double), value :: threshold
+            integer(c_int32_t), value :: higher_is_better
+            type(c_ptr), value :: index_out, weight_out
+            integer(c_int64_t), intent(out) :: n_selected
+            integer(c_int32_t), value :: flags
+        end function
         ! ---- every GPU of the box: the MC loop of dyna_main.f90:166-206 over all ranks of a communicator ----
         ! devices(n_ranks): CUDA device of each rank, or c_null_ptr for rank r -> device r
         integer(c_int) function dcp_comm_init(n_ranks, devices, comm) bind(C, name="dcp_comm_init")
@@ -93,7 +138,15 @@ module decipher_c_api
             import :: c_int, c_ptr
             type(c_ptr), value :: comm
         end function
-        ! arguments as dcp_run_ensemble, over ALL members; stats: c_null_ptr or a dcp_multi_stats (see the C header)
+        integer(c_int) function dcp_comm_size(comm) bind(C, name="dcp_comm_size")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: comm
+        end function
+        integer(c_int) function dcp_comm_uses_nccl(comm) bind(C, name="dcp_comm_uses_nccl")
+            import :: c_int, c_ptr
+            type(c_ptr), value :: comm
+        end function
+        ! arguments as dcp_run_ensemble, over ALL members; stats: c_null_ptr or c_loc of a type(dcp_multi_stats)
         integer(c_int) function dcp_run_ensemble_multi(comm, desc, n_member, mcpar, opts, q_out, perf_out, reach_totals, &
                                                        init_diag, status, stats) bind(C, name="dcp_run_ensemble_multi")
             import :: c_int, c_int64_t, c_ptr, dcp_catchment_desc, dcp_run_opts
