@@ -777,3 +777,23 @@ def f_fmt(where, fmt, values):
     if vals:
         raise FUnsupported(f"{where}: format {fmt!r} has fewer descriptors than items")
     return "".join(out)
+
+
+def i_iand(a, b):
+    return int(a) & int(b)
+
+
+def i_ior(a, b):
+    return int(a) | int(b)
+
+
+def i_ieor(a, b):
+    return int(a) ^ int(b)
+
+
+def i_ishft(a, n):
+    return int(a) << int(n) if n >= 0 else int(a) >> -int(n)
+
+
+def i_btest(a, pos):
+    return bool((int(a) >> int(pos)) & 1)

@@ -515,6 +515,7 @@ class Proc:
         self.copy_out = []       # positions of dummies returned to the caller
         self.uses = []
         self.broken = None
+        self.host = None         # the program / procedure an internal procedure is contained in
         self.formats = {}        # statement label -> format text
 
 
@@ -529,6 +530,13 @@ class Program:
         self.modvars = {}        # name -> Decl (parameters and module variables)
         self.modvar_order = []
         self.warnings = []
+        self.externals = set()   # procedures declared in interface bodies (defined elsewhere, e.g. bind(C))
+        for name, val in (("c_int", 4), ("c_int32_t", 4), ("c_int64_t", 8), ("c_double", 8), ("c_size_t", 8), ("c_null_ptr", 0)):
+            d = Decl(name, "i", param=True, init=("num", "i", str(val)))      # the named constants of iso_c_binding
+            d.modvar = True
+            self.modvars[name] = d
+            self.modvar_order.append(name)
+        self.types["c_ptr"] = TypeDef("c_ptr")
         self.linemap = {}        # line of the generated text -> (procedure, "file.f90:line") of the reference statement
 
     # ---------------------------------------------------------------------------------------------- parsing
@@ -539,6 +547,7 @@ class Program:
         cur_proc = None
         cur_iface = None
         in_exec = False
+        host = None
         for ln, s in lines:
             label = None
             m = re.match(r"^(\d+)\s+(.*)$", s)
@@ -563,10 +572,18 @@ class Program:
                 m = re.match(r"^module\s+procedure\s+(.*)$", s)
                 if m and cur_iface:
                     self.generics.setdefault(cur_iface, []).extend(x.strip() for x in m.group(1).split(","))
+                m = re.match(r"^(?:[\w()]+\s+)?(function|subroutine)\s+(\w+)", s)
+                if m and not s.startswith("end"):
+                    self.externals.add(m.group(2))
                 continue
             if cur_proc is not None:
                 if re.match(r"^end\s*(subroutine|function|program)\b", s) or s == "end":
                     self.procs[cur_proc.name] = cur_proc
+                    cur_proc = None
+                    continue
+                if s == "contains":                                # internal procedures follow: they see the host's entities
+                    self.procs[cur_proc.name] = cur_proc
+                    host = cur_proc
                     cur_proc = None
                     continue
                 if label is not None and re.match(r"^format\s*\(", s):
@@ -585,7 +602,7 @@ class Program:
                         except (SyntaxError, KeyError):
                             cur_proc.broken = f"parameter statement outside the subset: {s[:60]}"
                         continue
-                    m = re.match(r"^use\s+(\w+)", s)
+                    m = re.match(r"^use\b[\s,]*(?:(?:non_)?intrinsic\s*::\s*)?(\w+)", s)
                     if m:
                         cur_proc.uses.append(m.group(1))
                         continue
@@ -607,6 +624,7 @@ class Program:
                 module = m.group(1)
                 continue
             if re.match(r"^end\s*(module|program)?\b", s) and not re.match(r"^end\s*(if|do)", s):
+                host = None
                 continue
             m = re.match(r"^program\s+(\w+)$", s)
             if m:                                                  # a main program: a procedure without arguments
@@ -619,7 +637,7 @@ class Program:
             if m:
                 cur_iface = m.group(1) or ""
                 continue
-            m = re.match(r"^type\s*(?:,\s*\w+\s*)*(?:::)?\s*(\w+)$", s)
+            m = re.match(r"^type\s*(?:,\s*[\w()]+\s*)*(?:::)?\s*(\w+)$", s)
             if m and not s.startswith("type("):
                 cur_type = TypeDef(m.group(1))
                 self.types[cur_type.name] = cur_type
@@ -628,12 +646,14 @@ class Program:
             if m:
                 args = [a.strip() for a in (m.group(2) or "").split(",") if a.strip()]
                 cur_proc = Proc("sub", m.group(1), args, None, module, src)
+                cur_proc.host = host
                 in_exec = False
                 continue
             m = re.match(r"^(?:recursive\s+)?(?:[\w\s()*=]+?\s+)?function\s+(\w+)\s*\((.*?)\)\s*(?:result\s*\(\s*(\w+)\s*\))?$", s)
             if m:
                 args = [a.strip() for a in m.group(2).split(",") if a.strip()]
                 cur_proc = Proc("fun", m.group(1), args, m.group(3) or m.group(1), module, src)
+                cur_proc.host = host
                 in_exec = False
                 continue
             try:
@@ -739,7 +759,8 @@ _CV = {"i": "cv_i", "r": "cv_r", "d": "cv_d", "l": "cv_l", "c": "cv_c", "t": "cv
 
 _INTRINSICS = {"exp", "log", "cos", "sin", "tan", "atan", "sqrt", "abs", "min", "max", "dble", "real", "int", "nint", "floor",
                "ceiling", "mod", "sign", "size", "allocated", "sum", "minval", "maxval", "cshift", "trim", "len_trim",
-               "adjustl", "huge", "isnan", "count", "len", "index", "iachar", "ichar", "achar", "char"}
+               "adjustl", "huge", "isnan", "count", "len", "index", "iachar", "ichar", "achar", "char",
+               "c_loc", "c_associated", "c_sizeof", "command_argument_count", "iand", "ior", "ieor", "ishft", "btest"}
 
 
 class Gen:
@@ -757,6 +778,9 @@ class Gen:
     def lookup(self, name):
         if self.p is not None and name in self.p.decls:
             return self.p.decls[name]
+        if self.p is not None and self.p.host is not None and name in self.p.host.decls:
+            raise NotImplementedError(f"host association of {name}")      # parsed, not executed
+
         if name in self.prog.modvars:
             return self.prog.modvars[name]
         return None
@@ -854,6 +878,8 @@ class Gen:
                 rd = f.decls.get(f.result)
                 return (f"f_{name}({', '.join(self.expr(a) for a in args)})",
                         (rd.base if rd else "d", rd.tname if rd else None, rd.rank if rd else 0, "call"))
+            if name in self.prog.externals:
+                return (f"f_{name}({', '.join(self.expr(a) for a in args)})", (None, None, 0, "call"))
             if name in _INTRINSICS:
                 pa = []
                 for a in args:

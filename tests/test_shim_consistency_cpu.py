@@ -102,3 +102,41 @@ def test_interfaces_name_exported_symbols_with_matching_arguments():
         assert kinds == protos[name], (name, kinds, protos[name])
         if lib is not None:
             assert hasattr(lib, name), f"{name} is not exported by the library"
+
+
+import pytest  # noqa: E402
+import sys  # noqa: E402
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(HERE, "golden"))
+
+
+def _ref_present():
+    import make_f90_vectors
+    return make_f90_vectors.reference_available()
+
+
+@pytest.mark.skipif(not _ref_present(), reason="reference sources are not on this machine")
+def test_shim_main_program_is_consistent_with_the_reference_modules():
+    """shim/dyna_main_gpu.f90 (dyna_main.f90 with the Monte-Carlo loop replaced) run through the Fortran-subset translator
+    together with the reference's modules and the interface module: every name it uses is declared or provided by a module,
+    blocks balance, every call of a reference procedure (project, Tread_dyna, Inputs, mc_setup, genpar, file_open ...) passes
+    as many arguments as the reference's definition takes.  Not a compiler, but the errors a first compile would throw."""
+    import f90_translate as ft
+    import make_f90_vectors as mk
+    prog = ft.Program()
+    for f in mk.FILES:
+        prog.add_file(os.path.join(mk.REFERENCE, f))
+    prog.add_file(os.path.join(ROOT, "shim", "decipher_c_api.f90"))
+    n_before = set(prog.procs)
+    prog.add_file(os.path.join(ROOT, "shim", "dyna_main_gpu.f90"))
+    prog.finish()
+    mine = [p for name, p in prog.procs.items() if name not in n_before]
+    assert mine and any(p.name == "main" for p in mine)
+    for p in mine:
+        assert not p.broken, (p.name, p.broken)
+        try:
+            ft.Gen(prog, p).gen_proc()
+        except NotImplementedError as e:
+            assert "host association" in str(e), (p.name, e)          # internal procedures reading the program's variables
+    assert {"dcp_run_ensemble", "dcp_catchment_create"} <= prog.externals
