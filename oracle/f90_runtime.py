@@ -797,3 +797,19 @@ def i_ishft(a, n):
 
 def i_btest(a, pos):
     return bool((int(a) >> int(pos)) & 1)
+
+
+# ------------------------------------------------------------------------------------------------ iso_c_binding
+C_SIZEOF = {}      # class name of a bind(C) derived type -> sizeof of the C struct (filled by the driver from ctypes)
+
+
+def i_c_loc(x):
+    return x       # the "address" of an array is the array object itself: the callee sees the same storage
+
+
+def i_c_sizeof(x):
+    return C_SIZEOF[type(x).__name__]
+
+
+def i_c_associated(x):
+    return x is not None and not (isinstance(x, int) and x == 0)

@@ -455,7 +455,7 @@ def parse_declaration(toks):
             inner, i = _group(toks, i)
             if base == "t":
                 tname = inner[0].v
-            elif base == "r" and any(t.k == "num" and t.v[0] == "8" for t in inner):
+            elif base == "r" and any((t.k == "num" and t.v[0] == "8") or (t.k == "id" and t.v in ("c_double", "dp", "real64")) for t in inner):
                 base = "d"
         elif i < len(toks) and toks[i].k == "op" and toks[i].v == "*":        # real*8, character*20
             if base == "r" and toks[i + 1].k == "num" and toks[i + 1].v[0] == "8":
@@ -1307,6 +1307,8 @@ class Gen:
                 self.emit(f"{code} = cv_t({r})")
             else:
                 self.emit(f"{code} = {r}")
+        elif base == "t" and tname == "c_ptr":
+            self.emit(f"{code} = {r}")                               # a C address: the reference to the object, not a copy
         else:
             self.emit(f"{code} = {_CV[base]}({r})")
 

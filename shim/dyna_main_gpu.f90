@@ -1,7 +1,8 @@
 ! dyna_main_gpu.f90 -- `program main` of RRMODEL/dyna_main.f90 with the serial Monte-Carlo loop
 ! (dyna_main.f90:166-206) replaced by ONE call into libdecipher_b200.so.
 !
-! NOT COMPILED HERE (no Fortran compiler in the build image); shipped as the reference-side binding a
+! NOT COMPILED HERE (no Fortran compiler in the build image), but EXECUTED by tests/test_shim_consistency_cpu.py through the
+! Fortran-subset translator (oracle/f90_translate.py) with the reference modules; shipped as the reference-side binding a
 ! maintainer would add.  Everything above the loop is the reference's own code, unchanged; the part
 ! below flattens the derived types into the C descriptor, samples all parameter sets with the
 ! reference's genpar (same RANMAR stream, so the sets are bit-identical to the serial program's),

@@ -140,3 +140,26 @@ def test_shim_main_program_is_consistent_with_the_reference_modules():
         except NotImplementedError as e:
             assert "host association" in str(e), (p.name, e)          # internal procedures reading the program's variables
     assert {"dcp_run_ensemble", "dcp_catchment_create"} <= prog.externals
+
+
+@pytest.mark.skipif(not _ref_present(), reason="reference sources are not on this machine")
+@pytest.mark.parametrize("name", ["p_tree", "p_missing_flow"])
+def test_shim_main_program_executed_against_the_c_abi_call_sequence(name, tmp_path):
+    """shim/dyna_main_gpu.f90 EXECUTED (translator + the reference's own modules) on a project directory.  Its three calls into
+    the library are bound to stand-ins that rebuild the catchment from the bind(C) descriptor the Fortran code filled in and
+    hand it to the oracle, so what is tested is the Fortran side of the boundary: the flattening of dyna_hru / route_riv, index
+    and array-order conventions, one create + one run for the whole ensemble, mcpar in/out, and the per-member writer.  The
+    flows and totals it writes must equal what the UNMODIFIED reference program writes on the same files (p_*.npz)."""
+    import numpy as np
+    sys.path.insert(0, HERE)
+    import f90_cases
+    import shim_exec
+    from oracle_binding import oracle_run
+    ns = shim_exec.load()
+    root = str(tmp_path)
+    f90_cases.write_project(name, root)
+    r = shim_exec.run_main(ns, root, lambda cat, mc: oracle_run(cat, mc))
+    v = np.load(os.path.join(HERE, "golden", "f90_exec", name + ".npz"), allow_pickle=False)
+    assert r["n_create"] == 1 and r["n_run"] == 1                          # ONE call replaces the Monte-Carlo loop
+    assert r["q"].tobytes() == v["q"].tobytes() and r["totals"].tobytes() == v["totals"].tobytes()
+    assert r["flow_files"] == [str(f) for f in v["flow_files"]]
