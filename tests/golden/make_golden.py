@@ -1,9 +1,10 @@
-"""Generates tests/golden/*.npz: outputs of the CPU oracle on small seeded cases.
+"""Generates tests/golden/c1_small.npz and tree_ntt2.npz: outputs of the CPU oracle on two seeded cases with observed flow,
+i.e. including the performance measures (NSE, log-NSE, KGE, PBIAS, RMSE), which do not exist upstream.
 
-Provenance: the reference ships no fixtures and cannot be compiled in this environment (no Fortran
-compiler), so these vectors come from oracle/decipher_oracle.cpp (-O2, strict FP), cross-checked by the
-independent NumPy restatement (tests/test_oracle_crosscheck.py).  They pin the oracle against
-regressions and give the GPU tests a committed target.  Run: python tests/golden/make_golden.py"""
+These two files are ORACLE-made regression targets.  The link to the reference itself is tests/golden/f90_exec/ (written by
+make_f90_vectors.py from the reference's own source, executed): the oracle reproduces those bit for bit
+(tests/test_f90_pin_cpu.py), so what these goldens add is the objective functions and a committed target for the GPU tests at
+a somewhat larger size.  Run: python tests/golden/make_golden.py"""
 import os
 import sys
 
