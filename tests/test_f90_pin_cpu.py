@@ -136,6 +136,7 @@ def _check_against_executed_program(p, v, work):
     assert same_bits(mc, v["mcpar"])
     ref = oracle_run(cat, mc.copy(order="F"))
     assert same_bits(ref["q"], v["q"]) and same_bits(ref["reach_totals"], v["totals"])
+    assert same_bits(ref["q"], v["q_program"])           # ... as written by the reference's unmodified `program main` (dyna_main.f90)
     return cat
 
 
@@ -219,7 +220,7 @@ def test_live_translation_reproduces_the_committed_vectors():
     import tempfile
     with tempfile.TemporaryDirectory() as root:
         f90_cases.write_project("p_tree", root)
-        r = mk.run_project(ns, "p_tree", root)
+        r = mk.run_project(ns, "p_tree", root)            # includes a run of the unmodified main program (run_main_program)
         v = load("p_tree")
         for k in ("ac", "wtrans", "qobs_start", "frac_sub_area", "mcpar", "q", "totals"):
             assert same_bits(r[k], v[k]), k
