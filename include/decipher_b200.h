@@ -57,7 +57,7 @@ extern "C" {
 #define DCP_ST_INIT_ITERCAP   0x40      /* init search hit DCP_INIT_MAX_ITER (guard, not in reference)*/
 #define DCP_ST_HIST_DROPPED   0x80      /* hist_add_value dropped a cell (dta_route_processing.f90:378-382) */
 
-#define DCP_INIT_MAX_ITER     2000000   /* cap on the while loop of dyna_init_satzone.f90:134-174     */
+#define DCP_INIT_MAX_ITER     100000000 /* cap on the while loop of dyna_init_satzone.f90:134-174     */
 
 /* ---- run option flags -------------------------------------------------------------------- */
 #define DCP_OPT_CHECK_BALANCE   0x1     /* evaluate the results_ts / root_zone1 STOP conditions: they are statements

@@ -23,8 +23,8 @@
 //   * `sumeout` (RRMODEL/dyna_results_ts.f90:28,68) and `tot_reach_ppt`
 //     (RRMODEL/dyna_write_output.f90:55-57,63) are used uninitialised upstream; both start at 0 here.
 //   * STOP conditions become per-member status bits; the member keeps running.
-//   * the init search loop is capped at DCP_INIT_MAX_ITER = 2e6 iterations (hang guard; the executed
-//     reference needs up to ~3e4 on the test catchments).
+//   * the init search loop is capped at DCP_INIT_MAX_ITER = 1e8 iterations (hang guard; the executed
+//     reference needs up to 2.7e6 on the test catchments).
 //   * NSE / log-NSE do not exist upstream; they are defined in objective() below.
 
 #include "../include/decipher_b200.h"

@@ -100,7 +100,7 @@ def run_member(cat, mcpar):
     it = 0
     while abs(qb_diff) > F32(0.01):
         it += 1
-        if it > 2000000:
+        if it > 100000000:
             break
         sd, qbf, qb_tmp = calc_qb(D)
         prev, qb_diff = qb_diff, (qb_tmp - mean_q) * 1000

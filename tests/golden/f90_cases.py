@@ -47,6 +47,33 @@ CASES = {
 }
 
 
+def _fuzz_cases(n_cases=6, n_members=12, seed=777):
+    """randomised catchments (size, reaches, parameter layers, sub-steps, daily / hourly steps, tree / chain networks) and
+    parameter sets drawn uniformly from the bounds of the reference's params.dat, with srinit beyond srmax and a tiny smax
+    mixed in; a run of 240 such members (40 per catchment) gave no mismatch, 72 of them are committed"""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for c in range(n_cases):
+        kw = dict(nac=int(rng.integers(4, 12)), nriv=int(rng.integers(1, 4)), npt=int(rng.integers(1, 4)), ngp=2, nge=1,
+                  nstep=int(rng.integers(30, 80)), kW=int(rng.integers(2, 5)), seed=5000 + c, tree=bool(c % 2),
+                  ntt=int(rng.choice([1, 1, 2, 3])), dt=float(rng.choice([1.0, 1.0, 24.0])))
+        kw["nriv"] = min(kw["nriv"], kw["nac"])
+        ll, ul = synth.example_bounds(kw["npt"])
+        sets = []
+        for m in range(n_members):
+            mc = ll + rng.random((kw["npt"], 7)) * (ul - ll)
+            if m % 5 == 0:
+                mc[:, 3] = rng.uniform(0, 0.3, kw["npt"])
+            if m % 7 == 0:
+                mc[:, 6] = rng.uniform(0.01, 0.2, kw["npt"])
+            sets.append(mc.reshape(-1).tolist())
+        out[f"z_fuzz_{c}"] = dict(raw=kw, sets=sets)
+    return out
+
+
+CASES.update(_fuzz_cases())
+
+
 def build(name):
     """-> (Catchment, explicit parameter table (npt, 7, M) or None)"""
     c = CASES[name]
